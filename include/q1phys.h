@@ -1,0 +1,200 @@
+/*
+ * q1phys.h -- C ABI of the B200-native q1physrl_env movement step (libq1phys.so).
+ *
+ * The reference (matthewearl/q1physrl) has no FFI layer: its boundary for this path is a set of
+ * Python classes.  Each entry point below replaces one of those methods; the Python mirror in
+ * q1physrl_b200/ (and the stub a reference maintainer would add) binds them
+ * with ctypes.  Citations: env = q1physrl_env/q1physrl_env/env.py, phys = .../phys.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative Q1_E* code; q1_last_error() gives the text
+ *     (thread-local).  Nothing throws across the ABI.
+ *   - buffers are caller-owned.  Unless the name ends in _host every pointer is a DEVICE pointer on
+ *     the handle's GPU; `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *     stream).  The library owns only the persistent per-env state.
+ *   - a handle is bound to one device and is not thread-safe; use one handle per GPU.
+ *   - there is no CPU implementation behind this ABI: q1_create fails when no CUDA device exists.
+ */
+#ifndef Q1PHYS_H
+#define Q1PHYS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q1_ABI_VERSION 1
+
+enum {
+    Q1_OK = 0,
+    Q1_EINVAL = -1,   /* bad argument / unsupported configuration */
+    Q1_ECUDA = -2,    /* a CUDA runtime call failed */
+    Q1_ENODEV = -3,   /* no usable CUDA device */
+    Q1_ENOMEM = -4
+};
+
+/* q1_create flags */
+enum {
+    Q1_F_TRACK_RETURNS = 1u << 0,   /* keep a per-env f64 episode return + on-device episode metrics */
+    Q1_F_FORCE_F64_STAMPS = 1u << 1 /* keep env:200 key time stamps in f64 even when u8 tick counters are exact */
+};
+
+/* Built-in device-side policies of q1_rollout. */
+enum {
+    Q1_POLICY_RANDOM = 0,      /* uniform keys, uniform mouse in the action range */
+    Q1_POLICY_STRAFE_JUMP = 1  /* scripted: forward + alternating strafe/turn, jump taps */
+};
+
+/* POD mirror of env.Config (env:132-148). */
+typedef struct q1_config {
+    int64_t num_envs;
+    double zero_start_prob;
+    double initial_yaw_lo;      /* initial_yaw_range[0] */
+    double initial_yaw_hi;      /* initial_yaw_range[1] */
+    double max_initial_speed;
+    double time_delta;
+    double time_limit;
+    double action_range;
+    double fmove_max;
+    double smove_max;
+    double key_press_delay;
+    int32_t allow_yaw;
+    int32_t discrete_yaw_steps; /* -1 = continuous mouse action */
+    int32_t speed_reward;
+    int32_t hover;
+    int32_t smooth_keys;
+    int32_t auto_jump;
+    int32_t allow_jump;
+    int32_t reserved;
+} q1_config;
+
+typedef struct q1_env q1_env; /* opaque */
+
+typedef struct q1_env_info {
+    int64_t num_envs;
+    int32_t num_keys;           /* env:206-207 */
+    int32_t device;
+    int32_t f64_stamps;         /* 1: f64 key time stamps, 0: u8 tick counters */
+    int32_t track_returns;
+    int32_t key_delay_ticks;    /* ceil(key_press_delay / time_delta) in counter mode */
+    int32_t state_bytes_per_env;
+    uint64_t env_index_base;
+    uint64_t seed;
+    uint64_t ticks;             /* q1_step / q1_rollout ticks executed so far */
+} q1_env_info;
+
+/* Host-side view of the full per-env state in the reference's own layout and widths
+ * (phys:156-161, env:200-202, 375-379).  Any pointer may be NULL to skip that field. */
+typedef struct q1_state_view {
+    float   *vel;             /* (n,3) */
+    double  *z_pos;           /* (n,)  */
+    double  *yaw;             /* (n,)  */
+    double  *time_remaining;  /* (n,)  */
+    uint8_t *on_ground;       /* (n,)  */
+    uint8_t *jump_released;   /* (n,)  */
+    uint8_t *zero_start;      /* (n,)  */
+    uint8_t *last_keys;       /* (n,num_keys) */
+    double  *last_press;      /* (n,num_keys) */
+    double  *episode_return;  /* (n,)  only with Q1_F_TRACK_RETURNS */
+} q1_state_view;
+
+/* On-device episode statistics (q1physrl/train.py:54-57 `zero_start_total_reward`, and the
+ * episode_reward_mean / max RLLib tracks, train.py:67-71). */
+typedef struct q1_metrics {
+    double  zero_start_return_sum;
+    int64_t zero_start_episodes;
+    double  return_sum;
+    int64_t episodes;
+    double  return_max;
+} q1_metrics;
+
+const char *q1_last_error(void);
+int q1_abi_version(void);
+int q1_device_count(int *count);
+
+/* env:206-207 -- number of key actions for this config (3 or 4). */
+int q1_num_keys(const q1_config *cfg);
+
+/* env.VectorPhysEnv.__init__ (env:410-426) minus the implicit vector_reset.  `env_index_base` is
+ * the global index of this shard's env 0: reset draws are a pure function of
+ * (seed, global env index, reset epoch), so a sharded run equals the single-GPU run. */
+int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_index_base,
+              uint32_t flags, q1_env **out);
+int q1_destroy(q1_env *env);
+int q1_info(const q1_env *env, q1_env_info *out);
+int q1_sync(q1_env *env, void *stream);
+
+/* env.VectorPhysEnv.vector_reset (env:428-455).  obs (n,6) f32, may be NULL. */
+int q1_reset_all(q1_env *env, float *obs, void *stream);
+/* Batched env.VectorPhysEnv.reset_at (env:457-480): resets envs with mask[i] != 0 and overwrites
+ * their obs rows; other rows are left untouched.  obs may be NULL. */
+int q1_reset_masked(q1_env *env, const uint8_t *mask, float *obs, void *stream);
+/* env.VectorPhysEnv.reset_at(index) (env:457-480).  obs6_host: 6 floats in HOST memory. */
+int q1_reset_at_host(q1_env *env, int64_t index, float *obs6_host);
+
+/* env.VectorPhysEnv.vector_step (env:482-510), one lockstep tick for all envs.
+ *   keys        (n,num_keys) u8, bit 0 of each byte is the key action (env:228)
+ *   mouse       (n,) f32 for a continuous mouse action, (n,) i32 for discrete_yaw_steps != -1,
+ *               ignored (may be NULL) when allow_yaw is 0
+ *   obs         (n,6) f32    reward (n,) f32    done (n,) u8    zero_start (n,) u8 or NULL
+ *   auto_reset  0: reference behaviour, the caller resets finished envs;
+ *               1: envs whose episode ended are re-initialised in the same launch and their obs
+ *                  row holds the first observation of the new episode. */
+int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, float *obs, float *reward,
+            uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream);
+/* Same call with HOST buffers: stages through pinned memory, copies in, steps, copies out and
+ * synchronises.  This is what PhysEnv.step / VectorPhysEnv.vector_step bind for NumPy callers. */
+int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, float *obs, float *reward,
+                 uint8_t *done, uint8_t *zero_start, int auto_reset);
+
+/* `ticks` consecutive vector_step calls in one launch with a built-in policy generating the actions
+ * on the device (state stays in registers; finished envs auto-reset).  reward_sum (n,) f32 receives
+ * the per-env sum of rewards over the call, obs (n,6) the final observation; either may be NULL. */
+int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *obs,
+               float *reward_sum, void *stream);
+
+/* Observation of the current state without stepping (env:392-400). */
+int q1_observe(q1_env *env, float *obs, void *stream);
+
+/* Full state copy-out / copy-in through HOST arrays in the reference layout. */
+int q1_get_state_host(q1_env *env, const q1_state_view *view);
+int q1_set_state_host(q1_env *env, const q1_state_view *view);
+
+/* Episode statistics accumulated on the device since creation or the last clear (HOST struct).
+ * Requires Q1_F_TRACK_RETURNS. */
+int q1_get_metrics_host(q1_env *env, int clear, q1_metrics *out);
+
+/* phys.apply (phys:184-197) on explicit arrays: a pure function, no handle.  All (n,) except
+ * vel (n,3); pitch / roll may be NULL (= 0).  Output arrays must not alias the inputs. */
+int q1_phys_apply(int device, int64_t n,
+                  const double *yaw, const double *pitch, const double *roll,
+                  const double *fmove, const double *smove, const uint8_t *button2,
+                  const double *time_delta,
+                  const double *z_pos, const float *vel, const uint8_t *on_ground,
+                  const uint8_t *jump_released,
+                  double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
+                  uint8_t *jump_released_out, void *stream);
+/* Same with HOST arrays. */
+int q1_phys_apply_host(int device, int64_t n,
+                       const double *yaw, const double *pitch, const double *roll,
+                       const double *fmove, const double *smove, const uint8_t *button2,
+                       const double *time_delta,
+                       const double *z_pos, const float *vel, const uint8_t *on_ground,
+                       const uint8_t *jump_released,
+                       double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
+                       uint8_t *jump_released_out);
+
+/* env.ActionDecoder.map (env:225-269) on explicit decoder state, HOST arrays: last_keys
+ * (n,num_keys) u8, last_press (n,num_keys) f64 and yaw (n,) f64 are updated in place; mouse is f64
+ * here (the standalone decoder is driven by arbitrary callers, mkdemo.py:47-50). */
+int q1_decode_host(const q1_config *cfg, int device, int64_t n,
+                   uint8_t *last_keys, double *last_press, double *yaw,
+                   const uint8_t *keys, const double *mouse,
+                   const float *z_vel, const double *time_remaining,
+                   int64_t *smove, int64_t *fmove, uint8_t *jump);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Q1PHYS_H */

@@ -1,0 +1,76 @@
+"""Import the UNMODIFIED reference (`/root/reference/q1physrl_env`) in the build container.
+
+TEST INFRASTRUCTURE ONLY.  Used by `tests/golden/make_golden.py` (fixture generation) and by the
+`not gpu` tests that pin the oracle against the real reference when the checkout is mounted.  The
+reference cannot travel to the GPU box, so nothing on the `-m gpu` / smoke / bench path imports
+this module.
+
+Two shims are needed; both live here, never in the reference tree:
+  * a stub `gym` package (`gym.Env`, `gym.spaces.{Box,Discrete,Tuple}`, `gym.envs.registration`),
+    because gym is not installed;
+  * `numpy.int = int`, removed from NumPy 1.24 but used at env.py:228,269.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("Q1_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "q1physrl_env", "q1physrl_env", "env.py"))
+
+
+def _install_gym_stub():
+    if "gym" in sys.modules:
+        return
+    gym = types.ModuleType("gym")
+    spaces = types.ModuleType("gym.spaces")
+    envs = types.ModuleType("gym.envs")
+    registration = types.ModuleType("gym.envs.registration")
+
+    class Env:
+        pass
+
+    class Box:
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+    class Discrete:
+        def __init__(self, n):
+            self.n = n
+
+    class Tuple:
+        def __init__(self, spaces):
+            self.spaces = tuple(spaces)
+
+    registry = {}
+
+    def register(id, **kwargs):
+        registry[id] = kwargs
+
+    gym.Env = Env
+    spaces.Box, spaces.Discrete, spaces.Tuple = Box, Discrete, Tuple
+    registration.register = register
+    registration.registry = registry
+    envs.registration = registration
+    gym.spaces, gym.envs = spaces, envs
+    sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.envs": envs,
+                        "gym.envs.registration": registration})
+
+
+def load():
+    """Return `(env_module, phys_module)` of the unmodified reference."""
+    if not available():
+        raise RuntimeError(f"reference checkout not found under {REFERENCE_ROOT}")
+    _install_gym_stub()
+    if not hasattr(np, "int"):
+        np.int = int
+    path = os.path.join(REFERENCE_ROOT, "q1physrl_env")
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import q1physrl_env.env as ref_env
+    import q1physrl_env.phys as ref_phys
+    return ref_env, ref_phys
