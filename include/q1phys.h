@@ -40,6 +40,13 @@ enum {
     Q1_F_FORCE_F64_STAMPS = 1u << 1 /* keep env:200 key time stamps in f64 even when u8 tick counters are exact */
 };
 
+/* Element type of the `mouse` array handed to q1_step / q1_step_host. */
+enum {
+    Q1_MOUSE_F32 = 0,  /* the action space's own dtype (env:214-215); exact for discrete indices too */
+    Q1_MOUSE_I32 = 1,  /* discrete_yaw_steps index */
+    Q1_MOUSE_F64 = 2   /* the f64 column ActionDecoder._fix_actions produces (env:221-223) */
+};
+
 /* Built-in device-side policies of q1_rollout. */
 enum {
     Q1_POLICY_RANDOM = 0,      /* uniform keys, uniform mouse in the action range */
@@ -130,23 +137,33 @@ int q1_reset_all(q1_env *env, float *obs, void *stream);
 /* Batched env.VectorPhysEnv.reset_at (env:457-480): resets envs with mask[i] != 0 and overwrites
  * their obs rows; other rows are left untouched.  obs may be NULL. */
 int q1_reset_masked(q1_env *env, const uint8_t *mask, float *obs, void *stream);
+/* The two calls above with HOST buffers (mask (n,) u8, obs (n,6) f32; obs may be NULL). */
+int q1_reset_all_host(q1_env *env, float *obs_host);
+int q1_reset_masked_host(q1_env *env, const uint8_t *mask_host, float *obs_host);
 /* env.VectorPhysEnv.reset_at(index) (env:457-480).  obs6_host: 6 floats in HOST memory. */
 int q1_reset_at_host(q1_env *env, int64_t index, float *obs6_host);
 
 /* env.VectorPhysEnv.vector_step (env:482-510), one lockstep tick for all envs.
  *   keys        (n,num_keys) u8, bit 0 of each byte is the key action (env:228)
- *   mouse       (n,) f32 for a continuous mouse action, (n,) i32 for discrete_yaw_steps != -1,
- *               ignored (may be NULL) when allow_yaw is 0
+ *   mouse       (n,) raw mouse action (continuous value, or the index for discrete_yaw_steps
+ *               != -1) of element type mouse_kind (Q1_MOUSE_*); ignored (may be NULL) when
+ *               allow_yaw is 0
  *   obs         (n,6) f32    reward (n,) f32    done (n,) u8    zero_start (n,) u8 or NULL
  *   auto_reset  0: reference behaviour, the caller resets finished envs;
  *               1: envs whose episode ended are re-initialised in the same launch and their obs
  *                  row holds the first observation of the new episode. */
-int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, float *obs, float *reward,
-            uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream);
-/* Same call with HOST buffers: stages through pinned memory, copies in, steps, copies out and
- * synchronises.  This is what PhysEnv.step / VectorPhysEnv.vector_step bind for NumPy callers. */
-int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, float *obs, float *reward,
-                 uint8_t *done, uint8_t *zero_start, int auto_reset);
+int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
+            float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream);
+/* Same call with HOST buffers: copies the actions in, steps, copies the results out and
+ * synchronises.  This is what PhysEnv.step / VectorPhysEnv.vector_step bind for NumPy callers.
+ * Buffers from q1_host_alloc (or any page-locked memory) are transferred by DMA directly; pageable
+ * memory works too, at the driver's staging speed. */
+int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
+                 float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset);
+
+/* Page-locked host memory for the *_host entry points. */
+int q1_host_alloc(uint64_t bytes, void **out);
+int q1_host_free(void *ptr);
 
 /* `ticks` consecutive vector_step calls in one launch with a built-in policy generating the actions
  * on the device (state stays in registers; finished envs auto-reset).  reward_sum (n,) f32 receives
@@ -156,6 +173,7 @@ int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *
 
 /* Observation of the current state without stepping (env:392-400). */
 int q1_observe(q1_env *env, float *obs, void *stream);
+int q1_observe_host(q1_env *env, float *obs_host);
 
 /* Full state copy-out / copy-in through HOST arrays in the reference layout. */
 int q1_get_state_host(q1_env *env, const q1_state_view *view);

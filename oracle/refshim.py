@@ -68,9 +68,15 @@ def load():
     _install_gym_stub()
     if not hasattr(np, "int"):
         np.int = int
-    path = os.path.join(REFERENCE_ROOT, "q1physrl_env")
-    if path not in sys.path:
-        sys.path.insert(0, path)
-    import q1physrl_env.env as ref_env
-    import q1physrl_env.phys as ref_phys
+    # The reference package has no __init__.py (a namespace package), so the repo's own
+    # `q1physrl_env` alias package would shadow it on sys.path: import the reference's two files
+    # under a private package name bound to its directory instead.
+    import importlib
+    name = "_q1physrl_reference"
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "q1physrl_env", "q1physrl_env")]
+        sys.modules[name] = pkg
+    ref_phys = importlib.import_module(name + ".phys")
+    ref_env = importlib.import_module(name + ".env")
     return ref_env, ref_phys

@@ -1,0 +1,57 @@
+"""Build `libq1phys.so` (the sm_100a kernels + the C ABI of include/q1phys.h) in-tree with nvcc.
+
+nvcc cross-compiles without a GPU, so this runs on the CPU-only build container as well; the
+resulting `.so` is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libq1phys.so")
+SOURCES = [os.path.join(_HERE, "csrc", "q1phys.cu")]
+DEPENDS = SOURCES + [os.path.join(_HERE, "csrc", "q1_tick.cuh"),
+                     os.path.join(REPO_ROOT, "include", "q1phys.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    # the reference never fuses a multiply with an add (NumPy rounds after every ufunc); the kernels
+    # also use the explicit *_rn intrinsics, this is the belt to those braces.
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > built for p in DEPENDS)
+
+
+def build(force=False, verbose=False):
+    """Compile the library if it is missing or older than its sources; return its path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = find_nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libq1phys.so")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True, cwd=_HERE)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

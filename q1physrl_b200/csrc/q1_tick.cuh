@@ -1,0 +1,395 @@
+/*
+ * q1_tick.cuh -- device code of one q1physrl_env movement tick for ONE env held in registers.
+ *
+ * Everything here is written for sm_100a and mirrors the widths the reference executes under
+ * NumPy 2: f32 velocity, f64 z / yaw / time_remaining, f64 intermediates
+ * with a single rounding to f32 at the store, f32 friction speed.  All f64/f32 arithmetic goes
+ * through the *_rn intrinsics so that no multiply-add is ever contracted into an FMA, whatever the
+ * compiler flags are (the reference never fuses: einsum and ufuncs round after every operation).
+ *
+ * Citations: phys = q1physrl_env/q1physrl_env/phys.py, env = q1physrl_env/q1physrl_env/env.py.
+ */
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace q1 {
+
+/* ------------------------------------------------------------------ constants ---------------- */
+
+/* phys:47-53 (np.float32 scalars, all exactly representable). */
+constexpr float kMaxSpeed = 320.0f;
+constexpr float kStopSpeed = 100.0f;
+constexpr float kFriction = 4.0f;
+constexpr float kJumpSpeed = 270.0f;
+constexpr float kFloorHeight = 24.03125f;
+/* env:54-58 */
+constexpr float kInitialZ = 32.843201f;
+constexpr float kInitialVz = -12.0f;
+constexpr float kInitialYawZero = 90.0f;
+
+constexpr double kPi = 3.14159265358979323846; /* np.pi */
+
+/* flags byte of the persistent state */
+enum : uint32_t {
+    F_ON_GROUND = 1u,
+    F_JUMP_RELEASED = 2u,
+    F_ZERO_START = 4u,
+    F_LAST_KEY0 = 8u, /* bits 3..6 = last_keys[0..3] (env:201) */
+    F_LAST_KEY_SHIFT = 3u,
+    F_DONE_SEEN = 128u /* episode already reported to the metrics (time_remaining crossed 0) */
+};
+
+enum : int { KEY_LEFT = 0, KEY_RIGHT = 1, KEY_FORWARD = 2, KEY_JUMP = 3 }; /* env:61-73 */
+
+/* Per-config constants.  Passed to every kernel as a __grid_constant__ parameter: they live in
+ * the constant bank and reach the FP64 pipe as uniform operands (no shared-memory round trip). */
+struct Params {
+    int64_t n;
+    uint64_t env_index_base;
+    uint64_t seed;
+    /* env.Config numbers in the width they are used */
+    double dt;              /* time_delta */
+    double time_limit;
+    double key_delay;       /* key_press_delay */
+    double max_yaw_delta;   /* f64(f32(720) * f32(dt))           env:230 */
+    double action_range;    /* env:236 */
+    double yaw_steps;       /* f64(discrete_yaw_steps)           env:238 */
+    double accel_dt;        /* f64(f32(10)) * dt                 phys:78 */
+    double gravity_dt;      /* f64(f32(800)) * dt                phys:122 */
+    double fmove_half, fmove_full; /* trunc(f64(f32(fmove_max)) * {0.5, 1})   env:261,269 */
+    double smove_half, smove_full; /* trunc(f64(f32(smove_max)) * {0.5, 1})   env:260,269 */
+    double zero_start_prob, yaw_lo, yaw_hi, max_initial_speed;
+    float dt_f32;           /* f32(time_delta) for the reward      env:500-503 */
+    int32_t num_keys;       /* env:206-207 */
+    int32_t delay_ticks;    /* ceil(key_delay / dt) (counter mode) */
+    int32_t allow_yaw, discrete_yaw, speed_reward, hover, smooth_keys, auto_jump, allow_jump;
+    /* persistent state, struct of arrays */
+    float *vx, *vy, *vz;
+    double *z, *yaw, *trem;
+    uint32_t *timers;       /* counter mode: 4 x u8 "ticks until the key may be pressed again" */
+    double *stamps;         /* stamp mode: (num_keys, n) f64 last key press time (env:200) */
+    uint8_t *flags;
+    uint32_t *epoch;        /* reset count per env: RNG stream position, touched by resets only */
+    double *ep_return;      /* TRACK only: running f64 episode return */
+    double *metrics;        /* TRACK only: [zs_sum, zs_count, sum, count, max-as-ordered-bits] */
+};
+
+/* One env in registers. */
+struct Env {
+    float vx, vy, vz;
+    double z, yaw, trem;
+    uint32_t timers;
+    uint32_t flags;
+    double stamp[4];
+};
+
+/* ------------------------------------------------------------------ rounding-exact helpers --- */
+
+__device__ __forceinline__ double mul64(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add64(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub64(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div64(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float mul32(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add32(float a, float b) { return __fadd_rn(a, b); }
+
+/* ------------------------------------------------------------------ Philox4x32-10 ------------ */
+
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* 53-bit uniform in [0,1) from two words: the 27+26 bit construction of NumPy's random_sample. */
+__device__ __forceinline__ double unit53(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+/* ------------------------------------------------------------------ observation -------------- */
+
+/* env:381-400 with get_obs_scale (env:294-296), result cast to f32 (the dtype the env declares,
+ * env:416-417).  The reference divides in f64; time and yaw do exactly that.  For the three
+ * velocity entries and z the numerator is a small dyadic rational (multiple of 16, of 1/8) exactly
+ * representable in f32 and the divisor is 200 or 100, so the quotient is either exact or has a
+ * binary expansion of period <= 20: it can never sit within 2^-53 of an f32 rounding boundary, and
+ * rounding the exact quotient once to f32 equals rounding the f64 quotient to f32. */
+__device__ __forceinline__ float obs_vel(float v)
+{
+    float q = truncf(mul32(v, 0.0625f)); /* (v / 16).astype(int): exact scaling, toward zero */
+    if (fabsf(q) < 1048576.0f)
+        return __fdiv_rn(mul32(q, 16.0f), 200.0f);
+    return __double2float_rn(div64(mul64((double)(long long)q, 16.0), 200.0));
+}
+
+__device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6])
+{
+    o[0] = __double2float_rn(div64(e.trem, P.time_limit));
+    o[1] = __double2float_rn(div64(e.yaw, 90.0));
+    double r = rint(mul64(e.z, 8.0)); /* np.round: half to even (env:390) */
+    if (fabs(r) < 16777216.0)
+        o[2] = __fdiv_rn(mul32((float)r, 0.125f), 100.0f);
+    else
+        o[2] = __double2float_rn(div64(mul64(r, 0.125), 100.0));
+    o[3] = obs_vel(e.vx);
+    o[4] = obs_vel(e.vy);
+    o[5] = obs_vel(e.vz);
+}
+
+/* ------------------------------------------------------------------ phys.apply, one row ------ */
+
+/* phys:184-197 for one env.  (fx, rx, fy, ry) is the 2x2 block of _angle_vectors (phys:56-66). */
+__device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, double &z,
+                                          bool &on_ground, bool &jump_released,
+                                          double fx, double rx, double fy, double ry,
+                                          double fmove, double smove, bool jump, double dt,
+                                          double accel_dt, double gravity_dt)
+{
+    const bool was_on_ground = on_ground; /* phys:191 hands _air_move the OLD flag */
+
+    /* phys:95-103.  einsum = mul, mul, add; norm = sqrt(x*x + y*y). */
+    double wx = add64(mul64(fx, fmove), mul64(rx, smove));
+    double wy = add64(mul64(fy, fmove), mul64(ry, smove));
+    double ws = __dsqrt_rn(add64(mul64(wx, wx), mul64(wy, wy)));
+    double wdx = wx, wdy = wy;
+    if (ws > 0.0) {
+        wdx = div64(wx, ws);
+        wdy = div64(wy, ws);
+    }
+    double wish_speed = ws < (double)kMaxSpeed ? ws : (double)kMaxSpeed;
+    if (ws != ws)
+        wish_speed = ws;
+    /* phys:104-106 rescales wish_vel, which nothing reads afterwards. */
+
+    /* phys:108, phys:83-90 */
+    double hx = (double)vx, hy = (double)vy;
+    if (was_on_ground) {
+        float speed = __fsqrt_rn(add32(mul32(vx, vx), mul32(vy, vy)));
+        float control = speed > kStopSpeed ? speed : kStopSpeed;
+        double new_speed = sub64((double)speed, mul64(mul64(dt, (double)control), (double)kFriction));
+        if (!(new_speed > 0.0))
+            new_speed = 0.0;
+        if (speed > 0.0f) {
+            double ratio = div64(new_speed, (double)speed);
+            hx = mul64(hx, ratio);
+            hy = mul64(hy, ratio);
+        }
+    }
+
+    /* phys:69-80 */
+    double current = add64(mul64(hx, wdx), mul64(hy, wdy));
+    double clipped = (wish_speed > 30.0 && !was_on_ground) ? 30.0 : wish_speed;
+    double add = sub64(clipped, current);
+    if (!(add > 0.0))
+        add = 0.0;
+    double accel = mul64(accel_dt, wish_speed);
+    if (add < accel)
+        accel = add;
+    hx = add64(hx, mul64(accel, wdx));
+    hy = add64(hy, mul64(accel, wdy));
+
+    /* phys:190: the single f64 -> f32 rounding */
+    vx = __double2float_rn(hx);
+    vy = __double2float_rn(hy);
+
+    /* phys:112-132 */
+    jump_released = jump_released | !jump;
+    bool do_jump = was_on_ground && jump && jump_released;
+    float v = add32(vz, do_jump ? kJumpSpeed : 0.0f);
+    v = __double2float_rn(sub64((double)v, gravity_dt));
+    double zn = add64(z, mul64(dt, (double)v));
+    bool og = zn < (double)kFloorHeight;
+    z = og ? (double)kFloorHeight : zn;
+    vz = og ? 0.0f : v;
+    on_ground = og;
+}
+
+/* ------------------------------------------------------------------ env tick ----------------- */
+
+/* env.VectorPhysEnv.vector_step (env:482-510) for one env: hover override, ActionDecoder.map
+ * (env:225-269), phys.apply, reward, time, done.  keybits: bit k = key action k; mouse: the raw
+ * mouse action as f64 (continuous value or the discrete index). */
+template <bool STAMPS>
+__device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, double mouse,
+                                     float &reward, bool &done)
+{
+    if (P.hover) { /* env:483-485 */
+        e.vz = 0.0f;
+        e.z = 100.0;
+    }
+
+    /* ---- ActionDecoder.map ---- */
+    double mouse_x = 0.0;
+    if (P.allow_yaw) {
+        if (!P.discrete_yaw)
+            mouse_x = div64(mul64(mouse, P.max_yaw_delta), P.action_range);               /* env:236 */
+        else
+            mouse_x = div64(mul64(sub64(mouse, P.yaw_steps), P.max_yaw_delta), P.yaw_steps); /* env:238 */
+    }
+
+    const double now = sub64(P.time_limit, e.trem); /* env:241, 246 */
+    uint32_t last = (e.flags >> F_LAST_KEY_SHIFT) & 0xFu;
+    uint32_t down = 0;
+    uint32_t timers = e.timers;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < P.num_keys) {
+            bool elapsed;
+            if (STAMPS) {
+                elapsed = now >= add64(e.stamp[k], P.key_delay);                         /* env:241-242 */
+            } else {
+                /* ticks-until-allowed counter: one tick has passed since the last test */
+                uint32_t r = (timers >> (8 * k)) & 0xFFu;
+                r = r ? r - 1u : 0u;
+                timers = (timers & ~(0xFFu << (8 * k))) | (r << (8 * k));
+                elapsed = r == 0u;
+            }
+            uint32_t lk = (last >> k) & 1u;
+            uint32_t d = ((keybits >> k) & 1u) & ((elapsed ? 1u : 0u) | lk);            /* env:243 */
+            if (d & ~lk & 1u) {                                                         /* env:244-248 */
+                if (STAMPS)
+                    e.stamp[k] = now;
+                else
+                    timers = (timers & ~(0xFFu << (8 * k))) | ((uint32_t)P.delay_ticks << (8 * k));
+            }
+            down |= d << k;
+        }
+    }
+    e.timers = timers;
+
+    /* env:251-261: smoothed keys in {0, 1/2, 1}; fmove/smove are truncations of f32(max) * that,
+     * i.e. one of five values fixed by the config. */
+    int f2, s2; /* twice the smoothed forward key, twice (right - left) */
+    {
+        int dl = (down >> KEY_LEFT) & 1, dr = (down >> KEY_RIGHT) & 1, df = (down >> KEY_FORWARD) & 1;
+        if (P.smooth_keys) {
+            int ll = (last >> KEY_LEFT) & 1, lr = (last >> KEY_RIGHT) & 1, lf = (last >> KEY_FORWARD) & 1;
+            f2 = df + lf;
+            s2 = (dr + lr) - (dl + ll);
+        } else {
+            f2 = 2 * df;
+            s2 = 2 * (dr - dl);
+        }
+    }
+    double fmove = f2 == 2 ? P.fmove_full : (f2 == 1 ? P.fmove_half : 0.0);
+    int as2 = s2 < 0 ? -s2 : s2;
+    double smove = as2 == 2 ? P.smove_full : (as2 == 1 ? P.smove_half : 0.0);
+    if (s2 < 0)
+        smove = -smove;
+
+    bool jump;
+    if (P.auto_jump)
+        jump = e.vz <= 16.0f;                                                           /* env:263 */
+    else if (P.allow_jump)
+        jump = (down >> KEY_JUMP) & 1u;                                                 /* env:265 */
+    else
+        jump = false;                                                                   /* env:267 */
+
+    e.yaw = add64(e.yaw, mouse_x);                                                       /* env:258 */
+    e.flags = (e.flags & ~(0xFu << F_LAST_KEY_SHIFT)) | (down << F_LAST_KEY_SHIFT);     /* env:256 */
+
+    /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
+    double sy, cy;
+    sincos(div64(mul64(e.yaw, kPi), 180.0), &sy, &cy);                                    /* phys:58-59 */
+    bool og = e.flags & F_ON_GROUND, jr = e.flags & F_JUMP_RELEASED;
+    move_body(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt, P.accel_dt,
+              P.gravity_dt);
+    e.flags = (e.flags & ~(F_ON_GROUND | F_JUMP_RELEASED)) | (og ? F_ON_GROUND : 0u) |
+              (jr ? F_JUMP_RELEASED : 0u);
+
+    /* ---- reward, time, done (env:500-506) ---- */
+    if (P.speed_reward)
+        reward = mul32(P.dt_f32, __fsqrt_rn(add32(mul32(e.vx, e.vx), mul32(e.vy, e.vy))));
+    else
+        reward = mul32(P.dt_f32, e.vy);
+    e.trem = sub64(e.trem, P.dt);
+    done = e.trem < 0.0;
+}
+
+/* ------------------------------------------------------------------ reset -------------------- */
+
+/* env.VectorPhysEnv.reset_at (env:457-480) + ActionDecoder.reset_at (env:283-291) for one env,
+ * with the global np.random draws replaced by a counter-based stream: five uniforms that are a pure
+ * function of (seed, global env index, reset epoch).  np.random.uniform(x) is uniform(low=x,
+ * high=1.0) = x + (1 - x) * u, which this keeps. */
+template <bool STAMPS>
+__device__ __forceinline__ void reset_env(const Params &P, Env &e, uint64_t gidx, uint32_t epoch)
+{
+    uint32_t w[12];
+#pragma unroll
+    for (uint32_t j = 0; j < 3; j++)
+        philox4x32((uint32_t)gidx, (uint32_t)(gidx >> 32), epoch, 0x52455300u + j,
+                   (uint32_t)P.seed, (uint32_t)(P.seed >> 32), w + 4 * j);
+    double u0 = unit53(w[0], w[1]), u1 = unit53(w[2], w[3]), u2 = unit53(w[4], w[5]);
+    double u3 = unit53(w[6], w[7]), u4 = unit53(w[8], w[9]);
+
+    bool zs = u0 < P.zero_start_prob;
+    e.z = (double)kInitialZ;
+    e.vz = kInitialVz;
+    e.yaw = zs ? (double)kInitialYawZero : add64(P.yaw_lo, mul64(sub64(P.yaw_hi, P.yaw_lo), u1));
+    e.trem = zs ? P.time_limit : add64(P.time_limit, mul64(sub64(1.0, P.time_limit), u2));
+    double speed = zs ? 0.0 : add64(P.max_initial_speed, mul64(sub64(1.0, P.max_initial_speed), u3));
+    const double two_pi = 2.0 * kPi;
+    double angle = add64(two_pi, mul64(sub64(1.0, two_pi), u4));
+    if (P.hover) {
+        speed = 320.0;
+        angle = kPi / 2;
+    }
+    double sa, ca;
+    sincos(angle, &sa, &ca);
+    e.vx = __double2float_rn(mul64(speed, ca));
+    e.vy = __double2float_rn(mul64(speed, sa));
+    e.flags = F_JUMP_RELEASED | (zs ? F_ZERO_START : 0u);
+    e.timers = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        e.stamp[k] = -P.key_delay;
+}
+
+/* ------------------------------------------------------------------ built-in policies -------- */
+
+/* Synthetic action streams of q1_rollout, pure functions of (policy seed, global env, tick). */
+__device__ __forceinline__ void policy_action(const Params &P, int policy, uint64_t pseed,
+                                              uint64_t gidx, uint32_t tick_no, uint32_t &keybits,
+                                              double &mouse)
+{
+    if (policy == 0) {
+        uint32_t w[4];
+        philox4x32((uint32_t)gidx, (uint32_t)(gidx >> 32), tick_no, 0x41435400u, (uint32_t)pseed,
+                   (uint32_t)(pseed >> 32), w);
+        keybits = w[0] & ((1u << P.num_keys) - 1u);
+        if (!P.discrete_yaw) {
+            double unit = mul64((double)w[1], 1.0 / 4294967296.0);
+            mouse = (double)__double2float_rn(
+                add64(-P.action_range, mul64(mul64(2.0, P.action_range), unit)));
+        } else {
+            mouse = (double)(w[1] % (uint32_t)(2 * (int)P.yaw_steps + 1));
+        }
+    } else {
+        uint32_t phase = ((tick_no + (uint32_t)(gidx % 72u)) / 36u) & 1u;
+        keybits = (phase == 0 ? 1u << KEY_LEFT : 1u << KEY_RIGHT) | (1u << KEY_FORWARD);
+        if (P.num_keys == 4)
+            keybits |= (tick_no & 1u) << KEY_JUMP;
+        double turn = phase == 0 ? 1.5 : -1.5;
+        if (!P.discrete_yaw) {
+            mouse = (double)__double2float_rn(div64(mul64(turn, P.action_range), P.max_yaw_delta));
+        } else {
+            int steps = (int)P.yaw_steps;
+            mouse = (double)(steps + (phase == 0 ? 1 : -1) * ((steps + 3) / 4));
+        }
+    }
+}
+
+} // namespace q1

@@ -1,0 +1,1235 @@
+/*
+ * q1phys.cu -- sm_100a kernels and the C ABI (include/q1phys.h) of the q1physrl_env movement step.
+ *
+ * Data layout in HBM (struct of arrays, one element per env, every array 256-byte aligned inside
+ * one pool allocation):
+ *   vx, vy, vz f32 | z, yaw, time_remaining f64 | key timers 4 x u8 in a u32 (or (nk, n) f64 stamps)
+ *   | flags u8 | reset epoch u32 (touched by resets only) | episode return f64 (TRACK only)
+ * = 41 B per env in counter mode, read once and written once per tick.
+ *
+ * Citations: phys = q1physrl_env/q1physrl_env/phys.py, env = q1physrl_env/q1physrl_env/env.py.
+ */
+#include "../../include/q1phys.h"
+#include "q1_tick.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace q1;
+
+/* ====================================================================== device side ========= */
+
+namespace {
+
+constexpr int kBlock = 256;
+
+template <bool STAMPS>
+__device__ __forceinline__ void load_env(const Params &P, int64_t i, Env &e)
+{
+    e.vx = P.vx[i];
+    e.vy = P.vy[i];
+    e.vz = P.vz[i];
+    e.z = P.z[i];
+    e.yaw = P.yaw[i];
+    e.trem = P.trem[i];
+    e.flags = P.flags[i];
+    if (STAMPS) {
+        e.timers = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            e.stamp[k] = k < P.num_keys ? P.stamps[(int64_t)k * P.n + i] : 0.0;
+    } else {
+        e.timers = P.timers[i];
+    }
+}
+
+template <bool STAMPS>
+__device__ __forceinline__ void store_env(const Params &P, int64_t i, const Env &e)
+{
+    P.vx[i] = e.vx;
+    P.vy[i] = e.vy;
+    P.vz[i] = e.vz;
+    P.z[i] = e.z;
+    P.yaw[i] = e.yaw;
+    P.trem[i] = e.trem;
+    P.flags[i] = (uint8_t)e.flags;
+    if (STAMPS) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < P.num_keys)
+                P.stamps[(int64_t)k * P.n + i] = e.stamp[k];
+    } else {
+        P.timers[i] = e.timers;
+    }
+}
+
+__device__ __forceinline__ void store_obs(float *obs, int64_t i, const float o[6])
+{
+    float *row = obs + 6 * i;
+    if ((reinterpret_cast<uintptr_t>(obs) & 7u) == 0) {
+        float2 *r2 = reinterpret_cast<float2 *>(row);
+        r2[0] = make_float2(o[0], o[1]);
+        r2[1] = make_float2(o[2], o[3]);
+        r2[2] = make_float2(o[4], o[5]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            row[k] = o[k];
+    }
+}
+
+/* (n, nk) u8 key actions -> bit mask; bit 0 of each byte is the action (env:228 astype(int), and
+ * last_keys in {0,1} means `&` only ever sees bit 0). */
+__device__ __forceinline__ uint32_t load_keys(const uint8_t *keys, int64_t i, int nk)
+{
+    if (nk == 4 && (reinterpret_cast<uintptr_t>(keys) & 3u) == 0) {
+        uint32_t w = reinterpret_cast<const uint32_t *>(keys)[i];
+        return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
+    }
+    uint32_t m = 0;
+    for (int k = 0; k < nk; k++)
+        m |= (uint32_t)(keys[i * nk + k] & 1u) << k;
+    return m;
+}
+
+__device__ __forceinline__ double load_mouse(const void *mouse, int kind, int64_t i)
+{
+    if (kind == Q1_MOUSE_F32)
+        return (double)reinterpret_cast<const float *>(mouse)[i];
+    if (kind == Q1_MOUSE_I32)
+        return (double)reinterpret_cast<const int32_t *>(mouse)[i];
+    return reinterpret_cast<const double *>(mouse)[i];
+}
+
+/* -- episode metrics (q1physrl/train.py:54-57, 67-71) ------------------------------------------ */
+
+__device__ __forceinline__ unsigned long long ordered_bits(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+/* Called by full warps.  `finished`: this lane's episode ended this tick with return `ret`. */
+__device__ __forceinline__ void report_episodes(const Params &P, bool finished, bool zs, double ret)
+{
+    unsigned any = __ballot_sync(0xffffffffu, finished);
+    if (!any)
+        return;
+    double s = finished ? ret : 0.0, zsum = (finished && zs) ? ret : 0.0;
+    double mx = finished ? ret : -INFINITY;
+    int cnt = __popc(any), zcnt = __popc(__ballot_sync(0xffffffffu, finished && zs));
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        zsum += __shfl_xor_sync(0xffffffffu, zsum, off);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (zcnt) {
+            atomicAdd(&P.metrics[0], zsum);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&P.metrics[1]), (unsigned long long)zcnt);
+        }
+        atomicAdd(&P.metrics[2], s);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&P.metrics[3]), (unsigned long long)cnt);
+        atomicMax(reinterpret_cast<unsigned long long *>(&P.metrics[4]), ordered_bits(mx));
+    }
+}
+
+/* -- env.VectorPhysEnv.vector_step (env:482-510): one lockstep tick ---------------------------- */
+
+template <bool STAMPS, bool TRACK>
+__global__ void __launch_bounds__(kBlock)
+k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
+       const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
+       float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ zero_start,
+       int auto_reset)
+{
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = i < P.n;
+    bool finished = false, zs = false;
+    double ret = 0.0;
+    if (active) {
+        Env e;
+        load_env<STAMPS>(P, i, e);
+        uint32_t keybits = load_keys(keys, i, P.num_keys);
+        double m = 0.0;
+        if (P.allow_yaw)
+            m = load_mouse(mouse, mouse_kind, i);
+        float r;
+        bool d;
+        tick<STAMPS>(P, e, keybits, m, r, d);
+        zs = e.flags & F_ZERO_START;
+        if (TRACK) {
+            ret = add64(P.ep_return[i], (double)r);
+            finished = d && !(e.flags & F_DONE_SEEN);
+            if (finished)
+                e.flags |= F_DONE_SEEN;
+        }
+        reward[i] = r;
+        done[i] = d ? 1 : 0;
+        if (zero_start)
+            zero_start[i] = zs ? 1 : 0;
+        if (d && auto_reset) {
+            uint32_t ep = P.epoch[i] + 1u;
+            P.epoch[i] = ep;
+            reset_env<STAMPS>(P, e, P.env_index_base + (uint64_t)i, ep);
+            if (TRACK)
+                P.ep_return[i] = 0.0;
+        } else if (TRACK) {
+            P.ep_return[i] = ret;
+        }
+        float o[6];
+        observe(P, e, o);
+        store_obs(obs, i, o);
+        store_env<STAMPS>(P, i, e);
+    }
+    if (TRACK)
+        report_episodes(P, finished, zs, ret);
+}
+
+/* -- vector_reset / reset_at (env:428-480) -------------------------------------------------- */
+
+template <bool STAMPS, bool TRACK>
+__global__ void __launch_bounds__(kBlock)
+k_reset(const __grid_constant__ Params P, const uint8_t *__restrict__ mask, int64_t only,
+        float *__restrict__ obs, int64_t obs_row_offset)
+{
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (only >= 0)
+        i = (i == 0) ? only : P.n;
+    if (i >= P.n || (mask && !mask[i]))
+        return;
+    Env e;
+    uint32_t ep = P.epoch[i] + 1u;
+    P.epoch[i] = ep;
+    reset_env<STAMPS>(P, e, P.env_index_base + (uint64_t)i, ep);
+    store_env<STAMPS>(P, i, e);
+    if (TRACK)
+        P.ep_return[i] = 0.0;
+    if (obs) {
+        float o[6];
+        observe(P, e, o);
+        store_obs(obs, i + obs_row_offset, o);
+    }
+}
+
+template <bool STAMPS>
+__global__ void __launch_bounds__(kBlock)
+k_observe(const __grid_constant__ Params P, float *__restrict__ obs)
+{
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= P.n)
+        return;
+    Env e;
+    load_env<STAMPS>(P, i, e);
+    float o[6];
+    observe(P, e, o);
+    store_obs(obs, i, o);
+}
+
+/* -- multi-tick rollout with a device-side policy: state stays in registers -------------------- */
+
+template <bool STAMPS, bool TRACK>
+__global__ void __launch_bounds__(kBlock)
+k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick_base,
+          uint64_t policy_seed, float *__restrict__ obs, float *__restrict__ reward_sum)
+{
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = i < P.n;
+    const int64_t ii = active ? i : 0;
+    const uint64_t gidx = P.env_index_base + (uint64_t)ii;
+    Env e;
+    load_env<STAMPS>(P, ii, e);
+    uint32_t ep = P.epoch[ii];
+    double ret = TRACK ? P.ep_return[ii] : 0.0;
+    float rsum = 0.0f;
+    for (int t = 0; t < ticks; t++) {
+        uint32_t keybits;
+        double m;
+        policy_action(P, policy, policy_seed, gidx, tick_base + (uint32_t)t, keybits, m);
+        float r;
+        bool d;
+        tick<STAMPS>(P, e, keybits, m, r, d);
+        rsum = add32(rsum, r);
+        if (TRACK) {
+            ret = add64(ret, (double)r);
+            report_episodes(P, active && d, e.flags & F_ZERO_START, ret);
+        }
+        if (d) {
+            ep += 1u;
+            reset_env<STAMPS>(P, e, gidx, ep);
+            ret = 0.0;
+        }
+    }
+    if (!active)
+        return;
+    store_env<STAMPS>(P, i, e);
+    P.epoch[i] = ep;
+    if (TRACK)
+        P.ep_return[i] = ret;
+    if (reward_sum)
+        reward_sum[i] = rsum;
+    if (obs) {
+        float o[6];
+        observe(P, e, o);
+        store_obs(obs, i, o);
+    }
+}
+
+/* -- phys.apply on explicit arrays (phys:184-197) ----------------------------------------------- */
+
+__global__ void __launch_bounds__(kBlock)
+k_phys_apply(int64_t n, const double *__restrict__ yaw, const double *__restrict__ pitch,
+             const double *__restrict__ roll, const double *__restrict__ fmove,
+             const double *__restrict__ smove, const uint8_t *__restrict__ button2,
+             const double *__restrict__ time_delta, const double *__restrict__ z_pos,
+             const float *__restrict__ vel, const uint8_t *__restrict__ on_ground,
+             const uint8_t *__restrict__ jump_released, double *__restrict__ z_out,
+             float *__restrict__ vel_out, uint8_t *__restrict__ og_out, uint8_t *__restrict__ jr_out)
+{
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n)
+        return;
+    /* phys:58-66, general pitch / roll */
+    double sy, cy, sp = 0.0, cp = 1.0, sr = 0.0, cr = 1.0;
+    sincos(div64(mul64(yaw[i], kPi), 180.0), &sy, &cy);
+    if (pitch)
+        sincos(div64(mul64(pitch[i], kPi), 180.0), &sp, &cp);
+    if (roll)
+        sincos(div64(mul64(roll[i], kPi), 180.0), &sr, &cr);
+    double fx = mul64(cp, cy);
+    double rx = add64(mul64(mul64(mul64(-1.0, sr), sp), cy), mul64(mul64(-1.0, cr), -sy));
+    double fy = mul64(cp, sy);
+    double ry = add64(mul64(mul64(mul64(-1.0, sr), sp), sy), mul64(mul64(-1.0, cr), cy));
+
+    float vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+    double z = z_pos[i];
+    bool og = on_ground[i] != 0, jr = jump_released[i] != 0;
+    double dt = time_delta[i];
+    /* phys:78 f32(10) * dt, phys:122 f32(800) * dt */
+    move_body(vx, vy, vz, z, og, jr, fx, rx, fy, ry, fmove[i], smove[i], button2[i] != 0, dt,
+              mul64(10.0, dt), mul64(800.0, dt));
+    z_out[i] = z;
+    vel_out[3 * i] = vx;
+    vel_out[3 * i + 1] = vy;
+    vel_out[3 * i + 2] = vz;
+    og_out[i] = og;
+    jr_out[i] = jr;
+}
+
+/* -- env.ActionDecoder.map on explicit decoder state (env:225-269), f64 stamps ------------------- */
+
+__global__ void __launch_bounds__(kBlock)
+k_decode(const __grid_constant__ Params P, uint8_t *__restrict__ last_keys,
+         double *__restrict__ last_press, double *__restrict__ yaw,
+         const uint8_t *__restrict__ keys, const double *__restrict__ mouse,
+         const float *__restrict__ z_vel, const double *__restrict__ time_remaining,
+         int64_t *__restrict__ smove, int64_t *__restrict__ fmove, uint8_t *__restrict__ jump)
+{
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= P.n)
+        return;
+    const int nk = P.num_keys;
+    double mouse_x = 0.0;
+    if (P.allow_yaw) {
+        double m = mouse[i];
+        if (!P.discrete_yaw)
+            mouse_x = div64(mul64(m, P.max_yaw_delta), P.action_range);
+        else
+            mouse_x = div64(mul64(sub64(m, P.yaw_steps), P.max_yaw_delta), P.yaw_steps);
+    }
+    const double now = sub64(P.time_limit, time_remaining[i]);
+    int downs[4] = {0, 0, 0, 0}, lasts[4] = {0, 0, 0, 0};
+    for (int k = 0; k < nk; k++) {
+        int lk = last_keys[i * nk + k] & 1;
+        bool elapsed = now >= add64(last_press[i * nk + k], P.key_delay);
+        int d = (keys[i * nk + k] & 1) & ((elapsed ? 1 : 0) | lk);
+        if (d & ~lk & 1)
+            last_press[i * nk + k] = now;
+        last_keys[i * nk + k] = (uint8_t)d;
+        downs[k] = d;
+        lasts[k] = lk;
+    }
+    int f2, s2;
+    if (P.smooth_keys) {
+        f2 = downs[KEY_FORWARD] + lasts[KEY_FORWARD];
+        s2 = (downs[KEY_RIGHT] + lasts[KEY_RIGHT]) - (downs[KEY_LEFT] + lasts[KEY_LEFT]);
+    } else {
+        f2 = 2 * downs[KEY_FORWARD];
+        s2 = 2 * (downs[KEY_RIGHT] - downs[KEY_LEFT]);
+    }
+    double fm = f2 == 2 ? P.fmove_full : (f2 == 1 ? P.fmove_half : 0.0);
+    int as2 = s2 < 0 ? -s2 : s2;
+    double sm = as2 == 2 ? P.smove_full : (as2 == 1 ? P.smove_half : 0.0);
+    if (s2 < 0)
+        sm = -sm;
+    yaw[i] = add64(yaw[i], mouse_x);
+    smove[i] = (int64_t)sm;
+    fmove[i] = (int64_t)fm;
+    jump[i] = P.auto_jump ? (z_vel[i] <= 16.0f) : (P.allow_jump ? (uint8_t)downs[KEY_JUMP] : 0);
+}
+
+} // namespace
+
+/* ====================================================================== host side =========== */
+
+static thread_local std::string g_error;
+
+static int fail(int code, const std::string &msg)
+{
+    g_error = msg;
+    return code;
+}
+
+#define Q1_CUDA(call)                                                                             \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            return fail(Q1_ECUDA, std::string(#call) + ": " + cudaGetErrorString(err__));         \
+    } while (0)
+
+struct q1_env {
+    Params P{};
+    q1_config cfg{};
+    int device = 0;
+    bool stamps = false;
+    bool track = false;
+    uint32_t flags = 0;
+    void *pool = nullptr;
+    size_t pool_bytes = 0;
+    int state_bytes_per_env = 0;
+    uint64_t ticks = 0;
+    /* device scratch + stream of the *_host entry points */
+    cudaStream_t host_stream = nullptr;
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess)
+            prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+/* env.Config -> the numbers the kernels use, each in the width the reference computes it in. */
+int derive_params(const q1_config &c, Params &P, bool &counters_exact)
+{
+    if (c.num_envs <= 0)
+        return fail(Q1_EINVAL, "num_envs must be positive");
+    if (!(c.time_delta > 0))
+        return fail(Q1_EINVAL, "time_delta must be positive");
+    if (c.discrete_yaw_steps != -1 && c.discrete_yaw_steps < 1)
+        return fail(Q1_EINVAL, "discrete_yaw_steps must be -1 or >= 1");
+    if (c.key_press_delay < 0)
+        return fail(Q1_EINVAL, "key_press_delay must be >= 0");
+    P.n = c.num_envs;
+    P.dt = c.time_delta;
+    P.time_limit = c.time_limit;
+    P.key_delay = c.key_press_delay;
+    P.max_yaw_delta = (double)(720.0f * (float)c.time_delta); /* env:230 under NEP 50 */
+    P.action_range = c.action_range;
+    P.yaw_steps = (double)c.discrete_yaw_steps;
+    P.accel_dt = 10.0 * c.time_delta;
+    P.gravity_dt = 800.0 * c.time_delta;
+    P.fmove_half = std::trunc((double)(float)c.fmove_max * 0.5);
+    P.fmove_full = std::trunc((double)(float)c.fmove_max);
+    P.smove_half = std::trunc((double)(float)c.smove_max * 0.5);
+    P.smove_full = std::trunc((double)(float)c.smove_max);
+    P.zero_start_prob = c.zero_start_prob;
+    P.yaw_lo = c.initial_yaw_lo;
+    P.yaw_hi = c.initial_yaw_hi;
+    P.max_initial_speed = c.max_initial_speed;
+    P.dt_f32 = (float)c.time_delta;
+    P.num_keys = q1_num_keys(&c);
+    P.allow_yaw = c.allow_yaw != 0;
+    P.discrete_yaw = c.discrete_yaw_steps != -1;
+    P.speed_reward = c.speed_reward != 0;
+    P.hover = c.hover != 0;
+    P.smooth_keys = c.smooth_keys != 0;
+    P.auto_jump = c.auto_jump != 0;
+    P.allow_jump = c.allow_jump != 0;
+    /* u8 countdown timers reproduce the f64 stamp comparison exactly when delay/dt is safely away
+     * from an integer (rounding in TL - t_rem is ~1e-12 s), or when delay is 0. */
+    double q = c.key_press_delay / c.time_delta;
+    double frac = std::fabs(q - std::nearbyint(q));
+    counters_exact = (c.key_press_delay == 0.0) || (frac > 1e-6 && q < 254.0);
+    P.delay_ticks = counters_exact ? (int32_t)std::ceil(q) : 0;
+    return Q1_OK;
+}
+
+size_t align_up(size_t v) { return (v + 255u) & ~(size_t)255u; }
+
+template <typename F> int dispatch(const q1_env *env, F &&f)
+{
+    if (env->stamps)
+        return env->track ? f(std::true_type{}, std::true_type{}) : f(std::true_type{}, std::false_type{});
+    return env->track ? f(std::false_type{}, std::true_type{}) : f(std::false_type{}, std::false_type{});
+}
+
+int check_launch(const char *what)
+{
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return fail(Q1_ECUDA, std::string(what) + " launch: " + cudaGetErrorString(err));
+    return Q1_OK;
+}
+
+int ensure_scratch(q1_env *env, size_t bytes)
+{
+    if (!env->host_stream)
+        Q1_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+    if (env->scratch_bytes < bytes) {
+        if (env->scratch)
+            Q1_CUDA(cudaFree(env->scratch));
+        env->scratch = nullptr;
+        env->scratch_bytes = 0;
+        Q1_CUDA(cudaMalloc(&env->scratch, bytes));
+        env->scratch_bytes = bytes;
+    }
+    return Q1_OK;
+}
+
+} // namespace
+
+namespace {
+/* Bump allocator over one device buffer for the *_host conveniences without a handle. */
+struct Staging {
+    char *base = nullptr;
+    size_t size = 0, off = 0;
+    ~Staging()
+    {
+        if (base)
+            cudaFree(base);
+    }
+    int reserve(size_t bytes)
+    {
+        Q1_CUDA(cudaMalloc(reinterpret_cast<void **>(&base), bytes));
+        size = bytes;
+        return Q1_OK;
+    }
+    template <typename T> T *take(size_t count)
+    {
+        T *p = reinterpret_cast<T *>(base + off);
+        off = align_up(off + count * sizeof(T));
+        return p;
+    }
+};
+} // namespace
+
+extern "C" {
+
+const char *q1_last_error(void) { return g_error.c_str(); }
+
+int q1_abi_version(void) { return Q1_ABI_VERSION; }
+
+int q1_device_count(int *count)
+{
+    if (!count)
+        return fail(Q1_EINVAL, "count is NULL");
+    *count = 0;
+    cudaError_t err = cudaGetDeviceCount(count);
+    if (err != cudaSuccess) {
+        *count = 0;
+        return fail(Q1_ENODEV, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+    }
+    return Q1_OK;
+}
+
+int q1_num_keys(const q1_config *cfg)
+{
+    if (!cfg)
+        return fail(Q1_EINVAL, "cfg is NULL");
+    return (!cfg->auto_jump && cfg->allow_jump) ? 4 : 3; /* env:206-207 */
+}
+
+int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_index_base,
+              uint32_t flags, q1_env **out)
+{
+    if (!cfg || !out)
+        return fail(Q1_EINVAL, "cfg / out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(Q1_ENODEV, "no CUDA device: libq1phys has no CPU implementation");
+    if (device < 0 || device >= count)
+        return fail(Q1_EINVAL, "device index out of range");
+    q1_env *env = new (std::nothrow) q1_env();
+    if (!env)
+        return fail(Q1_ENOMEM, "out of host memory");
+    env->cfg = *cfg;
+    env->device = device;
+    env->flags = flags;
+    bool counters_exact = false;
+    int rc = derive_params(*cfg, env->P, counters_exact);
+    if (rc != Q1_OK) {
+        delete env;
+        return rc;
+    }
+    env->stamps = (flags & Q1_F_FORCE_F64_STAMPS) || !counters_exact;
+    env->track = flags & Q1_F_TRACK_RETURNS;
+    Params &P = env->P;
+    P.seed = seed;
+    P.env_index_base = env_index_base;
+
+    const size_t n = (size_t)P.n;
+    const int nk = P.num_keys;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes);
+        return o;
+    };
+    size_t o_vx = take(4 * n), o_vy = take(4 * n), o_vz = take(4 * n);
+    size_t o_z = take(8 * n), o_yaw = take(8 * n), o_trem = take(8 * n);
+    size_t o_keys = env->stamps ? take(8 * n * nk) : take(4 * n);
+    size_t o_flags = take(n), o_epoch = take(4 * n);
+    size_t o_ret = env->track ? take(8 * n) : 0;
+    size_t o_metrics = env->track ? take(64) : 0;
+    env->pool_bytes = off;
+    env->state_bytes_per_env = 12 + 24 + (env->stamps ? 8 * nk : 4) + 1 + (env->track ? 8 : 0);
+
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete env;
+        return fail(Q1_ECUDA, "cudaSetDevice failed");
+    }
+    cudaError_t err = cudaMalloc(&env->pool, env->pool_bytes);
+    if (err != cudaSuccess) {
+        delete env;
+        return fail(err == cudaErrorMemoryAllocation ? Q1_ENOMEM : Q1_ECUDA,
+                    std::string("cudaMalloc: ") + cudaGetErrorString(err));
+    }
+    err = cudaMemset(env->pool, 0, env->pool_bytes);
+    if (err != cudaSuccess) {
+        cudaFree(env->pool);
+        delete env;
+        return fail(Q1_ECUDA, std::string("cudaMemset: ") + cudaGetErrorString(err));
+    }
+    char *base = static_cast<char *>(env->pool);
+    P.vx = reinterpret_cast<float *>(base + o_vx);
+    P.vy = reinterpret_cast<float *>(base + o_vy);
+    P.vz = reinterpret_cast<float *>(base + o_vz);
+    P.z = reinterpret_cast<double *>(base + o_z);
+    P.yaw = reinterpret_cast<double *>(base + o_yaw);
+    P.trem = reinterpret_cast<double *>(base + o_trem);
+    P.timers = env->stamps ? nullptr : reinterpret_cast<uint32_t *>(base + o_keys);
+    P.stamps = env->stamps ? reinterpret_cast<double *>(base + o_keys) : nullptr;
+    P.flags = reinterpret_cast<uint8_t *>(base + o_flags);
+    P.epoch = reinterpret_cast<uint32_t *>(base + o_epoch);
+    P.ep_return = env->track ? reinterpret_cast<double *>(base + o_ret) : nullptr;
+    P.metrics = env->track ? reinterpret_cast<double *>(base + o_metrics) : nullptr;
+    *out = env;
+    return Q1_OK;
+}
+
+int q1_destroy(q1_env *env)
+{
+    if (!env)
+        return Q1_OK;
+    DeviceGuard guard(env->device);
+    if (env->scratch)
+        cudaFree(env->scratch);
+    if (env->host_stream)
+        cudaStreamDestroy(env->host_stream);
+    if (env->pool)
+        cudaFree(env->pool);
+    delete env;
+    return Q1_OK;
+}
+
+int q1_info(const q1_env *env, q1_env_info *out)
+{
+    if (!env || !out)
+        return fail(Q1_EINVAL, "env / out is NULL");
+    out->num_envs = env->P.n;
+    out->num_keys = env->P.num_keys;
+    out->device = env->device;
+    out->f64_stamps = env->stamps;
+    out->track_returns = env->track;
+    out->key_delay_ticks = env->P.delay_ticks;
+    out->state_bytes_per_env = env->state_bytes_per_env;
+    out->env_index_base = env->P.env_index_base;
+    out->seed = env->P.seed;
+    out->ticks = env->ticks;
+    return Q1_OK;
+}
+
+int q1_sync(q1_env *env, void *stream)
+{
+    if (!env)
+        return fail(Q1_EINVAL, "env is NULL");
+    DeviceGuard guard(env->device);
+    Q1_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return Q1_OK;
+}
+
+static int reset_launch(q1_env *env, const uint8_t *mask, int64_t only, float *obs,
+                        int64_t obs_row_offset, cudaStream_t s)
+{
+    unsigned grid = only >= 0 ? 1u : grid_for(env->P.n);
+    return dispatch(env, [&](auto st, auto tr) {
+        k_reset<decltype(st)::value, decltype(tr)::value>
+            <<<grid, kBlock, 0, s>>>(env->P, mask, only, obs, obs_row_offset);
+        return check_launch("k_reset");
+    });
+}
+
+int q1_reset_all(q1_env *env, float *obs, void *stream)
+{
+    if (!env)
+        return fail(Q1_EINVAL, "env is NULL");
+    DeviceGuard guard(env->device);
+    return reset_launch(env, nullptr, -1, obs, 0, static_cast<cudaStream_t>(stream));
+}
+
+int q1_reset_masked(q1_env *env, const uint8_t *mask, float *obs, void *stream)
+{
+    if (!env || !mask)
+        return fail(Q1_EINVAL, "env / mask is NULL");
+    DeviceGuard guard(env->device);
+    return reset_launch(env, mask, -1, obs, 0, static_cast<cudaStream_t>(stream));
+}
+
+/* mask_host == NULL: all envs.  Rows of envs that are not reset are left as they are in obs_host. */
+static int reset_host(q1_env *env, const uint8_t *mask_host, float *obs_host)
+{
+    DeviceGuard guard(env->device);
+    const size_t n = (size_t)env->P.n;
+    size_t o_obs = align_up(n);
+    int rc = ensure_scratch(env, o_obs + align_up(24 * n));
+    if (rc != Q1_OK)
+        return rc;
+    char *d = static_cast<char *>(env->scratch);
+    cudaStream_t s = env->host_stream;
+    uint8_t *d_mask = nullptr;
+    float *d_obs = obs_host ? reinterpret_cast<float *>(d + o_obs) : nullptr;
+    if (mask_host) {
+        d_mask = reinterpret_cast<uint8_t *>(d);
+        Q1_CUDA(cudaMemcpyAsync(d_mask, mask_host, n, cudaMemcpyHostToDevice, s));
+        if (obs_host)
+            Q1_CUDA(cudaMemcpyAsync(d_obs, obs_host, 24 * n, cudaMemcpyHostToDevice, s));
+    }
+    rc = reset_launch(env, d_mask, -1, d_obs, 0, s);
+    if (rc != Q1_OK)
+        return rc;
+    if (obs_host)
+        Q1_CUDA(cudaMemcpyAsync(obs_host, d_obs, 24 * n, cudaMemcpyDeviceToHost, s));
+    Q1_CUDA(cudaStreamSynchronize(s));
+    return Q1_OK;
+}
+
+int q1_reset_all_host(q1_env *env, float *obs_host)
+{
+    if (!env)
+        return fail(Q1_EINVAL, "env is NULL");
+    return reset_host(env, nullptr, obs_host);
+}
+
+int q1_reset_masked_host(q1_env *env, const uint8_t *mask_host, float *obs_host)
+{
+    if (!env || !mask_host)
+        return fail(Q1_EINVAL, "env / mask is NULL");
+    return reset_host(env, mask_host, obs_host);
+}
+
+int q1_reset_at_host(q1_env *env, int64_t index, float *obs6_host)
+{
+    if (!env)
+        return fail(Q1_EINVAL, "env is NULL");
+    if (index < 0 || index >= env->P.n)
+        return fail(Q1_EINVAL, "env index out of range");
+    DeviceGuard guard(env->device);
+    int rc = ensure_scratch(env, 64);
+    if (rc != Q1_OK)
+        return rc;
+    float *d_obs = static_cast<float *>(env->scratch);
+    rc = reset_launch(env, nullptr, index, obs6_host ? d_obs : nullptr, -index, env->host_stream);
+    if (rc != Q1_OK)
+        return rc;
+    if (obs6_host)
+        Q1_CUDA(cudaMemcpyAsync(obs6_host, d_obs, 6 * sizeof(float), cudaMemcpyDeviceToHost,
+                                env->host_stream));
+    Q1_CUDA(cudaStreamSynchronize(env->host_stream));
+    return Q1_OK;
+}
+
+int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
+            float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream)
+{
+    if (mouse_kind != Q1_MOUSE_F32 && mouse_kind != Q1_MOUSE_I32 && mouse_kind != Q1_MOUSE_F64)
+        return fail(Q1_EINVAL, "unknown mouse_kind");
+    if (!env || !keys || !obs || !reward || !done)
+        return fail(Q1_EINVAL, "env / keys / obs / reward / done is NULL");
+    if (env->P.allow_yaw && !mouse)
+        return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = dispatch(env, [&](auto st, auto tr) {
+        k_step<decltype(st)::value, decltype(tr)::value><<<grid_for(env->P.n), kBlock, 0, s>>>(
+            env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset);
+        return check_launch("k_step");
+    });
+    if (rc == Q1_OK)
+        env->ticks += 1;
+    return rc;
+}
+
+int q1_host_alloc(uint64_t bytes, void **out)
+{
+    if (!out)
+        return fail(Q1_EINVAL, "out is NULL");
+    *out = nullptr;
+    cudaError_t err = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (err != cudaSuccess)
+        return fail(err == cudaErrorMemoryAllocation ? Q1_ENOMEM : Q1_ECUDA,
+                    std::string("cudaHostAlloc: ") + cudaGetErrorString(err));
+    return Q1_OK;
+}
+
+int q1_host_free(void *ptr)
+{
+    if (ptr)
+        Q1_CUDA(cudaFreeHost(ptr));
+    return Q1_OK;
+}
+
+int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
+                 float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset)
+{
+    if (mouse_kind != Q1_MOUSE_F32 && mouse_kind != Q1_MOUSE_I32 && mouse_kind != Q1_MOUSE_F64)
+        return fail(Q1_EINVAL, "unknown mouse_kind");
+    const size_t mouse_size = mouse_kind == Q1_MOUSE_F64 ? 8 : 4;
+    if (!env || !keys || !obs || !reward || !done)
+        return fail(Q1_EINVAL, "env / keys / obs / reward / done is NULL");
+    if (env->P.allow_yaw && !mouse)
+        return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
+    DeviceGuard guard(env->device);
+    const size_t n = (size_t)env->P.n, nk = (size_t)env->P.num_keys;
+    size_t o_keys = 0, o_mouse = align_up(n * nk), o_obs = o_mouse + align_up(8 * n);
+    size_t o_rew = o_obs + align_up(24 * n), o_done = o_rew + align_up(4 * n);
+    size_t o_zs = o_done + align_up(n), total = o_zs + align_up(n);
+    int rc = ensure_scratch(env, total);
+    if (rc != Q1_OK)
+        return rc;
+    char *d = static_cast<char *>(env->scratch);
+    cudaStream_t s = env->host_stream;
+    Q1_CUDA(cudaMemcpyAsync(d + o_keys, keys, n * nk, cudaMemcpyHostToDevice, s));
+    if (env->P.allow_yaw)
+        Q1_CUDA(cudaMemcpyAsync(d + o_mouse, mouse, mouse_size * n, cudaMemcpyHostToDevice, s));
+    rc = q1_step(env, reinterpret_cast<uint8_t *>(d + o_keys), d + o_mouse, mouse_kind,
+                 reinterpret_cast<float *>(d + o_obs), reinterpret_cast<float *>(d + o_rew),
+                 reinterpret_cast<uint8_t *>(d + o_done),
+                 zero_start ? reinterpret_cast<uint8_t *>(d + o_zs) : nullptr, auto_reset, s);
+    if (rc != Q1_OK)
+        return rc;
+    Q1_CUDA(cudaMemcpyAsync(obs, d + o_obs, 24 * n, cudaMemcpyDeviceToHost, s));
+    Q1_CUDA(cudaMemcpyAsync(reward, d + o_rew, 4 * n, cudaMemcpyDeviceToHost, s));
+    Q1_CUDA(cudaMemcpyAsync(done, d + o_done, n, cudaMemcpyDeviceToHost, s));
+    if (zero_start)
+        Q1_CUDA(cudaMemcpyAsync(zero_start, d + o_zs, n, cudaMemcpyDeviceToHost, s));
+    Q1_CUDA(cudaStreamSynchronize(s));
+    return Q1_OK;
+}
+
+int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *obs,
+               float *reward_sum, void *stream)
+{
+    if (!env)
+        return fail(Q1_EINVAL, "env is NULL");
+    if (policy != Q1_POLICY_RANDOM && policy != Q1_POLICY_STRAFE_JUMP)
+        return fail(Q1_EINVAL, "unknown policy");
+    if (ticks < 0)
+        return fail(Q1_EINVAL, "ticks must be >= 0");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = dispatch(env, [&](auto st, auto tr) {
+        k_rollout<decltype(st)::value, decltype(tr)::value><<<grid_for(env->P.n), kBlock, 0, s>>>(
+            env->P, policy, ticks, (uint32_t)env->ticks, policy_seed, obs, reward_sum);
+        return check_launch("k_rollout");
+    });
+    if (rc == Q1_OK)
+        env->ticks += (uint64_t)ticks;
+    return rc;
+}
+
+int q1_observe(q1_env *env, float *obs, void *stream)
+{
+    if (!env || !obs)
+        return fail(Q1_EINVAL, "env / obs is NULL");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (env->stamps)
+        k_observe<true><<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, obs);
+    else
+        k_observe<false><<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, obs);
+    return check_launch("k_observe");
+}
+
+int q1_observe_host(q1_env *env, float *obs_host)
+{
+    if (!env || !obs_host)
+        return fail(Q1_EINVAL, "env / obs is NULL");
+    DeviceGuard guard(env->device);
+    const size_t n = (size_t)env->P.n;
+    int rc = ensure_scratch(env, align_up(24 * n));
+    if (rc != Q1_OK)
+        return rc;
+    float *d_obs = static_cast<float *>(env->scratch);
+    rc = q1_observe(env, d_obs, env->host_stream);
+    if (rc != Q1_OK)
+        return rc;
+    Q1_CUDA(cudaMemcpyAsync(obs_host, d_obs, 24 * n, cudaMemcpyDeviceToHost, env->host_stream));
+    Q1_CUDA(cudaStreamSynchronize(env->host_stream));
+    return Q1_OK;
+}
+
+/* -- state copy-out / copy-in in the reference layout ----------------------------------------- */
+
+int q1_get_state_host(q1_env *env, const q1_state_view *v)
+{
+    if (!env || !v)
+        return fail(Q1_EINVAL, "env / view is NULL");
+    DeviceGuard guard(env->device);
+    Q1_CUDA(cudaDeviceSynchronize());
+    const Params &P = env->P;
+    const size_t n = (size_t)P.n;
+    const int nk = P.num_keys;
+    if (v->vel) {
+        std::vector<float> a(n), b(n), c(n);
+        Q1_CUDA(cudaMemcpy(a.data(), P.vx, 4 * n, cudaMemcpyDeviceToHost));
+        Q1_CUDA(cudaMemcpy(b.data(), P.vy, 4 * n, cudaMemcpyDeviceToHost));
+        Q1_CUDA(cudaMemcpy(c.data(), P.vz, 4 * n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) {
+            v->vel[3 * i] = a[i];
+            v->vel[3 * i + 1] = b[i];
+            v->vel[3 * i + 2] = c[i];
+        }
+    }
+    if (v->z_pos)
+        Q1_CUDA(cudaMemcpy(v->z_pos, P.z, 8 * n, cudaMemcpyDeviceToHost));
+    if (v->yaw)
+        Q1_CUDA(cudaMemcpy(v->yaw, P.yaw, 8 * n, cudaMemcpyDeviceToHost));
+    std::vector<double> trem;
+    if (v->time_remaining || (v->last_press && !env->stamps)) {
+        trem.resize(n);
+        Q1_CUDA(cudaMemcpy(trem.data(), P.trem, 8 * n, cudaMemcpyDeviceToHost));
+        if (v->time_remaining)
+            memcpy(v->time_remaining, trem.data(), 8 * n);
+    }
+    if (v->on_ground || v->jump_released || v->zero_start || v->last_keys) {
+        std::vector<uint8_t> f(n);
+        Q1_CUDA(cudaMemcpy(f.data(), P.flags, n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) {
+            if (v->on_ground)
+                v->on_ground[i] = (f[i] & F_ON_GROUND) != 0;
+            if (v->jump_released)
+                v->jump_released[i] = (f[i] & F_JUMP_RELEASED) != 0;
+            if (v->zero_start)
+                v->zero_start[i] = (f[i] & F_ZERO_START) != 0;
+            if (v->last_keys)
+                for (int k = 0; k < nk; k++)
+                    v->last_keys[i * nk + k] = (f[i] >> (F_LAST_KEY_SHIFT + k)) & 1u;
+        }
+    }
+    if (v->last_press) {
+        if (env->stamps) {
+            std::vector<double> s(n * nk);
+            Q1_CUDA(cudaMemcpy(s.data(), P.stamps, 8 * n * nk, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; i++)
+                for (int k = 0; k < nk; k++)
+                    v->last_press[i * nk + k] = s[(size_t)k * n + i];
+        } else {
+            /* Counter mode keeps "ticks until the key may be pressed again"; the stamp handed back
+             * is the one that yields the same future decode decisions (exact stamps need
+             * Q1_F_FORCE_F64_STAMPS). */
+            std::vector<uint32_t> t(n);
+            Q1_CUDA(cudaMemcpy(t.data(), P.timers, 4 * n, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; i++) {
+                double now = P.time_limit - trem[i];
+                for (int k = 0; k < nk; k++) {
+                    int r = (t[i] >> (8 * k)) & 0xFF;
+                    v->last_press[i * nk + k] =
+                        r == 0 ? -P.key_delay : now - (double)(P.delay_ticks - r + 1) * P.dt;
+                }
+            }
+        }
+    }
+    if (v->episode_return) {
+        if (!env->track)
+            return fail(Q1_EINVAL, "episode_return requires Q1_F_TRACK_RETURNS");
+        Q1_CUDA(cudaMemcpy(v->episode_return, P.ep_return, 8 * n, cudaMemcpyDeviceToHost));
+    }
+    return Q1_OK;
+}
+
+int q1_set_state_host(q1_env *env, const q1_state_view *v)
+{
+    if (!env || !v)
+        return fail(Q1_EINVAL, "env / view is NULL");
+    DeviceGuard guard(env->device);
+    Q1_CUDA(cudaDeviceSynchronize());
+    const Params &P = env->P;
+    const size_t n = (size_t)P.n;
+    const int nk = P.num_keys;
+    if (v->vel) {
+        std::vector<float> a(n), b(n), c(n);
+        for (size_t i = 0; i < n; i++) {
+            a[i] = v->vel[3 * i];
+            b[i] = v->vel[3 * i + 1];
+            c[i] = v->vel[3 * i + 2];
+        }
+        Q1_CUDA(cudaMemcpy(P.vx, a.data(), 4 * n, cudaMemcpyHostToDevice));
+        Q1_CUDA(cudaMemcpy(P.vy, b.data(), 4 * n, cudaMemcpyHostToDevice));
+        Q1_CUDA(cudaMemcpy(P.vz, c.data(), 4 * n, cudaMemcpyHostToDevice));
+    }
+    if (v->z_pos)
+        Q1_CUDA(cudaMemcpy(P.z, v->z_pos, 8 * n, cudaMemcpyHostToDevice));
+    if (v->yaw)
+        Q1_CUDA(cudaMemcpy(P.yaw, v->yaw, 8 * n, cudaMemcpyHostToDevice));
+    if (v->time_remaining)
+        Q1_CUDA(cudaMemcpy(P.trem, v->time_remaining, 8 * n, cudaMemcpyHostToDevice));
+    if (v->on_ground || v->jump_released || v->zero_start || v->last_keys) {
+        std::vector<uint8_t> f(n);
+        Q1_CUDA(cudaMemcpy(f.data(), P.flags, n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) {
+            uint32_t x = f[i];
+            if (v->on_ground)
+                x = (x & ~F_ON_GROUND) | (v->on_ground[i] ? F_ON_GROUND : 0u);
+            if (v->jump_released)
+                x = (x & ~F_JUMP_RELEASED) | (v->jump_released[i] ? F_JUMP_RELEASED : 0u);
+            if (v->zero_start)
+                x = (x & ~F_ZERO_START) | (v->zero_start[i] ? F_ZERO_START : 0u);
+            if (v->last_keys) {
+                x &= ~(0xFu << F_LAST_KEY_SHIFT);
+                for (int k = 0; k < nk; k++)
+                    x |= (uint32_t)(v->last_keys[i * nk + k] & 1u) << (F_LAST_KEY_SHIFT + k);
+            }
+            f[i] = (uint8_t)x;
+        }
+        Q1_CUDA(cudaMemcpy(P.flags, f.data(), n, cudaMemcpyHostToDevice));
+    }
+    if (v->last_press) {
+        if (env->stamps) {
+            std::vector<double> s(n * nk);
+            for (size_t i = 0; i < n; i++)
+                for (int k = 0; k < nk; k++)
+                    s[(size_t)k * n + i] = v->last_press[i * nk + k];
+            Q1_CUDA(cudaMemcpy(P.stamps, s.data(), 8 * n * nk, cudaMemcpyHostToDevice));
+        } else {
+            /* ticks until now_j >= stamp + delay holds, now_j = now + j * dt (env:241-242) */
+            std::vector<double> trem(n);
+            Q1_CUDA(cudaMemcpy(trem.data(), P.trem, 8 * n, cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> t(n);
+            for (size_t i = 0; i < n; i++) {
+                double now = P.time_limit - trem[i];
+                uint32_t w = 0;
+                for (int k = 0; k < nk; k++) {
+                    double need = (v->last_press[i * nk + k] + P.key_delay - now) / P.dt;
+                    double r = std::ceil(need - 1e-9) + 1.0; /* the kernel decrements before testing */
+                    if (!(r > 0))
+                        r = 0;
+                    if (r > 255)
+                        r = 255;
+                    w |= (uint32_t)r << (8 * k);
+                }
+                t[i] = w;
+            }
+            Q1_CUDA(cudaMemcpy(P.timers, t.data(), 4 * n, cudaMemcpyHostToDevice));
+        }
+    }
+    if (v->episode_return) {
+        if (!env->track)
+            return fail(Q1_EINVAL, "episode_return requires Q1_F_TRACK_RETURNS");
+        Q1_CUDA(cudaMemcpy(P.ep_return, v->episode_return, 8 * n, cudaMemcpyHostToDevice));
+    }
+    return Q1_OK;
+}
+
+int q1_get_metrics_host(q1_env *env, int clear, q1_metrics *out)
+{
+    if (!env || !out)
+        return fail(Q1_EINVAL, "env / out is NULL");
+    if (!env->track)
+        return fail(Q1_EINVAL, "metrics require Q1_F_TRACK_RETURNS");
+    DeviceGuard guard(env->device);
+    Q1_CUDA(cudaDeviceSynchronize());
+    unsigned long long raw[5];
+    Q1_CUDA(cudaMemcpy(raw, env->P.metrics, sizeof(raw), cudaMemcpyDeviceToHost));
+    memcpy(&out->zero_start_return_sum, &raw[0], 8);
+    out->zero_start_episodes = (int64_t)raw[1];
+    memcpy(&out->return_sum, &raw[2], 8);
+    out->episodes = (int64_t)raw[3];
+    if (raw[4] == 0) {
+        out->return_max = -INFINITY;
+    } else {
+        unsigned long long b = (raw[4] >> 63) ? (raw[4] & 0x7FFFFFFFFFFFFFFFull) : ~raw[4];
+        memcpy(&out->return_max, &b, 8);
+    }
+    if (clear)
+        Q1_CUDA(cudaMemset(env->P.metrics, 0, sizeof(raw)));
+    return Q1_OK;
+}
+
+/* -- phys.apply ---------------------------------------------------------------------------------- */
+
+int q1_phys_apply(int device, int64_t n, const double *yaw, const double *pitch, const double *roll,
+                  const double *fmove, const double *smove, const uint8_t *button2,
+                  const double *time_delta, const double *z_pos, const float *vel,
+                  const uint8_t *on_ground, const uint8_t *jump_released, double *z_pos_out,
+                  float *vel_out, uint8_t *on_ground_out, uint8_t *jump_released_out, void *stream)
+{
+    if (n < 0)
+        return fail(Q1_EINVAL, "n must be >= 0");
+    if (n == 0)
+        return Q1_OK;
+    if (!yaw || !fmove || !smove || !button2 || !time_delta || !z_pos || !vel || !on_ground ||
+        !jump_released || !z_pos_out || !vel_out || !on_ground_out || !jump_released_out)
+        return fail(Q1_EINVAL, "a required array is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    k_phys_apply<<<grid_for(n), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, yaw, pitch, roll, fmove, smove, button2, time_delta, z_pos, vel, on_ground,
+        jump_released, z_pos_out, vel_out, on_ground_out, jump_released_out);
+    return check_launch("k_phys_apply");
+}
+
+
+int q1_phys_apply_host(int device, int64_t n, const double *yaw, const double *pitch,
+                       const double *roll, const double *fmove, const double *smove,
+                       const uint8_t *button2, const double *time_delta, const double *z_pos,
+                       const float *vel, const uint8_t *on_ground, const uint8_t *jump_released,
+                       double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
+                       uint8_t *jump_released_out)
+{
+    if (n < 0)
+        return fail(Q1_EINVAL, "n must be >= 0");
+    if (n == 0)
+        return Q1_OK;
+    if (!yaw || !fmove || !smove || !button2 || !time_delta || !z_pos || !vel || !on_ground ||
+        !jump_released || !z_pos_out || !vel_out || !on_ground_out || !jump_released_out)
+        return fail(Q1_EINVAL, "a required array is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    const size_t N = (size_t)n;
+    Staging st;
+    int rc = st.reserve(align_up(8 * N) * 8 + align_up(12 * N) * 2 + align_up(N) * 5 + 4096);
+    if (rc != Q1_OK)
+        return rc;
+    auto up = [&](auto *dst, const auto *src, size_t count) -> cudaError_t {
+        return cudaMemcpy(dst, src, count * sizeof(*src), cudaMemcpyHostToDevice);
+    };
+    double *d_yaw = st.take<double>(N), *d_pitch = pitch ? st.take<double>(N) : nullptr;
+    double *d_roll = roll ? st.take<double>(N) : nullptr;
+    double *d_fm = st.take<double>(N), *d_sm = st.take<double>(N), *d_dt = st.take<double>(N);
+    double *d_z = st.take<double>(N), *d_zo = st.take<double>(N);
+    float *d_vel = st.take<float>(3 * N), *d_velo = st.take<float>(3 * N);
+    uint8_t *d_b2 = st.take<uint8_t>(N), *d_og = st.take<uint8_t>(N), *d_jr = st.take<uint8_t>(N);
+    uint8_t *d_ogo = st.take<uint8_t>(N), *d_jro = st.take<uint8_t>(N);
+    Q1_CUDA(up(d_yaw, yaw, N));
+    if (pitch)
+        Q1_CUDA(up(d_pitch, pitch, N));
+    if (roll)
+        Q1_CUDA(up(d_roll, roll, N));
+    Q1_CUDA(up(d_fm, fmove, N));
+    Q1_CUDA(up(d_sm, smove, N));
+    Q1_CUDA(up(d_dt, time_delta, N));
+    Q1_CUDA(up(d_z, z_pos, N));
+    Q1_CUDA(up(d_vel, vel, 3 * N));
+    Q1_CUDA(up(d_b2, button2, N));
+    Q1_CUDA(up(d_og, on_ground, N));
+    Q1_CUDA(up(d_jr, jump_released, N));
+    rc = q1_phys_apply(device, n, d_yaw, d_pitch, d_roll, d_fm, d_sm, d_b2, d_dt, d_z, d_vel, d_og,
+                       d_jr, d_zo, d_velo, d_ogo, d_jro, nullptr);
+    if (rc != Q1_OK)
+        return rc;
+    Q1_CUDA(cudaMemcpy(z_pos_out, d_zo, 8 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(vel_out, d_velo, 12 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(on_ground_out, d_ogo, N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(jump_released_out, d_jro, N, cudaMemcpyDeviceToHost));
+    return Q1_OK;
+}
+
+/* -- ActionDecoder.map ----------------------------------------------------------------------------- */
+
+int q1_decode_host(const q1_config *cfg, int device, int64_t n, uint8_t *last_keys,
+                   double *last_press, double *yaw, const uint8_t *keys, const double *mouse,
+                   const float *z_vel, const double *time_remaining, int64_t *smove,
+                   int64_t *fmove, uint8_t *jump)
+{
+    if (!cfg)
+        return fail(Q1_EINVAL, "cfg is NULL");
+    if (n < 0)
+        return fail(Q1_EINVAL, "n must be >= 0");
+    if (n == 0)
+        return Q1_OK;
+    if (!last_keys || !last_press || !yaw || !keys || !z_vel || !time_remaining || !smove ||
+        !fmove || !jump)
+        return fail(Q1_EINVAL, "a required array is NULL");
+    if (cfg->allow_yaw && !mouse)
+        return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
+    q1_config c = *cfg;
+    c.num_envs = n;
+    Params P{};
+    bool unused = false;
+    int rc = derive_params(c, P, unused);
+    if (rc != Q1_OK)
+        return rc;
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    const size_t N = (size_t)n, nk = (size_t)P.num_keys;
+    Staging st;
+    rc = st.reserve(align_up(N * nk) * 2 + align_up(8 * N * nk) + align_up(8 * N) * 5 +
+                    align_up(4 * N) + align_up(N) + 4096);
+    if (rc != Q1_OK)
+        return rc;
+    uint8_t *d_lk = st.take<uint8_t>(N * nk), *d_keys = st.take<uint8_t>(N * nk);
+    double *d_lp = st.take<double>(N * nk), *d_yaw = st.take<double>(N);
+    double *d_mouse = st.take<double>(N), *d_tr = st.take<double>(N);
+    int64_t *d_sm = st.take<int64_t>(N), *d_fm = st.take<int64_t>(N);
+    float *d_zv = st.take<float>(N);
+    uint8_t *d_jump = st.take<uint8_t>(N);
+    Q1_CUDA(cudaMemcpy(d_lk, last_keys, N * nk, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_keys, keys, N * nk, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_lp, last_press, 8 * N * nk, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_yaw, yaw, 8 * N, cudaMemcpyHostToDevice));
+    if (cfg->allow_yaw)
+        Q1_CUDA(cudaMemcpy(d_mouse, mouse, 8 * N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_tr, time_remaining, 8 * N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_zv, z_vel, 4 * N, cudaMemcpyHostToDevice));
+    k_decode<<<grid_for(n), kBlock>>>(P, d_lk, d_lp, d_yaw, d_keys, d_mouse, d_zv, d_tr, d_sm, d_fm,
+                                      d_jump);
+    rc = check_launch("k_decode");
+    if (rc != Q1_OK)
+        return rc;
+    Q1_CUDA(cudaMemcpy(last_keys, d_lk, N * nk, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(last_press, d_lp, 8 * N * nk, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(yaw, d_yaw, 8 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(smove, d_sm, 8 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(fmove, d_fm, 8 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(jump, d_jump, N, cudaMemcpyDeviceToHost));
+    return Q1_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,144 @@
+"""GPU: the reference's Python API surface on the CUDA env: gym-style loop,
+RLLib-style vector calls, the attributes analyse.eval_sim reaches into, the alias package."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gym_style_loop_and_spaces():
+    from q1physrl_b200 import env as benv
+    e = benv.PhysEnv(benv.Config.get_default(), seed=5)
+    assert len(e.action_space.spaces) == 5 and e.action_space.spaces[0].n == 2
+    box = e.action_space.spaces[4]
+    assert box.shape == (1,) and np.float32(box.high[0]) == np.float32(10.08)
+    assert e.observation_space.shape == (6,)
+    obs = e.reset()
+    assert obs.shape == (6,) and obs.dtype == np.float32
+    np.random.seed(0)
+    total, steps, done = 0.0, 0, False
+    while not done:
+        obs, reward, done, info = e.step(e.action_space.sample())
+        assert obs.shape == (6,) and isinstance(info, dict) and "zero_start" in info
+        assert isinstance(reward, np.float32) and isinstance(done, (bool, np.bool_))
+        total += float(reward)
+        steps += 1
+        assert steps <= 721
+    assert steps >= 1
+    with pytest.raises(AssertionError):
+        benv.PhysEnv(dataclasses.replace(benv.Config.get_default(), num_envs=3))
+
+
+def test_rllib_style_vector_calls():
+    from q1physrl_b200 import env as benv
+    cfg = dict(harness.PARAMS_100M, num_envs=7, time_limit=0.5)
+    e = benv.VectorPhysEnv(cfg, seed=6)                        # constructed from a dict, as RLLib does
+    assert e.num_envs == 7 and e.get_unwrapped() == []
+    obs = e.vector_reset()
+    assert obs.shape == (7, 6)
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        # RLLib format: list of per-env tuples, discrete keys as ints, mouse as a 1-element array
+        actions = [tuple([int(k) for k in rng.integers(0, 2, 4)]
+                         + [np.array([rng.uniform(-10, 10)], np.float32)]) for _ in range(7)]
+        obs, rewards, dones, infos = e.vector_step(actions)
+        assert len(infos) == 7 and set(infos[0]) == {"zero_start"}
+        assert obs.shape == (7, 6) and rewards.shape == (7,) and dones.dtype == np.bool_
+        for i in np.nonzero(dones)[0]:
+            o = e.reset_at(int(i))
+            assert o.shape == (6,)
+            assert np.array_equal(o, e._get_obs_at(int(i)))
+            assert e._time_remaining[i] > 0
+    with pytest.raises(ValueError):
+        e.vector_step([(0, 0, 1, 0, 0.0)] * 3)               # wrong number of envs
+
+
+def test_eval_sim_style_usage():
+    """analyse.py:197-240: shadow ActionDecoder fed with obs z-vel and e._time_remaining; snapshot
+    semantics of e.player_state; PlayerState.concatenate."""
+    from q1physrl_b200 import env as benv, phys
+    config = benv.Config(**dict(harness.PARAMS_100M, num_envs=1, zero_start_prob=1.0, time_limit=1.0))
+    e = benv.VectorPhysEnv(dataclasses.asdict(config), seed=1)
+    o, = e.vector_reset()
+    dec = benv.ActionDecoder(config)
+    dec.vector_reset(e._yaw)
+    states, yaws = [], []
+    done, t = False, 0
+    while not done:
+        a = (0, int(t % 40 < 20), 1, int(t % 2), np.array([1.5], np.float32))
+        (yaw,), (smove,), (fmove,), (jump,) = dec.map([a], o[None, benv.Obs.Z_VEL], e._time_remaining)
+        states.append(e.player_state)
+        yaws.append(yaw)
+        (o,), (r,), (done,), _ = e.vector_step([a])
+        assert yaw == e._yaw[0]                               # shadow decoder tracks the env's yaw
+        t += 1
+    assert t == 73                                            # 1.0 s at dt=0.0138888 -> 73 ticks
+    ps = phys.PlayerState.concatenate(states)
+    assert ps.vel.shape == (t, 3) and ps.z_pos.shape == (t,)
+    assert not np.array_equal(states[0].vel, states[-1].vel)  # earlier snapshots were not mutated
+    assert ps.to_df().shape == (t, 6)
+
+
+def test_alias_package_and_state_roundtrip():
+    import q1physrl_env.env as alias_env
+    import q1physrl_env.phys as alias_phys
+    from q1physrl_b200 import env as benv, phys
+    assert alias_env.VectorPhysEnv is benv.VectorPhysEnv and alias_phys.apply is phys.apply
+    assert set(alias_env.__all__) == {'ActionDecoder', 'Config', 'get_obs_scale', 'INITIAL_YAW_ZERO',
+                                      'Key', 'Obs', 'PhysEnv', 'VectorPhysEnv'}
+    cfg = dict(harness.PARAMS_100M, num_envs=300)
+    for stamps in (False, True):
+        e = benv.VectorPhysEnv(cfg, seed=2, f64_key_stamps=stamps)
+        rng = np.random.default_rng(1)
+        for _ in range(30):
+            e.vector_step(harness.random_actions(cfg, rng, 300, 4))
+        s = e.get_state()
+        e2 = benv.VectorPhysEnv(cfg, seed=99, f64_key_stamps=stamps)
+        e2.set_state(s)
+        s2 = e2.get_state()
+        for f in harness.STATE_FIELDS:
+            assert np.array_equal(s[f], s2[f]), f
+        for _ in range(30):
+            acts = harness.random_actions(cfg, rng, 300, 4)
+            o1 = e.vector_step(acts)
+            o2 = e2.vector_step(acts)
+            for x, y in zip(o1[:3], o2[:3]):
+                assert np.array_equal(x, y)
+
+
+def test_reset_distribution_on_device():
+    from q1physrl_b200 import env as benv
+    cfg = dict(harness.PARAMS_100M, num_envs=200000, zero_start_prob=0.25)
+    e = benv.VectorPhysEnv(cfg, seed=7)
+    s = e.get_state()
+    zs = s["zero_start"]
+    assert abs(zs.mean() - 0.25) < 0.01
+    assert np.all(s["time_remaining"][zs] == 10) and np.all(s["yaw"][zs] == 90)
+    t = s["time_remaining"][~zs]
+    assert t.min() > 1 and t.max() <= 10 and abs(t.mean() - 5.5) < 0.05
+    sp = np.hypot(s["vel"][~zs, 0].astype(np.float64), s["vel"][~zs, 1])
+    assert sp.min() > 0.99 and sp.max() <= 700.001 and abs(sp.mean() - 350.5) < 3
+    y = s["yaw"][~zs]
+    assert y.min() >= 0 and y.max() < 360 and abs(y.mean() - 180) < 2
+    # a second reset draws fresh values; the same seed reproduces the first
+    e.vector_reset()
+    assert not np.array_equal(e.get_state()["yaw"], s["yaw"])
+    e2 = benv.VectorPhysEnv(cfg, seed=7)
+    assert np.array_equal(e2.get_state()["yaw"], s["yaw"])
+
+
+def test_errors_are_loud():
+    from q1physrl_b200 import env as benv, _lib
+    with pytest.raises(_lib.Q1Error):
+        benv.VectorPhysEnv(dict(harness.PARAMS_100M, num_envs=4, time_delta=0.0))
+    with pytest.raises(_lib.Q1Error):
+        benv.VectorPhysEnv(dict(harness.PARAMS_100M, num_envs=4), device=99)
+    e = benv.VectorPhysEnv(dict(harness.PARAMS_100M, num_envs=4))
+    with pytest.raises(_lib.Q1Error):
+        e.metrics()                                          # needs track_returns
+    with pytest.raises(_lib.Q1Error):
+        e.reset_at(4)

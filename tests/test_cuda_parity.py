@@ -1,0 +1,357 @@
+"""GPU: the CUDA path (through the C ABI / the Python mirror) against the golden fixtures recorded
+from the reference and against the C oracle on identical seeded inputs.
+
+Contract (BASELINE.json north_star): done / on_ground and every other flag bit-exact, z / yaw /
+time_remaining bit-exact (pure f64 add chains), velocity within 1e-5 abs -- the only source of a
+difference is CUDA's f64 sincos (<= 2 ulp) against glibc's; the tests report how many stored f32
+velocities are bit-identical.
+"""
+import numpy as np
+import pytest
+
+import harness
+from oracle import q1_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+VEL_ATOL = 1e-5
+
+
+@pytest.mark.parametrize("stamps", [False, True], ids=["counters", "f64stamps"])
+@pytest.mark.parametrize("name", harness.ENV_FIXTURES)
+def test_golden_replay(name, stamps, record_property):
+    g = harness.load_golden(name)
+    stats = harness.replay(harness.CudaAdapter(g["config"], f64_key_stamps=stamps), g,
+                           vel_atol=VEL_ATOL)
+    record_property("vel_bit_exact_fraction", 1 - stats["vel_mismatch"] / stats["vel_values"])
+    assert stats["obs_max_abs"] <= 1e-6
+    print(name, stats)
+
+
+def test_phys_apply_golden():
+    from q1physrl_b200 import phys
+    g = harness.load_golden("phys_apply_n4096")
+    inputs = phys.Inputs(yaw=g["yaw"], pitch=g["pitch"], roll=g["roll"], fmove=g["fmove"],
+                         smove=g["smove"], button2=g["button2"], time_delta=g["time_delta"])
+    ps = phys.PlayerState(g["z_pos"], g["vel"], g["on_ground"], g["jump_released"])
+    before = [a.copy() for a in (ps.z_pos, ps.vel, ps.on_ground, ps.jump_released)]
+    out = phys.apply(inputs, ps)
+    for a, b in zip(before, (ps.z_pos, ps.vel, ps.on_ground, ps.jump_released)):
+        assert np.array_equal(a, b)                        # pure function: inputs untouched
+    assert out.vel.dtype == np.float32 and out.z_pos.dtype == np.float64
+    assert np.array_equal(out.z_pos, g["out_z_pos"])
+    assert np.array_equal(out.on_ground, g["out_on_ground"])
+    assert np.array_equal(out.jump_released, g["out_jump_released"])
+    assert np.abs(out.vel.astype(np.float64) - g["out_vel"]).max() <= VEL_ATOL
+    print("phys.apply bit-exact velocity fraction",
+          np.mean(out.vel == g["out_vel"]))
+
+
+@pytest.mark.parametrize("name", ["decoder_n64", "decoder_discrete_n64"])
+def test_decoder_golden(name):
+    from q1physrl_b200 import env as benv
+    g = harness.load_golden(name)
+    cfg = benv.Config(**g["config"])
+    dec = benv.ActionDecoder(cfg)
+    dec.vector_reset(g["yaw0"])
+    for t in range(g["keys"].shape[0]):
+        acts = np.concatenate([g["keys"][t].astype(np.float64), g["mouse"][t][:, None]], axis=1)
+        yaw, sm, fm, jp = dec.map(acts, g["z_vel"][t], g["time_remaining"][t])
+        assert np.array_equal(yaw, g["yaw"][t]) and np.array_equal(sm, g["smove"][t])
+        assert np.array_equal(fm, g["fmove"][t]) and np.array_equal(jp, g["jump"][t])
+        assert sm.dtype == np.int64 and jp.dtype == np.bool_
+    assert np.array_equal(dec._last_keys, g["final_last_keys"])
+    assert np.array_equal(dec._last_key_press_time, g["final_last_press"])
+
+
+CONFIGS = {
+    "params100m": dict(harness.PARAMS_100M),
+    "zero_autojump": dict(harness.PARAMS_100M, zero_start_prob=1.0, auto_jump=True),
+    "rules_1_72": dict(harness.PARAMS_100M, time_delta=1. / 72, action_range=float(np.float32(10.08))),
+    "discrete_speed": dict(harness.PARAMS_100M, smooth_keys=False, smove_max=700, time_delta=0.014,
+                           time_limit=5, discrete_yaw_steps=5, speed_reward=True),
+    "hover_nojump": dict(harness.PARAMS_100M, hover=True, allow_jump=False, key_press_delay=0.0),
+    "integer_delay": dict(harness.PARAMS_100M, key_press_delay=0.25, time_delta=0.0125, time_limit=4.0),
+    "noyaw": dict(harness.PARAMS_100M, allow_yaw=False, zero_start_prob=0.5),
+}
+
+
+def _oracle_auto_reset(o, done, epochs, seed, base):
+    """Reset the done envs of the oracle with the draws the CUDA kernels make."""
+    idx = np.nonzero(done)[0]
+    if idx.size == 0:
+        return
+    epochs[idx] += 1
+    for ep in np.unique(epochs[idx]):
+        mask = np.zeros(o.n, bool)
+        mask[idx[epochs[idx] == ep]] = True
+        o.reset_from_philox(seed, base, int(ep), mask)
+
+
+@pytest.mark.parametrize("cfg_name", list(CONFIGS))
+def test_free_running_vs_oracle(cfg_name):
+    """>= 720 ticks, 4096 envs, fused auto-reset, identical action streams; CUDA vs C oracle."""
+    n, ticks, seed, base = 4096, 760, 99, 1 << 33
+    cfg = dict(CONFIGS[cfg_name], num_envs=n)
+    from q1physrl_b200 import env as benv
+    e = benv.VectorPhysEnv(cfg, seed=seed, env_index_base=base, reuse_output_buffers=False)
+    nk = e._num_keys
+    o = qo.OracleEnv(cfg)
+    epochs = np.ones(n, np.int64)                          # vector_reset in __init__ was epoch 1
+    o.reset_from_philox(seed, base, 1)
+    st = e.get_state(harness.STATE_FIELDS)
+    for f in ("z_pos", "yaw", "time_remaining", "zero_start", "on_ground"):
+        assert np.array_equal(st[f], o.get_state()[f].astype(st[f].dtype)), f
+    assert np.abs(st["vel"] - o.vel).max() <= VEL_ATOL   # reset velocity goes through sincos too
+    o.vel[...] = st["vel"]
+    rng = np.random.default_rng(5)
+    vel_bad = vel_tot = 0
+    for t in range(ticks):
+        keys, mouse = harness.random_actions(cfg, rng, n, nk)
+        obs, rew, done, infos = e.vector_step((keys, mouse), auto_reset=True)
+        zs_before = o.zero_start.astype(bool).copy()
+        oobs, orew, odone = o.step(keys, mouse.astype(np.float64))
+        assert np.array_equal(done, odone), f"done differs at tick {t}"
+        assert np.array_equal(infos._zero_start, zs_before)
+        _oracle_auto_reset(o, odone, epochs, seed, base)
+        if odone.any():
+            oobs = o.observe()
+        st = e.get_state(harness.STATE_FIELDS)
+        assert np.array_equal(st["on_ground"], o.on_ground.astype(bool)), f"on_ground, tick {t}"
+        assert np.array_equal(st["z_pos"], o.z_pos) and np.array_equal(st["yaw"], o.yaw)
+        assert np.array_equal(st["time_remaining"], o.time_remaining)
+        assert np.array_equal(st["last_keys"], o.last_keys.astype(bool))
+        assert np.array_equal(st["jump_released"], o.jump_released.astype(bool))
+        assert np.array_equal(st["zero_start"], o.zero_start.astype(bool))
+        dv = np.abs(st["vel"].astype(np.float64) - o.vel)
+        assert dv.max() <= VEL_ATOL, f"velocity differs by {dv.max()} at tick {t}"
+        vel_bad += int(np.count_nonzero(st["vel"] != o.vel))
+        vel_tot += dv.size
+        live = ~odone
+        assert np.abs(rew[live].astype(np.float64) - orew[live]).max() <= VEL_ATOL
+        assert np.abs(obs.astype(np.float64) - oobs.astype(np.float32)).max() <= 0.081
+        if vel_bad == 0:
+            assert np.array_equal(obs, oobs.astype(np.float32)), f"obs differs at tick {t}"
+            assert np.array_equal(rew, orew)
+    print(cfg_name, "bit-exact f32 velocity stores:", 1 - vel_bad / vel_tot, "of", vel_tot)
+    assert vel_bad / vel_tot < 1e-5
+
+
+@pytest.mark.parametrize("stamps", [False, True], ids=["counters", "f64stamps"])
+@pytest.mark.parametrize("cfg_name", list(CONFIGS))
+def test_teacher_forced_single_tick(cfg_name, stamps):
+    """Random reachable states x random actions, one tick, 65536 envs: every output field."""
+    n = 65536
+    cfg = dict(CONFIGS[cfg_name], num_envs=n)
+    from q1physrl_b200 import env as benv
+    e = benv.VectorPhysEnv(cfg, seed=3, f64_key_stamps=stamps, reuse_output_buffers=False)
+    nk = e._num_keys
+    rng = np.random.default_rng(17)
+    o = qo.OracleEnv(cfg)
+    for rep in range(3):
+        st0 = harness.random_state(cfg, rng, n, nk)
+        if rep == 1:                                      # edge cases: zero velocity, zero wish
+            st0["vel"][: n // 2] = 0
+        e.set_state(st0)
+        o.set_state(st0)
+        keys, mouse = harness.random_actions(cfg, rng, n, nk)
+        if rep == 1:
+            keys[: n // 4] = 0
+        obs, rew, done, _ = e.vector_step((keys, mouse))
+        oobs, orew, odone = o.step(keys, mouse.astype(np.float64))
+        st = e.get_state(harness.STATE_FIELDS)
+        assert np.array_equal(done, odone)
+        for f in ("on_ground", "jump_released", "zero_start", "last_keys"):
+            assert np.array_equal(st[f], getattr(o, f).astype(bool)), f
+        for f in ("z_pos", "yaw", "time_remaining"):
+            assert np.array_equal(st[f], getattr(o, f)), f
+        if e.info.f64_stamps:
+            assert np.array_equal(st["last_press"], o.last_press)
+        dv = np.abs(st["vel"].astype(np.float64) - o.vel)
+        assert dv.max() <= VEL_ATOL
+        same = np.all(st["vel"] == o.vel, axis=1)
+        assert same.mean() > 1 - 1e-4
+        assert np.array_equal(obs[same], oobs.astype(np.float32)[same])
+        assert np.array_equal(rew[same], orew[same])
+        # the tick after: key timers / stamps must lead to the same decode decisions
+        keys2, mouse2 = harness.random_actions(cfg, rng, n, nk)
+        o.vel[...] = st["vel"]
+        e.vector_step((keys2, mouse2))
+        o.step(keys2, mouse2.astype(np.float64))
+        st2 = e.get_state(harness.STATE_FIELDS)
+        assert np.array_equal(st2["last_keys"], o.last_keys.astype(bool))
+        assert np.array_equal(st2["yaw"], o.yaw)
+
+
+def test_edge_cases_landing_jump_and_time_crossing():
+    """Landing tick, jump tick, t_rem crossing 0 and stepping past done, yaw of thousands of deg."""
+    from q1physrl_b200 import env as benv
+    n = 8
+    cfg = dict(harness.PARAMS_100M, num_envs=n, time_delta=1. / 72)
+    e = benv.VectorPhysEnv(cfg, seed=1, reuse_output_buffers=False)
+    o = qo.OracleEnv(cfg)
+    floor = np.float64(np.float32(24.03125))
+    st = dict(
+        vel=np.array([[0, 0, 0], [300, 0, -200], [0, 320, 0], [1e-3, 0, 0], [0, 0, 0],
+                      [500, 500, 0], [-50, 20, 100], [0, 0, 0]], np.float32),
+        z_pos=np.array([floor, floor + 1.0, floor, floor, floor, floor, 60.0, floor]),
+        yaw=np.array([90, 7234.5, -5000.25, 0, 90, 45, 1e5, 90.0]),
+        time_remaining=np.array([10, 5, 1. / 72, 1e-9, 0.0, -3.0, 2.0, 10.0]),
+        on_ground=np.array([1, 0, 1, 1, 1, 1, 0, 1], bool),
+        jump_released=np.array([1, 1, 1, 1, 0, 1, 1, 1], bool),
+        zero_start=np.zeros(n, bool), last_keys=np.zeros((n, 4), bool),
+        last_press=np.full((n, 4), -0.3))
+    e.set_state(st)
+    o.set_state(st)
+    keys = np.array([[0, 0, 1, 1]] * n, np.uint8)
+    mouse = np.array([0, 10, -10, 3, 0, 0, 1, 0], np.float32)
+    for t in range(5):
+        obs, rew, done, _ = e.vector_step((keys, mouse))
+        oobs, orew, odone = o.step(keys, mouse.astype(np.float64))
+        s = e.get_state(harness.STATE_FIELDS)
+        assert np.array_equal(done, odone)
+        assert np.array_equal(s["on_ground"], o.on_ground.astype(bool))
+        assert np.array_equal(s["z_pos"], o.z_pos)
+        assert np.array_equal(s["time_remaining"], o.time_remaining)
+        assert np.abs(s["vel"].astype(np.float64) - o.vel).max() <= VEL_ATOL
+        assert np.abs(obs - oobs.astype(np.float32)).max() <= 1e-6
+        keys[:, 3] ^= 1
+
+
+def test_shards_equal_single_handle():
+    """Two half-size handles with env_index_base offsets reproduce one full-size handle."""
+    from q1physrl_b200 import env as benv
+    n = 8192
+    cfg = dict(harness.PARAMS_100M, num_envs=n)
+    full = benv.VectorPhysEnv(cfg, seed=11, reuse_output_buffers=False)
+    half = dict(cfg, num_envs=n // 2)
+    a = benv.VectorPhysEnv(half, seed=11, env_index_base=0, reuse_output_buffers=False)
+    b = benv.VectorPhysEnv(half, seed=11, env_index_base=n // 2, reuse_output_buffers=False)
+    rng = np.random.default_rng(2)
+    for t in range(800):
+        keys, mouse = harness.random_actions(cfg, rng, n, 4)
+        of, rf, df, _ = full.vector_step((keys, mouse), auto_reset=True)
+        oa, ra, da, _ = a.vector_step((keys[: n // 2], mouse[: n // 2]), auto_reset=True)
+        ob, rb, db, _ = b.vector_step((keys[n // 2:], mouse[n // 2:]), auto_reset=True)
+        assert np.array_equal(of, np.concatenate([oa, ob]))
+        assert np.array_equal(rf, np.concatenate([ra, rb]))
+        assert np.array_equal(df, np.concatenate([da, db]))
+    sf = full.get_state()
+    sa, sb = a.get_state(), b.get_state()
+    for f in harness.STATE_FIELDS:
+        assert np.array_equal(sf[f], np.concatenate([sa[f], sb[f]])), f
+
+
+@pytest.mark.parametrize("policy", ["random", "strafe_jump"])
+def test_rollout_kernel_vs_oracle(policy):
+    """The multi-tick in-register rollout equals tick-by-tick oracle stepping on the same policy
+    stream, including resets and the on-device episode metrics."""
+    from q1physrl_b200 import env as benv
+    n, ticks, seed, base, pseed = 2048, 1500, 21, 12345, 77
+    cfg = dict(harness.PARAMS_100M, num_envs=n, zero_start_prob=0.3)
+    e = benv.VectorPhysEnv(cfg, seed=seed, env_index_base=base, track_returns=True)
+    o = qo.OracleEnv(cfg)
+    epochs = np.ones(n, np.int64)
+    o.reset_from_philox(seed, base, 1)
+    o.vel[...] = e.get_state(("vel",))["vel"]
+    pid = {"random": 0, "strafe_jump": 1}[policy]
+    ret = np.zeros(n)
+    rsum = np.zeros(n, np.float32)
+    zs_returns, all_returns = [], []
+    done_ticks = 0
+    for chunk in (700, 800):
+        obs_t, rsum_t = e.rollout(policy, chunk, policy_seed=pseed)
+        rsum[:] = 0
+        for t in range(done_ticks, done_ticks + chunk):
+            keys, mouse = qo.policy_actions(cfg, pid, pseed, base, n, t)
+            zs = o.zero_start.astype(bool).copy()
+            _, rew, done = o.step(keys, mouse)
+            rsum += rew
+            ret += rew.astype(np.float64)
+            if done.any():
+                all_returns.extend(ret[done])
+                zs_returns.extend(ret[done & zs])
+                ret[done] = 0
+                _oracle_auto_reset(o, done, epochs, seed, base)
+        done_ticks += chunk
+        st = e.get_state(harness.STATE_FIELDS)
+        for f in ("z_pos", "yaw", "time_remaining"):
+            assert np.array_equal(st[f], getattr(o, f)), f
+        for f in ("on_ground", "jump_released", "zero_start", "last_keys"):
+            assert np.array_equal(st[f], getattr(o, f).astype(bool)), f
+        assert np.abs(st["vel"].astype(np.float64) - o.vel).max() <= VEL_ATOL
+        assert np.abs(obs_t.cpu().numpy() - o.observe().astype(np.float32)).max() <= 1e-6
+        assert np.abs(rsum_t.cpu().numpy() - rsum).max() <= 1e-3
+    m = e.metrics()
+    assert m["episodes"] == len(all_returns) and m["zero_start_episodes"] == len(zs_returns)
+    assert abs(m["episode_reward_sum"] - np.sum(all_returns)) <= 1e-6 * max(1, abs(np.sum(all_returns)))
+    assert abs(m["zero_start_total_reward_sum"] - np.sum(zs_returns)) <= 1e-6 * max(1, abs(np.sum(zs_returns)))
+    assert abs(m["episode_reward_max"] - np.max(all_returns)) <= 1e-9 * abs(np.max(all_returns))
+
+
+def test_step_metrics_and_masked_reset():
+    """track_returns through q1_step + caller-driven reset_masked (the RLLib flow, batched)."""
+    from q1physrl_b200 import env as benv
+    n = 4096
+    cfg = dict(harness.PARAMS_100M, num_envs=n, zero_start_prob=0.5, time_limit=1.0)
+    e = benv.VectorPhysEnv(cfg, seed=4, track_returns=True, reuse_output_buffers=False)
+    rng = np.random.default_rng(9)
+    ret = np.zeros(n)
+    fin, zfin = [], []
+    for t in range(200):
+        keys, mouse = harness.random_actions(cfg, rng, n, 4)
+        obs, rew, done, infos = e.vector_step((keys, mouse))
+        ret += rew.astype(np.float64)
+        if done.any():
+            zs = np.asarray(infos._zero_start)
+            fin.extend(ret[done])
+            zfin.extend(ret[done & zs])
+            ret[done] = 0
+            new_obs = e.reset_masked(done, obs.copy())
+            assert np.array_equal(new_obs[~done], obs[~done])
+            assert np.array_equal(new_obs[done], e._get_obs()[done])
+    m = e.metrics()
+    assert m["episodes"] == len(fin) > 0 and m["zero_start_episodes"] == len(zfin) > 0
+    assert abs(m["episode_reward_sum"] - np.sum(fin)) < 1e-6 * max(1.0, abs(np.sum(fin)))
+    assert abs(m["zero_start_total_reward_mean"] - np.mean(zfin)) < 1e-9 * max(1.0, abs(np.mean(zfin)))
+
+
+def test_full_size_properties():
+    """BASELINE config 3 at full size (2^20 envs, zero start + auto jump): size-independent
+    properties -- phase-locked episodes all end on tick 721, per-tick reward checksum equals the
+    oracle's on a strided sample, rollout kernel == tick-by-tick stepping."""
+    import torch
+    from q1physrl_b200 import env as benv
+    n = 1 << 20
+    cfg = dict(harness.PARAMS_100M, num_envs=n, zero_start_prob=1.0, auto_jump=True)
+    e = benv.VectorPhysEnv(cfg, seed=8)
+    sample = np.arange(0, n, 4099)
+    o = qo.OracleEnv(dict(cfg, num_envs=sample.size))
+    st = e.get_state(harness.STATE_FIELDS)
+    o.set_state({f: st[f][sample] for f in harness.STATE_FIELDS})
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dev = torch.device("cuda", 0)
+    for t in range(725):
+        keys = torch.randint(0, 2, (n, 3), generator=g, device=dev, dtype=torch.uint8)
+        mouse = (torch.rand(n, generator=g, device=dev, dtype=torch.float32) * 20 - 10)
+        obs, rew, done, zs = e.step_tensors(keys, mouse)
+        ndone = int(done.sum().item())
+        assert ndone == (n if t >= 720 else 0), (t, ndone)
+        if t % 60 == 0 or t >= 719:
+            k_s, m_s = keys.cpu().numpy()[sample], mouse.cpu().numpy()[sample]
+            oobs, orew, odone = o.step(k_s, m_s.astype(np.float64))
+            assert np.abs(obs.cpu().numpy()[sample] - oobs.astype(np.float32)).max() <= 1e-6
+            assert np.abs(rew.cpu().numpy()[sample].astype(np.float64) - orew).max() <= VEL_ATOL
+        else:
+            o.step(keys.cpu().numpy()[sample], mouse.cpu().numpy()[sample].astype(np.float64))
+    assert bool(zs.all().item())
+    # rollout kernel vs stepping with the same policy stream, at full size, via state checksums
+    a = benv.VectorPhysEnv(cfg, seed=8)
+    b = benv.VectorPhysEnv(cfg, seed=8)
+    a.rollout("random", 40, policy_seed=5)
+    for t in range(40):
+        keys, mouse = qo.policy_actions(cfg, 0, 5, 0, n, t)
+        b.vector_step((keys, mouse.astype(np.float32)), auto_reset=True)
+    sa, sb = a.get_state(), b.get_state()
+    for f in harness.STATE_FIELDS:
+        assert np.array_equal(sa[f], sb[f]), f

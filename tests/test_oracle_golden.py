@@ -1,0 +1,88 @@
+"""CPU: the C oracle against the golden fixtures recorded from the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle (the reference holds
+no golden vectors of its own)."""
+import numpy as np
+import pytest
+
+import harness
+from oracle import q1_oracle as qo
+
+
+@pytest.mark.parametrize("name", harness.ENV_FIXTURES)
+def test_oracle_replays_reference_bit_exactly(name):
+    g = harness.load_golden(name)
+    stats = harness.replay(harness.OracleAdapter(g["config"]), g, vel_atol=0.0)
+    assert stats["vel_mismatch"] == 0 and stats["obs_mismatch"] == 0 and stats["reward_mismatch"] == 0
+
+
+def test_known_answers():
+    """SURVEY.md 8(c) known-answer values, as recorded from the reference."""
+    g = harness.load_golden("dummy_trainer")
+    assert g["keys"].shape[0] == 358                       # episode length, dt=0.014, TL=5
+    assert g["done"][-1].all() and not g["done"][:-1].any()
+    assert abs(float(g["reward"].astype(np.float64).sum()) - 226.97066) < 1e-3
+    np.testing.assert_allclose(g["obs0"][0], [1.0, 1.0, 0.32875, 0.0, 0.0, 0.0], atol=1e-12)
+    np.testing.assert_allclose(g["obs"][0][0], [0.9972, 1.0, 0.325, 0.0, 0.08, -0.08], atol=1e-12)
+    np.testing.assert_allclose(g["obs"][-1][0], [-0.0024, -4.73333333, 0.57125, -0.4, 1.28, 0.64],
+                               atol=1e-8)
+    g = harness.load_golden("zero_autojump_n16")          # dt=0.013888888888888 -> 721 ticks
+    first_done = np.argmax(g["done"], axis=0)
+    assert (first_done == 720).all()
+    g = harness.load_golden("strafe_jump_n8")              # dt=1/72 -> 720 ticks
+    assert (np.argmax(g["done"], axis=0) == 719).all()
+
+
+def test_oracle_phys_apply_matches_reference():
+    g = harness.load_golden("phys_apply_n4096")
+    z, vel, og, jr = qo.phys_apply(g["yaw"], g["pitch"], g["roll"], g["fmove"], g["smove"],
+                                   g["button2"], g["time_delta"], g["z_pos"], g["vel"],
+                                   g["on_ground"], g["jump_released"])
+    assert np.array_equal(z, g["out_z_pos"])
+    assert np.array_equal(vel, g["out_vel"])
+    assert np.array_equal(og, g["out_on_ground"])
+    assert np.array_equal(jr, g["out_jump_released"])
+
+
+@pytest.mark.parametrize("name", ["decoder_n64", "decoder_discrete_n64"])
+def test_oracle_decoder_matches_reference(name):
+    g = harness.load_golden(name)
+    cfg, nk = g["config"], int(g["num_keys"])
+    n = g["yaw0"].shape[0]
+    last_keys = np.zeros((n, nk), np.uint8)
+    last_press = np.full((n, nk), -cfg["key_press_delay"], np.float64)
+    yaw = g["yaw0"].copy()
+    for t in range(g["keys"].shape[0]):
+        y, sm, fm, jp = qo.decode(cfg, last_keys, last_press, yaw, g["keys"][t], g["mouse"][t],
+                                  g["z_vel"][t], g["time_remaining"][t])
+        assert np.array_equal(y, g["yaw"][t]) and np.array_equal(sm, g["smove"][t])
+        assert np.array_equal(fm, g["fmove"][t]) and np.array_equal(jp, g["jump"][t])
+    assert np.array_equal(last_keys.astype(bool), g["final_last_keys"])
+    assert np.array_equal(last_press, g["final_last_press"])
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    assert qo.philox4x32(0, 0, 0, 0, 0, 0) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert qo.philox4x32(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == \
+        (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert qo.philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_reset_distribution_quirks():
+    """env.py:439-446: uniform(x) is U(x, 1): time in (1, TL], speed in (1, max], angle in (1, 2pi]."""
+    cfg = dict(harness.PARAMS_100M, num_envs=20000, zero_start_prob=0.25)
+    o = qo.OracleEnv(cfg)
+    o.reset_from_philox(seed=7, env_index_base=0, epoch=1)
+    zs = o.zero_start.astype(bool)
+    assert abs(zs.mean() - 0.25) < 0.02
+    assert np.all(o.time_remaining[zs] == 10) and np.all(o.yaw[zs] == 90)
+    assert np.all(o.vel[zs, :2] == 0)
+    t = o.time_remaining[~zs]
+    assert t.min() > 1 and t.max() <= 10 and abs(t.mean() - 5.5) < 0.1
+    sp = np.hypot(o.vel[~zs, 0].astype(np.float64), o.vel[~zs, 1])
+    assert sp.min() > 0.99 and sp.max() <= 700.001 and abs(sp.mean() - 350.5) < 8
+    ang = np.arctan2(o.vel[~zs, 1], o.vel[~zs, 0]) % (2 * np.pi)
+    assert ang.min() > 0.99                                   # nothing in [0, 1) rad
+    assert np.all(o.z_pos == np.float64(np.float32(32.843201))) and np.all(o.vel[:, 2] == -12)
+    assert not o.on_ground.any() and o.jump_released.all()
