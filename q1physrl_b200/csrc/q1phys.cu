@@ -472,6 +472,10 @@ int derive_params(const q1_config &c, Params &P, bool &counters_exact)
     double q = c.key_press_delay / c.time_delta;
     double frac = std::fabs(q - std::nearbyint(q));
     counters_exact = (c.key_press_delay == 0.0) || (frac > 1e-6 && q < 254.0);
+    /* A fresh episode must satisfy "elapsed" at once, i.e. time_limit - t_rem >= -delay + delay = 0.
+     * Resets draw t_rem = uniform(low=time_limit, high=1.0) (env:439, 466), which stays <= time_limit
+     * only for time_limit >= 1; below that the f64 stamps are kept. */
+    counters_exact = counters_exact && c.time_limit >= 1.0;
     P.delay_ticks = counters_exact ? (int32_t)std::ceil(q) : 0;
     return Q1_OK;
 }

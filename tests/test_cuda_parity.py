@@ -127,8 +127,7 @@ def test_free_running_vs_oracle(cfg_name):
         assert dv.max() <= VEL_ATOL, f"velocity differs by {dv.max()} at tick {t}"
         vel_bad += int(np.count_nonzero(st["vel"] != o.vel))
         vel_tot += dv.size
-        live = ~odone
-        assert np.abs(rew[live].astype(np.float64) - orew[live]).max() <= VEL_ATOL
+        assert np.abs(rew.astype(np.float64) - orew).max() <= VEL_ATOL
         assert np.abs(obs.astype(np.float64) - oobs.astype(np.float32)).max() <= 0.081
         if vel_bad == 0:
             assert np.array_equal(obs, oobs.astype(np.float32)), f"obs differs at tick {t}"
