@@ -37,7 +37,9 @@ enum {
 /* q1_create flags */
 enum {
     Q1_F_TRACK_RETURNS = 1u << 0,   /* keep a per-env f64 episode return + on-device episode metrics */
-    Q1_F_FORCE_F64_STAMPS = 1u << 1 /* keep env:200 key time stamps in f64 even when u8 tick counters are exact */
+    Q1_F_FORCE_F64_STAMPS = 1u << 1, /* keep env:200 key time stamps in f64 even when u8 tick counters are exact */
+    Q1_F_IEEE_DIVISION = 1u << 2    /* divide with the CUDA IEEE intrinsics instead of the (equally exact,
+                                       branch-free) reciprocal-multiply sequences: slower, for self-checks */
 };
 
 /* Element type of the `mouse` array handed to q1_step / q1_step_host. */
@@ -211,6 +213,13 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n,
                    const uint8_t *keys, const double *mouse,
                    const float *z_vel, const double *time_remaining,
                    int64_t *smove, int64_t *fmove, uint8_t *jump);
+
+/* Self-check of the branch-free reciprocal-multiply division sequences the kernels use against the
+ * CUDA IEEE intrinsics, on ~`samples` random operand pairs per class (bit comparison):
+ *   [0] reciprocal  [1] a / variable b  [2] a / constant  [3] wish_vel / wish_speed range
+ *   [4] new_speed / speed range  [5] the f32 observation quotients, exhaustive.
+ * Every count must be 0. */
+int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[6]);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ c_i64, c_u64, c_i32, c_u32, c_int = (ctypes.c_int64, ctypes.c_uint64, ctypes.c_i
 c_double, c_void_p, c_char_p = ctypes.c_double, ctypes.c_void_p, ctypes.c_char_p
 
 Q1_OK, Q1_EINVAL, Q1_ECUDA, Q1_ENODEV, Q1_ENOMEM = 0, -1, -2, -3, -4
-Q1_F_TRACK_RETURNS, Q1_F_FORCE_F64_STAMPS = 1, 2
+Q1_F_TRACK_RETURNS, Q1_F_FORCE_F64_STAMPS, Q1_F_IEEE_DIVISION = 1, 2, 4
 Q1_MOUSE_F32, Q1_MOUSE_I32, Q1_MOUSE_F64 = 0, 1, 2
 Q1_POLICY_RANDOM, Q1_POLICY_STRAFE_JUMP = 0, 1
 Q1_ABI_VERSION = 1
@@ -111,6 +111,7 @@ SIGNATURES = {
     "q1_get_metrics_host": (c_int, [c_void_p, c_int, ctypes.POINTER(Q1Metrics)]),
     "q1_phys_apply": (c_int, [c_int, c_i64] + [c_void_p] * 15 + [c_void_p]),
     "q1_phys_apply_host": (c_int, [c_int, c_i64] + [c_void_p] * 15),
+    "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 6)]),
     "q1_decode_host": (c_int, [ctypes.POINTER(Q1Config), c_int, c_i64] + [c_void_p] * 10),
 }
 

@@ -61,10 +61,15 @@ struct Params {
     double fmove_half, fmove_full; /* trunc(f64(f32(fmove_max)) * {0.5, 1})   env:261,269 */
     double smove_half, smove_full; /* trunc(f64(f32(smove_max)) * {0.5, 1})   env:260,269 */
     double zero_start_prob, yaw_lo, yaw_hi, max_initial_speed;
+    /* RN(1/b) of the constant divisors, for div_const() */
+    double rcp_action_range, rcp_yaw_steps, rcp_time_limit;
+    double fmove_tab[3];    /* fmove for twice-the-smoothed-forward-key = 0, 1, 2 */
+    double smove_tab[5];    /* smove for twice-(right - left) + 2 = 0 .. 4 */
     float dt_f32;           /* f32(time_delta) for the reward      env:500-503 */
     int32_t num_keys;       /* env:206-207 */
     int32_t delay_ticks;    /* ceil(key_delay / dt) (counter mode) */
     int32_t allow_yaw, discrete_yaw, speed_reward, hover, smooth_keys, auto_jump, allow_jump;
+    int32_t ieee_div;       /* use the IEEE division intrinsics instead of the reciprocal sequences */
     /* persistent state, struct of arrays */
     float *vx, *vy, *vz;
     double *z, *yaw, *trem;
@@ -93,6 +98,56 @@ __device__ __forceinline__ double sub64(double a, double b) { return __dsub_rn(a
 __device__ __forceinline__ double div64(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ float mul32(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add32(float a, float b) { return __fadd_rn(a, b); }
+
+__device__ __forceinline__ double fma64(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+/* Correctly rounded a / b for a constant divisor b with y = RN(1 / b) precomputed on the host.
+ * Markstein's theorem: with y the correctly rounded reciprocal and q a faithful quotient,
+ * RN(q + RN(a - b q) y) = RN(a / b).  The first correction makes q faithful (RN(a y) alone can be
+ * 2 ulp off), the second makes it exact.  Five FP64-pipe operations, no branches, no special-case
+ * path: valid for finite a with |a / b| comfortably inside the normal range (|a| in [2^-900, 2^900]
+ * or zero), which covers everything this path divides. */
+__device__ __forceinline__ double div_const(double a, double b, double y)
+{
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+
+/* RN(1 / b) for a normal b well inside the exponent range: hardware seed (2^-23), one cubic and
+ * one Markstein step.  q1_selftest_division checks this bit for bit against __drcp_rn / __ddiv_rn
+ * on 10^10 random operands, one in 64 of them with a significand of all ones. */
+__device__ __forceinline__ double rcp_rn(double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = __fma_rn(-b, y, 1.0);
+    double t = __fma_rn(e, e, e);
+    y = __fma_rn(y, t, y);            /* relative error ~2^-69 before rounding */
+    e = __fma_rn(-b, y, 1.0);
+    y = __fma_rn(y, e, y);            /* RN(1 / b) ... */
+    /* ... except for a significand of all ones, where the last step lands exactly on a tie
+     * (Markstein's one exception, probability 2^-52): take the IEEE intrinsic there. */
+    const bool all_ones = (__double2loint(b) == -1) & ((__double2hiint(b) & 0xFFFFF) == 0xFFFFF);
+    if (__builtin_expect(all_ones, 0))
+        y = __drcp_rn(b);
+    return y;
+}
+
+/* a / b given y = RN(1 / b) (same theorem as div_const). */
+__device__ __forceinline__ double div_rcp(double a, double b, double y) { return div_const(a, b, y); }
+
+/* f32 quotient a / b, b a constant with y = RN32(1 / b); a exactly representable, |a| < 2^24. */
+__device__ __forceinline__ float div_const32(float a, float b, float y)
+{
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
 
 /* ------------------------------------------------------------------ Philox4x32-10 ------------ */
 
@@ -126,31 +181,44 @@ __device__ __forceinline__ double unit53(uint32_t a, uint32_t b)
  * representable in f32 and the divisor is 200 or 100, so the quotient is either exact or has a
  * binary expansion of period <= 20: it can never sit within 2^-53 of an f32 rounding boundary, and
  * rounding the exact quotient once to f32 equals rounding the f64 quotient to f32. */
+template <bool LEAN>
 __device__ __forceinline__ float obs_vel(float v)
 {
     float q = truncf(mul32(v, 0.0625f)); /* (v / 16).astype(int): exact scaling, toward zero */
-    if (fabsf(q) < 1048576.0f)
+    if (fabsf(q) < 1048576.0f) {
+        if (LEAN)
+            return div_const32(mul32(q, 16.0f), 200.0f, 1.0f / 200.0f);
         return __fdiv_rn(mul32(q, 16.0f), 200.0f);
+    }
     return __double2float_rn(div64(mul64((double)(long long)q, 16.0), 200.0));
 }
 
+template <bool LEAN>
 __device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6])
 {
-    o[0] = __double2float_rn(div64(e.trem, P.time_limit));
-    o[1] = __double2float_rn(div64(e.yaw, 90.0));
+    if (LEAN) {
+        o[0] = __double2float_rn(div_const(e.trem, P.time_limit, P.rcp_time_limit));
+        o[1] = __double2float_rn(div_const(e.yaw, 90.0, 1.0 / 90.0));
+    } else {
+        o[0] = __double2float_rn(div64(e.trem, P.time_limit));
+        o[1] = __double2float_rn(div64(e.yaw, 90.0));
+    }
     double r = rint(mul64(e.z, 8.0)); /* np.round: half to even (env:390) */
-    if (fabs(r) < 16777216.0)
-        o[2] = __fdiv_rn(mul32((float)r, 0.125f), 100.0f);
-    else
+    if (fabs(r) < 16777216.0) {
+        float zq = mul32((float)r, 0.125f);
+        o[2] = LEAN ? div_const32(zq, 100.0f, 1.0f / 100.0f) : __fdiv_rn(zq, 100.0f);
+    } else {
         o[2] = __double2float_rn(div64(mul64(r, 0.125), 100.0));
-    o[3] = obs_vel(e.vx);
-    o[4] = obs_vel(e.vy);
-    o[5] = obs_vel(e.vz);
+    }
+    o[3] = obs_vel<LEAN>(e.vx);
+    o[4] = obs_vel<LEAN>(e.vy);
+    o[5] = obs_vel<LEAN>(e.vz);
 }
 
 /* ------------------------------------------------------------------ phys.apply, one row ------ */
 
 /* phys:184-197 for one env.  (fx, rx, fy, ry) is the 2x2 block of _angle_vectors (phys:56-66). */
+template <bool LEAN>
 __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, double &z,
                                           bool &on_ground, bool &jump_released,
                                           double fx, double rx, double fy, double ry,
@@ -162,11 +230,26 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
     /* phys:95-103.  einsum = mul, mul, add; norm = sqrt(x*x + y*y). */
     double wx = add64(mul64(fx, fmove), mul64(rx, smove));
     double wy = add64(mul64(fy, fmove), mul64(ry, smove));
-    double ws = __dsqrt_rn(add64(mul64(wx, wx), mul64(wy, wy)));
-    double wdx = wx, wdy = wy;
-    if (ws > 0.0) {
-        wdx = div64(wx, ws);
-        wdy = div64(wy, ws);
+    double ws2 = add64(mul64(wx, wx), mul64(wy, wy));
+    double ws, wdx = wx, wdy = wy;
+    if (LEAN) {
+        /* keep sqrt and the reciprocal on their branch-free fast paths: a zero (no key held) is
+         * replaced by 1 for the arithmetic and selected back afterwards */
+        const bool moving = ws2 > 0.0;
+        double arg = moving ? ws2 : 1.0;
+        asm("" : "+d"(arg)); /* keep the select in front of sqrt (else sqrt(0) takes the slow path) */
+        ws = __dsqrt_rn(arg);
+        double y = rcp_rn(ws);
+        double qx = div_rcp(wx, ws, y), qy = div_rcp(wy, ws, y);
+        ws = moving ? ws : ws2;
+        wdx = moving ? qx : wx;
+        wdy = moving ? qy : wy;
+    } else {
+        ws = __dsqrt_rn(ws2);
+        if (ws > 0.0) {
+            wdx = div64(wx, ws);
+            wdy = div64(wy, ws);
+        }
     }
     double wish_speed = ws < (double)kMaxSpeed ? ws : (double)kMaxSpeed;
     if (ws != ws)
@@ -182,7 +265,9 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
         if (!(new_speed > 0.0))
             new_speed = 0.0;
         if (speed > 0.0f) {
-            double ratio = div64(new_speed, (double)speed);
+            double sd = (double)speed;
+            double ratio = (LEAN && speed > 1e-30f) ? div_rcp(new_speed, sd, rcp_rn(sd))
+                                                    : div64(new_speed, sd);
             hx = mul64(hx, ratio);
             hy = mul64(hy, ratio);
         }
@@ -221,7 +306,7 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
 /* env.VectorPhysEnv.vector_step (env:482-510) for one env: hover override, ActionDecoder.map
  * (env:225-269), phys.apply, reward, time, done.  keybits: bit k = key action k; mouse: the raw
  * mouse action as f64 (continuous value or the discrete index). */
-template <bool STAMPS>
+template <bool STAMPS, bool LEAN>
 __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, double mouse,
                                      float &reward, bool &done)
 {
@@ -233,44 +318,50 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
     /* ---- ActionDecoder.map ---- */
     double mouse_x = 0.0;
     if (P.allow_yaw) {
-        if (!P.discrete_yaw)
-            mouse_x = div64(mul64(mouse, P.max_yaw_delta), P.action_range);               /* env:236 */
-        else
-            mouse_x = div64(mul64(sub64(mouse, P.yaw_steps), P.max_yaw_delta), P.yaw_steps); /* env:238 */
-    }
-
-    const double now = sub64(P.time_limit, e.trem); /* env:241, 246 */
-    uint32_t last = (e.flags >> F_LAST_KEY_SHIFT) & 0xFu;
-    uint32_t down = 0;
-    uint32_t timers = e.timers;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (k < P.num_keys) {
-            bool elapsed;
-            if (STAMPS) {
-                elapsed = now >= add64(e.stamp[k], P.key_delay);                         /* env:241-242 */
-            } else {
-                /* ticks-until-allowed counter: one tick has passed since the last test */
-                uint32_t r = (timers >> (8 * k)) & 0xFFu;
-                r = r ? r - 1u : 0u;
-                timers = (timers & ~(0xFFu << (8 * k))) | (r << (8 * k));
-                elapsed = r == 0u;
-            }
-            uint32_t lk = (last >> k) & 1u;
-            uint32_t d = ((keybits >> k) & 1u) & ((elapsed ? 1u : 0u) | lk);            /* env:243 */
-            if (d & ~lk & 1u) {                                                         /* env:244-248 */
-                if (STAMPS)
-                    e.stamp[k] = now;
-                else
-                    timers = (timers & ~(0xFFu << (8 * k))) | ((uint32_t)P.delay_ticks << (8 * k));
-            }
-            down |= d << k;
+        if (!P.discrete_yaw) {                                                           /* env:236 */
+            double t = mul64(mouse, P.max_yaw_delta);
+            mouse_x = LEAN ? div_const(t, P.action_range, P.rcp_action_range) : div64(t, P.action_range);
+        } else {                                                                         /* env:238 */
+            double t = mul64(sub64(mouse, P.yaw_steps), P.max_yaw_delta);
+            mouse_x = LEAN ? div_const(t, P.yaw_steps, P.rcp_yaw_steps) : div64(t, P.yaw_steps);
         }
     }
-    e.timers = timers;
 
-    /* env:251-261: smoothed keys in {0, 1/2, 1}; fmove/smove are truncations of f32(max) * that,
-     * i.e. one of five values fixed by the config. */
+    const uint32_t key_mask = (1u << P.num_keys) - 1u;
+    const uint32_t last = (e.flags >> F_LAST_KEY_SHIFT) & 0xFu;
+    uint32_t elapsed;   /* bit k: key k may be pressed again (env:241-242) */
+    double now = 0.0;
+    if (STAMPS) {
+        now = sub64(P.time_limit, e.trem);
+        elapsed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < P.num_keys)
+                elapsed |= (now >= add64(e.stamp[k], P.key_delay) ? 1u : 0u) << k;
+    } else {
+        /* four u8 "ticks until allowed" counters in one word: saturating decrement (a tick has
+         * passed since the last test), then gather the four is-zero bits */
+        uint32_t t = e.timers;
+        uint32_t nz = ((t | ((t | 0x80808080u) - 0x01010101u)) >> 7) & 0x01010101u; /* byte != 0 */
+        t -= nz;
+        uint32_t z = (((t | ((t | 0x80808080u) - 0x01010101u)) >> 7) & 0x01010101u) ^ 0x01010101u;
+        elapsed = (z * 0x01020408u) >> 24;
+        e.timers = t;
+    }
+    const uint32_t down = keybits & (elapsed | last) & key_mask;                        /* env:243 */
+    const uint32_t rising = down & ~last;                                               /* env:244 */
+    if (STAMPS) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((rising >> k) & 1u)
+                e.stamp[k] = now;                                                        /* env:246 */
+    } else {
+        uint32_t m = ((rising * 0x00204081u) & 0x01010101u) * 0xFFu;  /* bit k -> byte k mask */
+        e.timers = (e.timers & ~m) | (((uint32_t)P.delay_ticks * 0x01010101u) & m);
+    }
+
+    /* env:251-261: smoothed keys in {0, 1/2, 1}; fmove / smove are truncations of f32(max) * that,
+     * i.e. one of three / five values fixed by the config (tabulated in Params). */
     int f2, s2; /* twice the smoothed forward key, twice (right - left) */
     {
         int dl = (down >> KEY_LEFT) & 1, dr = (down >> KEY_RIGHT) & 1, df = (down >> KEY_FORWARD) & 1;
@@ -283,11 +374,8 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
             s2 = 2 * (dr - dl);
         }
     }
-    double fmove = f2 == 2 ? P.fmove_full : (f2 == 1 ? P.fmove_half : 0.0);
-    int as2 = s2 < 0 ? -s2 : s2;
-    double smove = as2 == 2 ? P.smove_full : (as2 == 1 ? P.smove_half : 0.0);
-    if (s2 < 0)
-        smove = -smove;
+    const double fmove = P.fmove_tab[f2];
+    const double smove = P.smove_tab[s2 + 2];
 
     bool jump;
     if (P.auto_jump)
@@ -302,10 +390,13 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
 
     /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
     double sy, cy;
-    sincos(div64(mul64(e.yaw, kPi), 180.0), &sy, &cy);                                    /* phys:58-59 */
+    {
+        double t = mul64(e.yaw, kPi);                                                    /* phys:58-59 */
+        sincos(LEAN ? div_const(t, 180.0, 1.0 / 180.0) : div64(t, 180.0), &sy, &cy);
+    }
     bool og = e.flags & F_ON_GROUND, jr = e.flags & F_JUMP_RELEASED;
-    move_body(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt, P.accel_dt,
-              P.gravity_dt);
+    move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,
+                    P.accel_dt, P.gravity_dt);
     e.flags = (e.flags & ~(F_ON_GROUND | F_JUMP_RELEASED)) | (og ? F_ON_GROUND : 0u) |
               (jr ? F_JUMP_RELEASED : 0u);
 

@@ -87,14 +87,17 @@ __device__ __forceinline__ void store_obs(float *obs, int64_t i, const float o[6
  * last_keys in {0,1} means `&` only ever sees bit 0). */
 __device__ __forceinline__ uint32_t load_keys(const uint8_t *keys, int64_t i, int nk)
 {
-    if (nk == 4 && (reinterpret_cast<uintptr_t>(keys) & 3u) == 0) {
-        uint32_t w = reinterpret_cast<const uint32_t *>(keys)[i];
-        return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
+    if (nk == 4) {
+        if ((reinterpret_cast<uintptr_t>(keys) & 3u) == 0) {
+            uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(keys) + i);
+            return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
+        }
+        const uint8_t *k = keys + 4 * i;
+        return (__ldg(k) & 1u) | ((__ldg(k + 1) & 1u) << 1) | ((__ldg(k + 2) & 1u) << 2) |
+               ((__ldg(k + 3) & 1u) << 3);
     }
-    uint32_t m = 0;
-    for (int k = 0; k < nk; k++)
-        m |= (uint32_t)(keys[i * nk + k] & 1u) << k;
-    return m;
+    const uint8_t *k = keys + 3 * i;
+    return (__ldg(k) & 1u) | ((__ldg(k + 1) & 1u) << 1) | ((__ldg(k + 2) & 1u) << 2);
 }
 
 __device__ __forceinline__ double load_mouse(const void *mouse, int kind, int64_t i)
@@ -142,7 +145,7 @@ __device__ __forceinline__ void report_episodes(const Params &P, bool finished, 
 
 /* -- env.VectorPhysEnv.vector_step (env:482-510): one lockstep tick ---------------------------- */
 
-template <bool STAMPS, bool TRACK>
+template <bool STAMPS, bool TRACK, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
        const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
@@ -162,7 +165,7 @@ k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             m = load_mouse(mouse, mouse_kind, i);
         float r;
         bool d;
-        tick<STAMPS>(P, e, keybits, m, r, d);
+        tick<STAMPS, LEAN>(P, e, keybits, m, r, d);
         zs = e.flags & F_ZERO_START;
         if (TRACK) {
             ret = add64(P.ep_return[i], (double)r);
@@ -184,7 +187,7 @@ k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             P.ep_return[i] = ret;
         }
         float o[6];
-        observe(P, e, o);
+        observe<LEAN>(P, e, o);
         store_obs(obs, i, o);
         store_env<STAMPS>(P, i, e);
     }
@@ -194,7 +197,7 @@ k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
 
 /* -- vector_reset / reset_at (env:428-480) -------------------------------------------------- */
 
-template <bool STAMPS, bool TRACK>
+template <bool STAMPS, bool TRACK, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_reset(const __grid_constant__ Params P, const uint8_t *__restrict__ mask, int64_t only,
         float *__restrict__ obs, int64_t obs_row_offset)
@@ -213,12 +216,12 @@ k_reset(const __grid_constant__ Params P, const uint8_t *__restrict__ mask, int6
         P.ep_return[i] = 0.0;
     if (obs) {
         float o[6];
-        observe(P, e, o);
+        observe<LEAN>(P, e, o);
         store_obs(obs, i + obs_row_offset, o);
     }
 }
 
-template <bool STAMPS>
+template <bool STAMPS, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_observe(const __grid_constant__ Params P, float *__restrict__ obs)
 {
@@ -228,13 +231,13 @@ k_observe(const __grid_constant__ Params P, float *__restrict__ obs)
     Env e;
     load_env<STAMPS>(P, i, e);
     float o[6];
-    observe(P, e, o);
+    observe<LEAN>(P, e, o);
     store_obs(obs, i, o);
 }
 
 /* -- multi-tick rollout with a device-side policy: state stays in registers -------------------- */
 
-template <bool STAMPS, bool TRACK>
+template <bool STAMPS, bool TRACK, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick_base,
           uint64_t policy_seed, float *__restrict__ obs, float *__restrict__ reward_sum)
@@ -254,7 +257,7 @@ k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick
         policy_action(P, policy, policy_seed, gidx, tick_base + (uint32_t)t, keybits, m);
         float r;
         bool d;
-        tick<STAMPS>(P, e, keybits, m, r, d);
+        tick<STAMPS, LEAN>(P, e, keybits, m, r, d);
         rsum = add32(rsum, r);
         if (TRACK) {
             ret = add64(ret, (double)r);
@@ -276,7 +279,7 @@ k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick
         reward_sum[i] = rsum;
     if (obs) {
         float o[6];
-        observe(P, e, o);
+        observe<LEAN>(P, e, o);
         store_obs(obs, i, o);
     }
 }
@@ -312,7 +315,7 @@ k_phys_apply(int64_t n, const double *__restrict__ yaw, const double *__restrict
     bool og = on_ground[i] != 0, jr = jump_released[i] != 0;
     double dt = time_delta[i];
     /* phys:78 f32(10) * dt, phys:122 f32(800) * dt */
-    move_body(vx, vy, vz, z, og, jr, fx, rx, fy, ry, fmove[i], smove[i], button2[i] != 0, dt,
+    move_body<false>(vx, vy, vz, z, og, jr, fx, rx, fy, ry, fmove[i], smove[i], button2[i] != 0, dt,
               mul64(10.0, dt), mul64(800.0, dt));
     z_out[i] = z;
     vel_out[3 * i] = vx;
@@ -372,6 +375,82 @@ k_decode(const __grid_constant__ Params P, uint8_t *__restrict__ last_keys,
     smove[i] = (int64_t)sm;
     fmove[i] = (int64_t)fm;
     jump[i] = P.auto_jump ? (z_vel[i] <= 16.0f) : (P.allow_jump ? (uint8_t)downs[KEY_JUMP] : 0);
+}
+
+/* -- self-test of the branch-free division sequences against the IEEE intrinsics ------------------ */
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &x)
+{
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* random double with a uniform significand and an exponent in [-span, span] */
+__device__ __forceinline__ double random_double(uint64_t &rng, int span, bool signed_)
+{
+    uint64_t w = splitmix64(rng);
+    uint64_t mant = w & 0xFFFFFFFFFFFFFull;
+    uint32_t sel = (uint32_t)(w >> 52) & 0x3FFu;
+    if ((sel & 0x3Fu) == 0)
+        mant = 0xFFFFFFFFFFFFFull;               /* significand of all ones: Markstein's exception */
+    else if ((sel & 0x3Fu) == 1)
+        mant = 0;
+    else if ((sel & 0x3Fu) == 2)
+        mant = 1;
+    int e = (int)(splitmix64(rng) % (uint64_t)(2 * span + 1)) - span;
+    uint64_t bits = ((uint64_t)(1023 + e) << 52) | mant;
+    if (signed_ && (w >> 63))
+        bits |= 0x8000000000000000ull;
+    return __longlong_as_double((long long)bits);
+}
+
+__global__ void __launch_bounds__(256)
+k_selftest(uint64_t iters, uint64_t seed, unsigned long long *__restrict__ out)
+{
+    uint64_t rng = seed * 0x2545F4914F6CDD1Dull + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2 + 1;
+    unsigned long long bad[6] = {0, 0, 0, 0, 0, 0};
+    const double consts[8] = {10.0, (double)10.08f, 180.0, 90.0, 5.0, 7.0, 4.0, 0.013888888888888};
+    for (uint64_t it = 0; it < iters; it++) {
+        /* 0: reciprocal, wide range */
+        double b = random_double(rng, 200, false);
+        double y = rcp_rn(b);
+        bad[0] += __double_as_longlong(y) != __double_as_longlong(__drcp_rn(b));
+        /* 1: quotient by a variable divisor, wide range */
+        double a = random_double(rng, 200, true);
+        bad[1] += __double_as_longlong(div_rcp(a, b, y)) != __double_as_longlong(__ddiv_rn(a, b));
+        /* 2: quotient by constants the path uses (and a random constant) */
+        double c = (it & 8) ? random_double(rng, 20, false) : consts[it & 7];
+        double yc = __drcp_rn(c);
+        bad[2] += __double_as_longlong(div_const(a, c, yc)) != __double_as_longlong(__ddiv_rn(a, c));
+        /* 3: the physics ranges: wish velocity / wish speed, new_speed / speed */
+        double ws = 1.0 + (double)(splitmix64(rng) >> 11) * (2000.0 / 9007199254740992.0);
+        double wx = ((double)(splitmix64(rng) >> 11) * (2.0 / 9007199254740992.0) - 1.0) * ws;
+        bad[3] += __double_as_longlong(div_rcp(wx, ws, rcp_rn(ws))) !=
+                  __double_as_longlong(__ddiv_rn(wx, ws));
+        float sp = __uint_as_float(0x30000000u + (uint32_t)(splitmix64(rng) % 0x16000000ull));
+        double ns = (double)sp * ((double)(splitmix64(rng) >> 11) * (1.0 / 9007199254740992.0));
+        bad[4] += __double_as_longlong(div_rcp(ns, (double)sp, rcp_rn((double)sp))) !=
+                  __double_as_longlong(__ddiv_rn(ns, (double)sp));
+    }
+    /* 5: the f32 observation quotients, exhaustively: multiples of 16 over 200 and multiples of
+     * 1/8 over 100, against the reference's f64 division rounded to f32 */
+    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t m = tid; m < (1ull << 21); m += nth) {
+        float q = (float)((long long)m - (1ll << 20));
+        float v = q * 16.0f;
+        bad[5] += __float_as_uint(div_const32(v, 200.0f, 1.0f / 200.0f)) !=
+                  __float_as_uint(__double2float_rn(__ddiv_rn((double)v, 200.0)));
+    }
+    for (uint64_t m = tid; m < (1ull << 25); m += nth) {
+        float zq = (float)((long long)m - (1ll << 24)) * 0.125f;
+        bad[5] += __float_as_uint(div_const32(zq, 100.0f, 1.0f / 100.0f)) !=
+                  __float_as_uint(__double2float_rn(__ddiv_rn((double)zq, 100.0)));
+    }
+    for (int k = 0; k < 6; k++)
+        if (bad[k])
+            atomicAdd(&out[k], bad[k]);
 }
 
 } // namespace
@@ -454,6 +533,17 @@ int derive_params(const q1_config &c, Params &P, bool &counters_exact)
     P.fmove_full = std::trunc((double)(float)c.fmove_max);
     P.smove_half = std::trunc((double)(float)c.smove_max * 0.5);
     P.smove_full = std::trunc((double)(float)c.smove_max);
+    P.rcp_action_range = 1.0 / c.action_range;
+    P.rcp_yaw_steps = 1.0 / (double)c.discrete_yaw_steps;
+    P.rcp_time_limit = 1.0 / c.time_limit;
+    P.fmove_tab[0] = 0.0;
+    P.fmove_tab[1] = P.fmove_half;
+    P.fmove_tab[2] = P.fmove_full;
+    P.smove_tab[0] = -P.smove_full;
+    P.smove_tab[1] = -P.smove_half;
+    P.smove_tab[2] = 0.0;
+    P.smove_tab[3] = P.smove_half;
+    P.smove_tab[4] = P.smove_full;
     P.zero_start_prob = c.zero_start_prob;
     P.yaw_lo = c.initial_yaw_lo;
     P.yaw_hi = c.initial_yaw_hi;
@@ -484,9 +574,14 @@ size_t align_up(size_t v) { return (v + 255u) & ~(size_t)255u; }
 
 template <typename F> int dispatch(const q1_env *env, F &&f)
 {
+    auto with_lean = [&](auto st, auto tr) {
+        return env->P.ieee_div ? f(st, tr, std::false_type{}) : f(st, tr, std::true_type{});
+    };
     if (env->stamps)
-        return env->track ? f(std::true_type{}, std::true_type{}) : f(std::true_type{}, std::false_type{});
-    return env->track ? f(std::false_type{}, std::true_type{}) : f(std::false_type{}, std::false_type{});
+        return env->track ? with_lean(std::true_type{}, std::true_type{})
+                          : with_lean(std::true_type{}, std::false_type{});
+    return env->track ? with_lean(std::false_type{}, std::true_type{})
+                      : with_lean(std::false_type{}, std::false_type{});
 }
 
 int check_launch(const char *what)
@@ -590,6 +685,10 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     }
     env->stamps = (flags & Q1_F_FORCE_F64_STAMPS) || !counters_exact;
     env->track = flags & Q1_F_TRACK_RETURNS;
+    /* the reciprocal sequences assume positive divisors in a sane exponent range */
+    auto sane = [](double v) { return v > 1e-100 && v < 1e100; };
+    env->P.ieee_div = (flags & Q1_F_IEEE_DIVISION) || !sane(cfg->time_limit) ||
+                      (cfg->allow_yaw && cfg->discrete_yaw_steps == -1 && !sane(cfg->action_range));
     Params &P = env->P;
     P.seed = seed;
     P.env_index_base = env_index_base;
@@ -690,8 +789,8 @@ static int reset_launch(q1_env *env, const uint8_t *mask, int64_t only, float *o
                         int64_t obs_row_offset, cudaStream_t s)
 {
     unsigned grid = only >= 0 ? 1u : grid_for(env->P.n);
-    return dispatch(env, [&](auto st, auto tr) {
-        k_reset<decltype(st)::value, decltype(tr)::value>
+    return dispatch(env, [&](auto st, auto tr, auto ln) {
+        k_reset<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
             <<<grid, kBlock, 0, s>>>(env->P, mask, only, obs, obs_row_offset);
         return check_launch("k_reset");
     });
@@ -787,8 +886,9 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
         return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
     DeviceGuard guard(env->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = dispatch(env, [&](auto st, auto tr) {
-        k_step<decltype(st)::value, decltype(tr)::value><<<grid_for(env->P.n), kBlock, 0, s>>>(
+    int rc = dispatch(env, [&](auto st, auto tr, auto ln) {
+        k_step<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
+            <<<grid_for(env->P.n), kBlock, 0, s>>>(
             env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset);
         return check_launch("k_step");
     });
@@ -865,8 +965,9 @@ int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *
         return fail(Q1_EINVAL, "ticks must be >= 0");
     DeviceGuard guard(env->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = dispatch(env, [&](auto st, auto tr) {
-        k_rollout<decltype(st)::value, decltype(tr)::value><<<grid_for(env->P.n), kBlock, 0, s>>>(
+    int rc = dispatch(env, [&](auto st, auto tr, auto ln) {
+        k_rollout<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
+            <<<grid_for(env->P.n), kBlock, 0, s>>>(
             env->P, policy, ticks, (uint32_t)env->ticks, policy_seed, obs, reward_sum);
         return check_launch("k_rollout");
     });
@@ -881,11 +982,11 @@ int q1_observe(q1_env *env, float *obs, void *stream)
         return fail(Q1_EINVAL, "env / obs is NULL");
     DeviceGuard guard(env->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (env->stamps)
-        k_observe<true><<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, obs);
-    else
-        k_observe<false><<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, obs);
-    return check_launch("k_observe");
+    return dispatch(env, [&](auto st, auto, auto ln) {
+        k_observe<decltype(st)::value, decltype(ln)::value>
+            <<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, obs);
+        return check_launch("k_observe");
+    });
 }
 
 int q1_observe_host(q1_env *env, float *obs_host)
@@ -1234,6 +1335,30 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n, uint8_t *last_ke
     Q1_CUDA(cudaMemcpy(fmove, d_fm, 8 * N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(jump, d_jump, N, cudaMemcpyDeviceToHost));
     return Q1_OK;
+}
+
+int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[6])
+{
+    if (!mismatches)
+        return fail(Q1_EINVAL, "mismatches is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    unsigned long long *d_out = nullptr;
+    Q1_CUDA(cudaMalloc(&d_out, 6 * sizeof(unsigned long long)));
+    Q1_CUDA(cudaMemset(d_out, 0, 6 * sizeof(unsigned long long)));
+    const unsigned blocks = 148 * 8;
+    uint64_t iters = (samples + (uint64_t)blocks * 256 - 1) / ((uint64_t)blocks * 256);
+    k_selftest<<<blocks, 256>>>(iters, seed, d_out);
+    int rc = check_launch("k_selftest");
+    if (rc == Q1_OK) {
+        cudaError_t err = cudaMemcpy(mismatches, d_out, 6 * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess)
+            rc = fail(Q1_ECUDA, std::string("k_selftest: ") + cudaGetErrorString(err));
+    }
+    cudaFree(d_out);
+    return rc;
 }
 
 } /* extern "C" */

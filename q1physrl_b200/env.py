@@ -321,6 +321,8 @@ class VectorPhysEnv(VectorEnv):
       track_returns     keep per-env episode returns and the on-device episode metrics
       f64_key_stamps    force the reference's f64 key-press time stamps (default: u8 tick counters
                         whenever those are provably equivalent)
+      ieee_division     divide with the CUDA IEEE intrinsics instead of the branch-free reciprocal
+                        sequences (same results, slower; used by the self-checks)
       reuse_output_buffers  return views of two alternating page-locked buffer sets from
                         `vector_step` instead of fresh arrays (default: only for num_envs >= 65536)
     """
@@ -328,7 +330,8 @@ class VectorPhysEnv(VectorEnv):
 
     def __init__(self, config, *, device: int = 0, seed: Optional[int] = None,
                  env_index_base: int = 0, track_returns: bool = False,
-                 f64_key_stamps: bool = False, reuse_output_buffers: Optional[bool] = None):
+                 f64_key_stamps: bool = False, ieee_division: bool = False,
+                 reuse_output_buffers: Optional[bool] = None):
         if isinstance(config, dict):
             config = Config(**config)
         self._config = config
@@ -350,7 +353,8 @@ class VectorPhysEnv(VectorEnv):
             seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
         self._seed = int(seed)
         flags = (_lib.Q1_F_TRACK_RETURNS if track_returns else 0) | \
-                (_lib.Q1_F_FORCE_F64_STAMPS if f64_key_stamps else 0)
+                (_lib.Q1_F_FORCE_F64_STAMPS if f64_key_stamps else 0) | \
+                (_lib.Q1_F_IEEE_DIVISION if ieee_division else 0)
         self._handle = ctypes.c_void_p()
         cfg = _pod_config(self._config, self.num_envs)
         _lib.check(self._lib.q1_create(ctypes.byref(cfg), self._device, self._seed,
