@@ -119,7 +119,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB_PATH
+    """The in-tree library; Q1PHYS_LIB overrides it (kernel-variant experiments)."""
+    return os.environ.get("Q1PHYS_LIB") or _build.LIB_PATH
 
 
 def load():

@@ -31,14 +31,21 @@ constexpr float kInitialYawZero = 90.0f;
 
 constexpr double kPi = 3.14159265358979323846; /* np.pi */
 
-/* flags byte of the persistent state */
+/* The per-env "bits" word of the persistent state:
+ *   bits  0..19  four 5-bit "ticks until the key may be pressed again" counters (counter mode)
+ *   bits 20..27  flags */
 enum : uint32_t {
-    F_ON_GROUND = 1u,
-    F_JUMP_RELEASED = 2u,
-    F_ZERO_START = 4u,
-    F_LAST_KEY0 = 8u, /* bits 3..6 = last_keys[0..3] (env:201) */
-    F_LAST_KEY_SHIFT = 3u,
-    F_DONE_SEEN = 128u /* episode already reported to the metrics (time_remaining crossed 0) */
+    TIMER_BITS = 5u,
+    TIMER_MAX = 31u,
+    TIMER_FIELD_MASK = 0xFFFFFu,
+    TIMER_LOW = 0x08421u,       /* bit 0 of each 5-bit field */
+    TIMER_HIGH = 0x84210u,      /* bit 4 of each 5-bit field */
+    F_SHIFT = 20u,
+    F_ON_GROUND = 1u << 20,
+    F_JUMP_RELEASED = 1u << 21,
+    F_ZERO_START = 1u << 22,
+    F_LAST_KEY_SHIFT = 23u,     /* bits 23..26 = last_keys[0..3] (env:201) */
+    F_DONE_SEEN = 1u << 27      /* episode already reported to the metrics (time_remaining crossed 0) */
 };
 
 enum : int { KEY_LEFT = 0, KEY_RIGHT = 1, KEY_FORWARD = 2, KEY_JUMP = 3 }; /* env:61-73 */
@@ -70,12 +77,11 @@ struct Params {
     int32_t delay_ticks;    /* ceil(key_delay / dt) (counter mode) */
     int32_t allow_yaw, discrete_yaw, speed_reward, hover, smooth_keys, auto_jump, allow_jump;
     int32_t ieee_div;       /* use the IEEE division intrinsics instead of the reciprocal sequences */
-    /* persistent state, struct of arrays */
-    float *vx, *vy, *vz;
-    double *z, *yaw, *trem;
-    uint32_t *timers;       /* counter mode: 4 x u8 "ticks until the key may be pressed again" */
+    /* persistent state: three record arrays (+ stamps in stamp mode), see q1phys.cu */
+    float4 *rec_a;          /* {vx, vy, vz, bits} */
+    double2 *rec_b;         /* {z_pos, yaw} */
+    double *trem;           /* time_remaining */
     double *stamps;         /* stamp mode: (num_keys, n) f64 last key press time (env:200) */
-    uint8_t *flags;
     uint32_t *epoch;        /* reset count per env: RNG stream position, touched by resets only */
     double *ep_return;      /* TRACK only: running f64 episode return */
     double *metrics;        /* TRACK only: [zs_sum, zs_count, sum, count, max-as-ordered-bits] */
@@ -84,9 +90,8 @@ struct Params {
 /* One env in registers. */
 struct Env {
     float vx, vy, vz;
+    uint32_t bits;
     double z, yaw, trem;
-    uint32_t timers;
-    uint32_t flags;
     double stamp[4];
 };
 
@@ -171,6 +176,56 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 __device__ __forceinline__ double unit53(uint32_t a, uint32_t b)
 {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+/* ------------------------------------------------------------------ sin / cos ---------------- */
+
+/* Minimax coefficients of sin(r) = r + r^3 S(r^2) and cos(r) = 1 - r^2/2 + r^4 C(r^2) on
+ * |r| <= pi/4 (the fdlibm k_sin / k_cos sets), kept in the constant bank so the FP64 pipe reads
+ * them as operands instead of building each 64-bit immediate from two moves. */
+__constant__ double kSinCosCoef[12] = {
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
+/* sin and cos of a (radians), < 1 ulp like libdevice's sincos but branch-free for |a| < 1e5 (yaw
+ * below 5.7 million degrees): quadrant by the round-to-nearest magic add, three-term Cody-Waite
+ * reduction with fused multiply-adds, two Horner chains.  Larger arguments take libdevice's path. */
+__device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
+{
+    if (__builtin_expect(!(fabs(a) < 1.0e5), 0)) {
+        sincos(a, &s, &c);
+        return;
+    }
+    const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
+    double t = __fma_rn(a, 6.36619772367581382433e-01, magic);
+    const int q = __double2loint(t);
+    const double j = __dsub_rn(t, magic);
+    double r = __fma_rn(j, -1.57079632679489655800e+00, a);
+    r = __fma_rn(j, -6.12323399573676603587e-17, r);
+    r = __fma_rn(j, 1.4973849048591698e-33, r); /* pi/2 = 1.5707963267948966 + 6.123233995736766e-17 - 1.4973849048591698e-33 */
+    const double z = __dmul_rn(r, r);
+    double ps = kSinCosCoef[5];
+    ps = __fma_rn(ps, z, kSinCosCoef[4]);
+    ps = __fma_rn(ps, z, kSinCosCoef[3]);
+    ps = __fma_rn(ps, z, kSinCosCoef[2]);
+    ps = __fma_rn(ps, z, kSinCosCoef[1]);
+    ps = __fma_rn(ps, z, kSinCosCoef[0]);
+    double pc = kSinCosCoef[11];
+    pc = __fma_rn(pc, z, kSinCosCoef[10]);
+    pc = __fma_rn(pc, z, kSinCosCoef[9]);
+    pc = __fma_rn(pc, z, kSinCosCoef[8]);
+    pc = __fma_rn(pc, z, kSinCosCoef[7]);
+    pc = __fma_rn(pc, z, kSinCosCoef[6]);
+    const double sr = __fma_rn(__dmul_rn(r, z), ps, r);
+    const double cr = __fma_rn(z, __fma_rn(z, pc, -0.5), 1.0);
+    /* quadrant: q odd swaps, bit 1 negates sin (after the swap), bits 0^1 negate cos */
+    double ss = (q & 1) ? cr : sr;
+    double cc = (q & 1) ? sr : cr;
+    const int sflip = (q & 2) << 30, cflip = ((q + 1) & 2) << 30;
+    s = __hiloint2double(__double2hiint(ss) ^ sflip, __double2loint(ss));
+    c = __hiloint2double(__double2hiint(cc) ^ cflip, __double2loint(cc));
 }
 
 /* ------------------------------------------------------------------ observation -------------- */
@@ -328,7 +383,7 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
     }
 
     const uint32_t key_mask = (1u << P.num_keys) - 1u;
-    const uint32_t last = (e.flags >> F_LAST_KEY_SHIFT) & 0xFu;
+    const uint32_t last = (e.bits >> F_LAST_KEY_SHIFT) & 0xFu;
     uint32_t elapsed;   /* bit k: key k may be pressed again (env:241-242) */
     double now = 0.0;
     if (STAMPS) {
@@ -339,14 +394,14 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
             if (k < P.num_keys)
                 elapsed |= (now >= add64(e.stamp[k], P.key_delay) ? 1u : 0u) << k;
     } else {
-        /* four u8 "ticks until allowed" counters in one word: saturating decrement (a tick has
+        /* four 5-bit "ticks until allowed" counters in one word: saturating decrement (a tick has
          * passed since the last test), then gather the four is-zero bits */
-        uint32_t t = e.timers;
-        uint32_t nz = ((t | ((t | 0x80808080u) - 0x01010101u)) >> 7) & 0x01010101u; /* byte != 0 */
+        uint32_t t = e.bits & TIMER_FIELD_MASK;
+        uint32_t nz = ((t | ((t | TIMER_HIGH) - TIMER_LOW)) >> 4) & TIMER_LOW;   /* field != 0 */
         t -= nz;
-        uint32_t z = (((t | ((t | 0x80808080u) - 0x01010101u)) >> 7) & 0x01010101u) ^ 0x01010101u;
-        elapsed = (z * 0x01020408u) >> 24;
-        e.timers = t;
+        uint32_t z = (((t | ((t | TIMER_HIGH) - TIMER_LOW)) >> 4) & TIMER_LOW) ^ TIMER_LOW;
+        elapsed = ((z * 0x1111u) >> 12) & 0xFu;
+        e.bits = (e.bits & ~TIMER_FIELD_MASK) | t;
     }
     const uint32_t down = keybits & (elapsed | last) & key_mask;                        /* env:243 */
     const uint32_t rising = down & ~last;                                               /* env:244 */
@@ -356,8 +411,8 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
             if ((rising >> k) & 1u)
                 e.stamp[k] = now;                                                        /* env:246 */
     } else {
-        uint32_t m = ((rising * 0x00204081u) & 0x01010101u) * 0xFFu;  /* bit k -> byte k mask */
-        e.timers = (e.timers & ~m) | (((uint32_t)P.delay_ticks * 0x01010101u) & m);
+        uint32_t m = ((rising * 0x1111u) & TIMER_LOW) * TIMER_MAX;      /* bit k -> 5-bit field k mask */
+        e.bits = (e.bits & ~m) | (((uint32_t)P.delay_ticks * TIMER_LOW) & m);
     }
 
     /* env:251-261: smoothed keys in {0, 1/2, 1}; fmove / smove are truncations of f32(max) * that,
@@ -386,18 +441,21 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
         jump = false;                                                                   /* env:267 */
 
     e.yaw = add64(e.yaw, mouse_x);                                                       /* env:258 */
-    e.flags = (e.flags & ~(0xFu << F_LAST_KEY_SHIFT)) | (down << F_LAST_KEY_SHIFT);     /* env:256 */
+    e.bits = (e.bits & ~(0xFu << F_LAST_KEY_SHIFT)) | (down << F_LAST_KEY_SHIFT);       /* env:256 */
 
     /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
     double sy, cy;
     {
         double t = mul64(e.yaw, kPi);                                                    /* phys:58-59 */
-        sincos(LEAN ? div_const(t, 180.0, 1.0 / 180.0) : div64(t, 180.0), &sy, &cy);
+        if (LEAN)
+            sincos_rad(div_const(t, 180.0, 1.0 / 180.0), sy, cy);
+        else
+            sincos(div64(t, 180.0), &sy, &cy);
     }
-    bool og = e.flags & F_ON_GROUND, jr = e.flags & F_JUMP_RELEASED;
+    bool og = e.bits & F_ON_GROUND, jr = e.bits & F_JUMP_RELEASED;
     move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,
                     P.accel_dt, P.gravity_dt);
-    e.flags = (e.flags & ~(F_ON_GROUND | F_JUMP_RELEASED)) | (og ? F_ON_GROUND : 0u) |
+    e.bits = (e.bits & ~(F_ON_GROUND | F_JUMP_RELEASED)) | (og ? F_ON_GROUND : 0u) |
               (jr ? F_JUMP_RELEASED : 0u);
 
     /* ---- reward, time, done (env:500-506) ---- */
@@ -442,8 +500,7 @@ __device__ __forceinline__ void reset_env(const Params &P, Env &e, uint64_t gidx
     sincos(angle, &sa, &ca);
     e.vx = __double2float_rn(mul64(speed, ca));
     e.vy = __double2float_rn(mul64(speed, sa));
-    e.flags = F_JUMP_RELEASED | (zs ? F_ZERO_START : 0u);
-    e.timers = 0u;
+    e.bits = F_JUMP_RELEASED | (zs ? F_ZERO_START : 0u); /* timers 0: every key may be pressed */
 #pragma unroll
     for (int k = 0; k < 4; k++)
         e.stamp[k] = -P.key_delay;

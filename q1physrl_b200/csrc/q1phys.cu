@@ -1,17 +1,22 @@
 /*
  * q1phys.cu -- sm_100a kernels and the C ABI (include/q1phys.h) of the q1physrl_env movement step.
  *
- * Data layout in HBM (struct of arrays, one element per env, every array 256-byte aligned inside
- * one pool allocation):
- *   vx, vy, vz f32 | z, yaw, time_remaining f64 | key timers 4 x u8 in a u32 (or (nk, n) f64 stamps)
- *   | flags u8 | reset epoch u32 (touched by resets only) | episode return f64 (TRACK only)
- * = 41 B per env in counter mode, read once and written once per tick.
+ * Data layout in HBM, per env (every array 256-byte aligned inside one pool allocation):
+ *   rec_a  float4  {vx, vy, vz, bits}   bits = four 5-bit key timers | on_ground, jump_released,
+ *                                       zero_start, last_keys[4], done_seen
+ *   rec_b  double2 {z_pos, yaw}
+ *   trem   double  time_remaining
+ *   [stamp mode only: (nk, n) f64 key-press time stamps]
+ *   epoch  u32     reset count (RNG stream position), touched by resets only
+ *   [TRACK only: f64 running episode return]
+ * = 40 B per env in counter mode, read once and written once per tick with 16-byte accesses.
  *
  * Citations: phys = q1physrl_env/q1physrl_env/phys.py, env = q1physrl_env/q1physrl_env/env.py.
  */
 #include "../../include/q1phys.h"
 #include "q1_tick.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,45 +31,42 @@ using namespace q1;
 
 namespace {
 
-constexpr int kBlock = 256;
+constexpr int kBlock = 128;        /* threads per CTA: one env per thread and tile */
+#ifndef Q1_STEP_CTAS
+#define Q1_STEP_CTAS 8
+#endif
+constexpr int kStepCtasPerSm = Q1_STEP_CTAS; /* resident CTAs per SM the persistent step kernel is sized for */
 
 template <bool STAMPS>
 __device__ __forceinline__ void load_env(const Params &P, int64_t i, Env &e)
 {
-    e.vx = P.vx[i];
-    e.vy = P.vy[i];
-    e.vz = P.vz[i];
-    e.z = P.z[i];
-    e.yaw = P.yaw[i];
+    const float4 a = P.rec_a[i];
+    const double2 b = P.rec_b[i];
+    e.vx = a.x;
+    e.vy = a.y;
+    e.vz = a.z;
+    e.bits = __float_as_uint(a.w);
+    e.z = b.x;
+    e.yaw = b.y;
     e.trem = P.trem[i];
-    e.flags = P.flags[i];
     if (STAMPS) {
-        e.timers = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++)
             e.stamp[k] = k < P.num_keys ? P.stamps[(int64_t)k * P.n + i] : 0.0;
-    } else {
-        e.timers = P.timers[i];
     }
 }
 
 template <bool STAMPS>
 __device__ __forceinline__ void store_env(const Params &P, int64_t i, const Env &e)
 {
-    P.vx[i] = e.vx;
-    P.vy[i] = e.vy;
-    P.vz[i] = e.vz;
-    P.z[i] = e.z;
-    P.yaw[i] = e.yaw;
+    P.rec_a[i] = make_float4(e.vx, e.vy, e.vz, __uint_as_float(e.bits));
+    P.rec_b[i] = make_double2(e.z, e.yaw);
     P.trem[i] = e.trem;
-    P.flags[i] = (uint8_t)e.flags;
     if (STAMPS) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (k < P.num_keys)
                 P.stamps[(int64_t)k * P.n + i] = e.stamp[k];
-    } else {
-        P.timers[i] = e.timers;
     }
 }
 
@@ -103,10 +105,10 @@ __device__ __forceinline__ uint32_t load_keys(const uint8_t *keys, int64_t i, in
 __device__ __forceinline__ double load_mouse(const void *mouse, int kind, int64_t i)
 {
     if (kind == Q1_MOUSE_F32)
-        return (double)reinterpret_cast<const float *>(mouse)[i];
+        return (double)__ldg(reinterpret_cast<const float *>(mouse) + i);
     if (kind == Q1_MOUSE_I32)
-        return (double)reinterpret_cast<const int32_t *>(mouse)[i];
-    return reinterpret_cast<const double *>(mouse)[i];
+        return (double)__ldg(reinterpret_cast<const int32_t *>(mouse) + i);
+    return __ldg(reinterpret_cast<const double *>(mouse) + i);
 }
 
 /* -- episode metrics (q1physrl/train.py:54-57, 67-71) ------------------------------------------ */
@@ -117,7 +119,8 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-/* Called by full warps.  `finished`: this lane's episode ended this tick with return `ret`. */
+/* Called by full warps.  `finished`: this lane's episode ended this tick with return `ret`.
+ * Warp-ballot first: a warp without a finished episode leaves after one instruction. */
 __device__ __forceinline__ void report_episodes(const Params &P, bool finished, bool zs, double ret)
 {
     unsigned any = __ballot_sync(0xffffffffu, finished);
@@ -143,16 +146,237 @@ __device__ __forceinline__ void report_episodes(const Params &P, bool finished, 
     }
 }
 
+/* -- TMA (cp.async.bulk) + mbarrier plumbing ------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+}
+/* global -> shared bulk copy that signals `bar` with the byte count when it lands */
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+/* shared -> global bulk copy, tracked by this thread's bulk async-group */
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_addr(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* all bulk groups of this thread have finished READING shared memory */
+__device__ __forceinline__ void bulk_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_smem_to_async_proxy()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 /* -- env.VectorPhysEnv.vector_step (env:482-510): one lockstep tick ---------------------------- */
 
+/* One tile = kBlock envs.  Shared-memory image of a tile in flight: the three state records and
+ * the action arrays as they lie in HBM (inputs), the results as they will lie in HBM (outputs). */
+struct __align__(128) StepStage {
+    float4 rec_a[kBlock];          /* in, rewritten in place -> out */
+    double2 rec_b[kBlock];         /* in, rewritten in place -> out */
+    double trem[kBlock];           /* in, rewritten in place -> out */
+    double mouse[kBlock];          /* in: f32 / i32 use the first half */
+    uint8_t keys[kBlock * 4];      /* in: kBlock x num_keys */
+    float obs[kBlock * 6];         /* out */
+    float reward[kBlock];          /* out */
+    uint8_t done[kBlock];          /* out */
+    uint8_t zero_start[kBlock];    /* out */
+};
+constexpr int kStages = 2;
+
+/* Persistent, TMA-pipelined step kernel (counter mode, full tiles, 16-byte aligned buffers).
+ * gridDim.x = #SMs x kStepCtasPerSm; CTA c walks tiles c, c + grid, ...  All global traffic is bulk
+ * copies issued by one elected thread: the next tile's records and actions stream into one stage
+ * (completion on an mbarrier) while the CTA computes the current tile from the other; results
+ * are written back in place in shared memory and leave as bulk stores.  Threads touch only shared
+ * memory (16-byte LDS/STS, 32-bit addresses), so there is no per-thread global address arithmetic
+ * and no load latency on the compute warps' scoreboard. */
+template <bool TRACK, bool LEAN>
+__global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
+k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
+           const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
+           float *__restrict__ reward, uint8_t *__restrict__ done,
+           uint8_t *__restrict__ zero_start, int auto_reset, int64_t tiles)
+{
+    __shared__ StepStage stage[kStages];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    const int tid = threadIdx.x;
+    const uint32_t nk = (uint32_t)P.num_keys;
+    const uint32_t mouse_bytes = P.allow_yaw ? (mouse_kind == Q1_MOUSE_F64 ? 8u : 4u) * kBlock : 0u;
+    const uint32_t in_bytes = sizeof(float4) * kBlock + sizeof(double2) * kBlock +
+                              sizeof(double) * kBlock + nk * kBlock + mouse_bytes;
+
+    auto issue_loads = [&](int s, int64_t tile) {
+        StepStage &st = stage[s];
+        const int64_t base = tile * kBlock;
+        mbar_expect_tx(&full_bar[s], in_bytes);
+        bulk_load(st.rec_a, P.rec_a + base, sizeof(float4) * kBlock, &full_bar[s]);
+        bulk_load(st.rec_b, P.rec_b + base, sizeof(double2) * kBlock, &full_bar[s]);
+        bulk_load(st.trem, P.trem + base, sizeof(double) * kBlock, &full_bar[s]);
+        bulk_load(st.keys, keys + base * nk, nk * kBlock, &full_bar[s]);
+        if (mouse_bytes)
+            bulk_load(st.mouse, static_cast<const char *>(mouse) + base * (mouse_bytes / kBlock),
+                      mouse_bytes, &full_bar[s]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++)
+            mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_smem_to_async_proxy();
+#pragma unroll
+        for (int s = 0; s < kStages; s++) {
+            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            if (tile < tiles)
+                issue_loads(s, tile);
+        }
+    }
+    __syncthreads();
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        StepStage &st = stage[s];
+        const int64_t i = tile * kBlock + tid;
+        mbar_wait(&full_bar[s], parity);
+
+        Env e;
+        {
+            const float4 a = st.rec_a[tid];
+            const double2 b = st.rec_b[tid];
+            e.vx = a.x;
+            e.vy = a.y;
+            e.vz = a.z;
+            e.bits = __float_as_uint(a.w);
+            e.z = b.x;
+            e.yaw = b.y;
+            e.trem = st.trem[tid];
+        }
+        uint32_t keybits;
+        if (nk == 4) {
+            const uint32_t w = reinterpret_cast<const uint32_t *>(st.keys)[tid];
+            keybits = (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
+        } else {
+            const uint8_t *k = st.keys + 3 * tid;
+            keybits = (k[0] & 1u) | ((k[1] & 1u) << 1) | ((k[2] & 1u) << 2);
+        }
+        double m = 0.0;
+        if (P.allow_yaw) {
+            if (mouse_kind == Q1_MOUSE_F32)
+                m = (double)reinterpret_cast<const float *>(st.mouse)[tid];
+            else if (mouse_kind == Q1_MOUSE_I32)
+                m = (double)reinterpret_cast<const int32_t *>(st.mouse)[tid];
+            else
+                m = st.mouse[tid];
+        }
+        float r;
+        bool d;
+        tick<false, LEAN>(P, e, keybits, m, r, d);
+        const bool zs = e.bits & F_ZERO_START;
+        bool finished = false;
+        double ret = 0.0;
+        if (TRACK) {
+            ret = add64(P.ep_return[i], (double)r);
+            finished = d && !(e.bits & F_DONE_SEEN);
+            if (finished)
+                e.bits |= F_DONE_SEEN;
+        }
+        st.reward[tid] = r;
+        st.done[tid] = d ? 1 : 0;
+        st.zero_start[tid] = zs ? 1 : 0;
+        if (d && auto_reset) {
+            uint32_t ep = P.epoch[i] + 1u;
+            P.epoch[i] = ep;
+            reset_env<false>(P, e, P.env_index_base + (uint64_t)i, ep);
+            if (TRACK)
+                P.ep_return[i] = 0.0;
+        } else if (TRACK) {
+            P.ep_return[i] = ret;
+        }
+        float o[6];
+        observe<LEAN>(P, e, o);
+        {
+            float2 *row = reinterpret_cast<float2 *>(&st.obs[tid * 6]);
+            row[0] = make_float2(o[0], o[1]);
+            row[1] = make_float2(o[2], o[3]);
+            row[2] = make_float2(o[4], o[5]);
+            st.rec_a[tid] = make_float4(e.vx, e.vy, e.vz, __uint_as_float(e.bits));
+            st.rec_b[tid] = make_double2(e.z, e.yaw);
+            st.trem[tid] = e.trem;
+        }
+        fence_smem_to_async_proxy();
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t base = tile * kBlock;
+            bulk_store(P.rec_a + base, st.rec_a, sizeof(float4) * kBlock);
+            bulk_store(P.rec_b + base, st.rec_b, sizeof(double2) * kBlock);
+            bulk_store(P.trem + base, st.trem, sizeof(double) * kBlock);
+            bulk_store(obs + base * 6, st.obs, sizeof(float) * 6 * kBlock);
+            bulk_store(reward + base, st.reward, sizeof(float) * kBlock);
+            bulk_store(done + base, st.done, kBlock);
+            if (zero_start)
+                bulk_store(zero_start + base, st.zero_start, kBlock);
+            bulk_commit();
+            const int64_t next = tile + (int64_t)kStages * gridDim.x;
+            if (next < tiles) {
+                bulk_wait_read_all(); /* the stores have drained this stage: refill it */
+                issue_loads(s, next);
+            }
+        }
+        if (TRACK)
+            report_episodes(P, finished, zs, ret);
+        if (++s == kStages) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+    if (tid == 0)
+        bulk_wait_all();
+}
+
+/* The same tick, one env per thread with plain loads and stores: f64-stamp mode, ragged tails
+ * (n not a multiple of kBlock) and buffers that are not 16-byte aligned.  Covers envs [first, n). */
 template <bool STAMPS, bool TRACK, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
        const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
        float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ zero_start,
-       int auto_reset)
+       int auto_reset, int64_t first)
 {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t i = first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = i < P.n;
     bool finished = false, zs = false;
     double ret = 0.0;
@@ -166,12 +390,12 @@ k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         float r;
         bool d;
         tick<STAMPS, LEAN>(P, e, keybits, m, r, d);
-        zs = e.flags & F_ZERO_START;
+        zs = e.bits & F_ZERO_START;
         if (TRACK) {
             ret = add64(P.ep_return[i], (double)r);
-            finished = d && !(e.flags & F_DONE_SEEN);
+            finished = d && !(e.bits & F_DONE_SEEN);
             if (finished)
-                e.flags |= F_DONE_SEEN;
+                e.bits |= F_DONE_SEEN;
         }
         reward[i] = r;
         done[i] = d ? 1 : 0;
@@ -261,7 +485,7 @@ k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick
         rsum = add32(rsum, r);
         if (TRACK) {
             ret = add64(ret, (double)r);
-            report_episodes(P, active && d, e.flags & F_ZERO_START, ret);
+            report_episodes(P, active && d, e.bits & F_ZERO_START, ret);
         }
         if (d) {
             ep += 1u;
@@ -484,6 +708,7 @@ struct q1_env {
     int state_bytes_per_env = 0;
     uint64_t ticks = 0;
     /* device scratch + stream of the *_host entry points */
+    int sm_count = 148;
     cudaStream_t host_stream = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -557,11 +782,11 @@ int derive_params(const q1_config &c, Params &P, bool &counters_exact)
     P.smooth_keys = c.smooth_keys != 0;
     P.auto_jump = c.auto_jump != 0;
     P.allow_jump = c.allow_jump != 0;
-    /* u8 countdown timers reproduce the f64 stamp comparison exactly when delay/dt is safely away
+    /* 5-bit countdown timers reproduce the f64 stamp comparison exactly when delay/dt is safely away
      * from an integer (rounding in TL - t_rem is ~1e-12 s), or when delay is 0. */
     double q = c.key_press_delay / c.time_delta;
     double frac = std::fabs(q - std::nearbyint(q));
-    counters_exact = (c.key_press_delay == 0.0) || (frac > 1e-6 && q < 254.0);
+    counters_exact = (c.key_press_delay == 0.0) || (frac > 1e-6 && q < 30.0); /* 5-bit counters */
     /* A fresh episode must satisfy "elapsed" at once, i.e. time_limit - t_rem >= -delay + delay = 0.
      * Resets draw t_rem = uniform(low=time_limit, high=1.0) (env:439, 466), which stays <= time_limit
      * only for time_limit >= 1; below that the f64 stamps are kept. */
@@ -701,20 +926,27 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
         off = align_up(off + bytes);
         return o;
     };
-    size_t o_vx = take(4 * n), o_vy = take(4 * n), o_vz = take(4 * n);
-    size_t o_z = take(8 * n), o_yaw = take(8 * n), o_trem = take(8 * n);
-    size_t o_keys = env->stamps ? take(8 * n * nk) : take(4 * n);
-    size_t o_flags = take(n), o_epoch = take(4 * n);
+    size_t o_a = take(16 * n), o_b = take(16 * n), o_trem = take(8 * n);
+    size_t o_stamps = env->stamps ? take(8 * n * nk) : 0;
+    size_t o_epoch = take(4 * n);
     size_t o_ret = env->track ? take(8 * n) : 0;
     size_t o_metrics = env->track ? take(64) : 0;
     env->pool_bytes = off;
-    env->state_bytes_per_env = 12 + 24 + (env->stamps ? 8 * nk : 4) + 1 + (env->track ? 8 : 0);
+    env->state_bytes_per_env = 16 + 16 + 8 + (env->stamps ? 8 * nk : 0) + (env->track ? 8 : 0);
 
     DeviceGuard guard(device);
     if (!guard.ok) {
         delete env;
         return fail(Q1_ECUDA, "cudaSetDevice failed");
     }
+    cudaDeviceGetAttribute(&env->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (env->sm_count <= 0)
+        env->sm_count = 148;
+    /* kStepCtasPerSm CTAs x 21 KB of staging must fit: ask for the large shared-memory carveout */
+    cudaFuncSetAttribute(k_step_tma<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_step_tma<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_step_tma<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_step_tma<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaError_t err = cudaMalloc(&env->pool, env->pool_bytes);
     if (err != cudaSuccess) {
         delete env;
@@ -728,15 +960,10 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
         return fail(Q1_ECUDA, std::string("cudaMemset: ") + cudaGetErrorString(err));
     }
     char *base = static_cast<char *>(env->pool);
-    P.vx = reinterpret_cast<float *>(base + o_vx);
-    P.vy = reinterpret_cast<float *>(base + o_vy);
-    P.vz = reinterpret_cast<float *>(base + o_vz);
-    P.z = reinterpret_cast<double *>(base + o_z);
-    P.yaw = reinterpret_cast<double *>(base + o_yaw);
+    P.rec_a = reinterpret_cast<float4 *>(base + o_a);
+    P.rec_b = reinterpret_cast<double2 *>(base + o_b);
     P.trem = reinterpret_cast<double *>(base + o_trem);
-    P.timers = env->stamps ? nullptr : reinterpret_cast<uint32_t *>(base + o_keys);
-    P.stamps = env->stamps ? reinterpret_cast<double *>(base + o_keys) : nullptr;
-    P.flags = reinterpret_cast<uint8_t *>(base + o_flags);
+    P.stamps = env->stamps ? reinterpret_cast<double *>(base + o_stamps) : nullptr;
     P.epoch = reinterpret_cast<uint32_t *>(base + o_epoch);
     P.ep_return = env->track ? reinterpret_cast<double *>(base + o_ret) : nullptr;
     P.metrics = env->track ? reinterpret_cast<double *>(base + o_metrics) : nullptr;
@@ -886,12 +1113,32 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
         return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
     DeviceGuard guard(env->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = dispatch(env, [&](auto st, auto tr, auto ln) {
-        k_step<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
-            <<<grid_for(env->P.n), kBlock, 0, s>>>(
-            env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset);
-        return check_launch("k_step");
-    });
+    const int64_t n = env->P.n;
+    auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    /* full tiles go through the TMA-pipelined kernel when every buffer it bulk-copies is 16-byte
+     * aligned (tile strides are multiples of 16 by construction); the rest takes the plain kernel */
+    int64_t tma_tiles = 0;
+    if (!env->stamps && aligned16(keys) && aligned16(obs) && aligned16(reward) && aligned16(done) &&
+        (!zero_start || aligned16(zero_start)) && (!env->P.allow_yaw || aligned16(mouse)))
+        tma_tiles = n / kBlock;
+    int rc = Q1_OK;
+    if (tma_tiles > 0)
+        rc = dispatch(env, [&](auto, auto tr, auto ln) {
+            unsigned grid = (unsigned)std::min<int64_t>(tma_tiles,
+                                                        (int64_t)env->sm_count * kStepCtasPerSm);
+            k_step_tma<decltype(tr)::value, decltype(ln)::value><<<grid, kBlock, 0, s>>>(
+                env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset,
+                tma_tiles);
+            return check_launch("k_step_tma");
+        });
+    const int64_t first = tma_tiles * kBlock;
+    if (rc == Q1_OK && first < n)
+        rc = dispatch(env, [&](auto st, auto tr, auto ln) {
+            k_step<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
+                <<<grid_for(n - first), kBlock, 0, s>>>(env->P, keys, mouse, mouse_kind, obs,
+                                                       reward, done, zero_start, auto_reset, first);
+            return check_launch("k_step");
+        });
     if (rc == Q1_OK)
         env->ticks += 1;
     return rc;
@@ -1018,21 +1265,28 @@ int q1_get_state_host(q1_env *env, const q1_state_view *v)
     const Params &P = env->P;
     const size_t n = (size_t)P.n;
     const int nk = P.num_keys;
-    if (v->vel) {
-        std::vector<float> a(n), b(n), c(n);
-        Q1_CUDA(cudaMemcpy(a.data(), P.vx, 4 * n, cudaMemcpyDeviceToHost));
-        Q1_CUDA(cudaMemcpy(b.data(), P.vy, 4 * n, cudaMemcpyDeviceToHost));
-        Q1_CUDA(cudaMemcpy(c.data(), P.vz, 4 * n, cudaMemcpyDeviceToHost));
+    std::vector<float4> ra;
+    if (v->vel || v->on_ground || v->jump_released || v->zero_start || v->last_keys ||
+        (v->last_press && !env->stamps)) {
+        ra.resize(n);
+        Q1_CUDA(cudaMemcpy(ra.data(), P.rec_a, 16 * n, cudaMemcpyDeviceToHost));
+    }
+    if (v->vel)
         for (size_t i = 0; i < n; i++) {
-            v->vel[3 * i] = a[i];
-            v->vel[3 * i + 1] = b[i];
-            v->vel[3 * i + 2] = c[i];
+            v->vel[3 * i] = ra[i].x;
+            v->vel[3 * i + 1] = ra[i].y;
+            v->vel[3 * i + 2] = ra[i].z;
+        }
+    if (v->z_pos || v->yaw) {
+        std::vector<double2> rb(n);
+        Q1_CUDA(cudaMemcpy(rb.data(), P.rec_b, 16 * n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) {
+            if (v->z_pos)
+                v->z_pos[i] = rb[i].x;
+            if (v->yaw)
+                v->yaw[i] = rb[i].y;
         }
     }
-    if (v->z_pos)
-        Q1_CUDA(cudaMemcpy(v->z_pos, P.z, 8 * n, cudaMemcpyDeviceToHost));
-    if (v->yaw)
-        Q1_CUDA(cudaMemcpy(v->yaw, P.yaw, 8 * n, cudaMemcpyDeviceToHost));
     std::vector<double> trem;
     if (v->time_remaining || (v->last_press && !env->stamps)) {
         trem.resize(n);
@@ -1040,38 +1294,41 @@ int q1_get_state_host(q1_env *env, const q1_state_view *v)
         if (v->time_remaining)
             memcpy(v->time_remaining, trem.data(), 8 * n);
     }
+    auto bits_of = [&](size_t i) {
+        uint32_t w;
+        memcpy(&w, &ra[i].w, 4);
+        return w;
+    };
     if (v->on_ground || v->jump_released || v->zero_start || v->last_keys) {
-        std::vector<uint8_t> f(n);
-        Q1_CUDA(cudaMemcpy(f.data(), P.flags, n, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; i++) {
+            uint32_t w = bits_of(i);
             if (v->on_ground)
-                v->on_ground[i] = (f[i] & F_ON_GROUND) != 0;
+                v->on_ground[i] = (w & F_ON_GROUND) != 0;
             if (v->jump_released)
-                v->jump_released[i] = (f[i] & F_JUMP_RELEASED) != 0;
+                v->jump_released[i] = (w & F_JUMP_RELEASED) != 0;
             if (v->zero_start)
-                v->zero_start[i] = (f[i] & F_ZERO_START) != 0;
+                v->zero_start[i] = (w & F_ZERO_START) != 0;
             if (v->last_keys)
                 for (int k = 0; k < nk; k++)
-                    v->last_keys[i * nk + k] = (f[i] >> (F_LAST_KEY_SHIFT + k)) & 1u;
+                    v->last_keys[i * nk + k] = (w >> (F_LAST_KEY_SHIFT + k)) & 1u;
         }
     }
     if (v->last_press) {
         if (env->stamps) {
-            std::vector<double> s(n * nk);
-            Q1_CUDA(cudaMemcpy(s.data(), P.stamps, 8 * n * nk, cudaMemcpyDeviceToHost));
+            std::vector<double> st(n * nk);
+            Q1_CUDA(cudaMemcpy(st.data(), P.stamps, 8 * n * nk, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < n; i++)
                 for (int k = 0; k < nk; k++)
-                    v->last_press[i * nk + k] = s[(size_t)k * n + i];
+                    v->last_press[i * nk + k] = st[(size_t)k * n + i];
         } else {
             /* Counter mode keeps "ticks until the key may be pressed again"; the stamp handed back
              * is the one that yields the same future decode decisions (exact stamps need
              * Q1_F_FORCE_F64_STAMPS). */
-            std::vector<uint32_t> t(n);
-            Q1_CUDA(cudaMemcpy(t.data(), P.timers, 4 * n, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < n; i++) {
                 double now = P.time_limit - trem[i];
+                uint32_t w = bits_of(i);
                 for (int k = 0; k < nk; k++) {
-                    int r = (t[i] >> (8 * k)) & 0xFF;
+                    int r = (w >> (TIMER_BITS * k)) & TIMER_MAX;
                     v->last_press[i * nk + k] =
                         r == 0 ? -P.key_delay : now - (double)(P.delay_ticks - r + 1) * P.dt;
                 }
@@ -1095,28 +1352,36 @@ int q1_set_state_host(q1_env *env, const q1_state_view *v)
     const Params &P = env->P;
     const size_t n = (size_t)P.n;
     const int nk = P.num_keys;
-    if (v->vel) {
-        std::vector<float> a(n), b(n), c(n);
+    if (v->z_pos || v->yaw) {
+        std::vector<double2> rb(n);
+        Q1_CUDA(cudaMemcpy(rb.data(), P.rec_b, 16 * n, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; i++) {
-            a[i] = v->vel[3 * i];
-            b[i] = v->vel[3 * i + 1];
-            c[i] = v->vel[3 * i + 2];
+            if (v->z_pos)
+                rb[i].x = v->z_pos[i];
+            if (v->yaw)
+                rb[i].y = v->yaw[i];
         }
-        Q1_CUDA(cudaMemcpy(P.vx, a.data(), 4 * n, cudaMemcpyHostToDevice));
-        Q1_CUDA(cudaMemcpy(P.vy, b.data(), 4 * n, cudaMemcpyHostToDevice));
-        Q1_CUDA(cudaMemcpy(P.vz, c.data(), 4 * n, cudaMemcpyHostToDevice));
+        Q1_CUDA(cudaMemcpy(P.rec_b, rb.data(), 16 * n, cudaMemcpyHostToDevice));
     }
-    if (v->z_pos)
-        Q1_CUDA(cudaMemcpy(P.z, v->z_pos, 8 * n, cudaMemcpyHostToDevice));
-    if (v->yaw)
-        Q1_CUDA(cudaMemcpy(P.yaw, v->yaw, 8 * n, cudaMemcpyHostToDevice));
     if (v->time_remaining)
         Q1_CUDA(cudaMemcpy(P.trem, v->time_remaining, 8 * n, cudaMemcpyHostToDevice));
-    if (v->on_ground || v->jump_released || v->zero_start || v->last_keys) {
-        std::vector<uint8_t> f(n);
-        Q1_CUDA(cudaMemcpy(f.data(), P.flags, n, cudaMemcpyDeviceToHost));
+    const bool counters = v->last_press && !env->stamps;
+    if (v->vel || v->on_ground || v->jump_released || v->zero_start || v->last_keys || counters) {
+        std::vector<float4> ra(n);
+        Q1_CUDA(cudaMemcpy(ra.data(), P.rec_a, 16 * n, cudaMemcpyDeviceToHost));
+        std::vector<double> trem;
+        if (counters) {
+            trem.resize(n);
+            Q1_CUDA(cudaMemcpy(trem.data(), P.trem, 8 * n, cudaMemcpyDeviceToHost));
+        }
         for (size_t i = 0; i < n; i++) {
-            uint32_t x = f[i];
+            if (v->vel) {
+                ra[i].x = v->vel[3 * i];
+                ra[i].y = v->vel[3 * i + 1];
+                ra[i].z = v->vel[3 * i + 2];
+            }
+            uint32_t x;
+            memcpy(&x, &ra[i].w, 4);
             if (v->on_ground)
                 x = (x & ~F_ON_GROUND) | (v->on_ground[i] ? F_ON_GROUND : 0u);
             if (v->jump_released)
@@ -1128,38 +1393,31 @@ int q1_set_state_host(q1_env *env, const q1_state_view *v)
                 for (int k = 0; k < nk; k++)
                     x |= (uint32_t)(v->last_keys[i * nk + k] & 1u) << (F_LAST_KEY_SHIFT + k);
             }
-            f[i] = (uint8_t)x;
-        }
-        Q1_CUDA(cudaMemcpy(P.flags, f.data(), n, cudaMemcpyHostToDevice));
-    }
-    if (v->last_press) {
-        if (env->stamps) {
-            std::vector<double> s(n * nk);
-            for (size_t i = 0; i < n; i++)
-                for (int k = 0; k < nk; k++)
-                    s[(size_t)k * n + i] = v->last_press[i * nk + k];
-            Q1_CUDA(cudaMemcpy(P.stamps, s.data(), 8 * n * nk, cudaMemcpyHostToDevice));
-        } else {
-            /* ticks until now_j >= stamp + delay holds, now_j = now + j * dt (env:241-242) */
-            std::vector<double> trem(n);
-            Q1_CUDA(cudaMemcpy(trem.data(), P.trem, 8 * n, cudaMemcpyDeviceToHost));
-            std::vector<uint32_t> t(n);
-            for (size_t i = 0; i < n; i++) {
+            if (counters) {
+                /* ticks until now_j >= stamp + delay holds, now_j = now + j * dt (env:241-242);
+                 * +1 because the kernel decrements before it tests */
                 double now = P.time_limit - trem[i];
-                uint32_t w = 0;
+                x &= ~TIMER_FIELD_MASK;
                 for (int k = 0; k < nk; k++) {
                     double need = (v->last_press[i * nk + k] + P.key_delay - now) / P.dt;
-                    double r = std::ceil(need - 1e-9) + 1.0; /* the kernel decrements before testing */
+                    double r = std::ceil(need - 1e-9) + 1.0;
                     if (!(r > 0))
                         r = 0;
-                    if (r > 255)
-                        r = 255;
-                    w |= (uint32_t)r << (8 * k);
+                    if (r > TIMER_MAX)
+                        r = TIMER_MAX;
+                    x |= (uint32_t)r << (TIMER_BITS * k);
                 }
-                t[i] = w;
             }
-            Q1_CUDA(cudaMemcpy(P.timers, t.data(), 4 * n, cudaMemcpyHostToDevice));
+            memcpy(&ra[i].w, &x, 4);
         }
+        Q1_CUDA(cudaMemcpy(P.rec_a, ra.data(), 16 * n, cudaMemcpyHostToDevice));
+    }
+    if (v->last_press && env->stamps) {
+        std::vector<double> st(n * nk);
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < nk; k++)
+                st[(size_t)k * n + i] = v->last_press[i * nk + k];
+        Q1_CUDA(cudaMemcpy(P.stamps, st.data(), 8 * n * nk, cudaMemcpyHostToDevice));
     }
     if (v->episode_return) {
         if (!env->track)
