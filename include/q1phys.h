@@ -217,9 +217,10 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n,
 /* Self-check of the branch-free reciprocal-multiply division sequences the kernels use against the
  * CUDA IEEE intrinsics, on ~`samples` random operand pairs per class (bit comparison):
  *   [0] reciprocal  [1] a / variable b  [2] a / constant  [3] wish_vel / wish_speed range
- *   [4] new_speed / speed range  [5] the f32 observation quotients, exhaustive.
+ *   [4] new_speed / speed range  [5] the f32 observation quotients (v / 200, z / 100), exhaustive
+ *   [6], [7] the same two f32 quotient sets with a second correction step.
  * Every count must be 0. */
-int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[6]);
+int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[8]);
 
 #ifdef __cplusplus
 }

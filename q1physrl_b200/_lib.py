@@ -111,7 +111,7 @@ SIGNATURES = {
     "q1_get_metrics_host": (c_int, [c_void_p, c_int, ctypes.POINTER(Q1Metrics)]),
     "q1_phys_apply": (c_int, [c_int, c_i64] + [c_void_p] * 15 + [c_void_p]),
     "q1_phys_apply_host": (c_int, [c_int, c_i64] + [c_void_p] * 15),
-    "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 6)]),
+    "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 8)]),
     "q1_decode_host": (c_int, [ctypes.POINTER(Q1Config), c_int, c_i64] + [c_void_p] * 10),
 }
 

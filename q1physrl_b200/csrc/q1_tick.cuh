@@ -74,18 +74,26 @@ struct Params {
     double smove_tab[5];    /* smove for twice-(right - left) + 2 = 0 .. 4 */
     float dt_f32;           /* f32(time_delta) for the reward      env:500-503 */
     int32_t num_keys;       /* env:206-207 */
-    int32_t delay_ticks;    /* ceil(key_delay / dt) (counter mode) */
+    int32_t delay_ticks;    /* D = ceil(key_delay / dt) (counter mode) */
+    int32_t press_ticks;    /* max(D - 1, 0): counter value stored on a key press */
+    int32_t jump_mode;      /* 0: never (env:267)  1: jump key (env:265)  2: auto jump (env:263) */
     int32_t allow_yaw, discrete_yaw, speed_reward, hover, smooth_keys, auto_jump, allow_jump;
     int32_t ieee_div;       /* use the IEEE division intrinsics instead of the reciprocal sequences */
-    /* persistent state: three record arrays (+ stamps in stamp mode), see q1phys.cu */
-    float4 *rec_a;          /* {vx, vy, vz, bits} */
-    double2 *rec_b;         /* {z_pos, yaw} */
-    double *trem;           /* time_remaining */
+    /* persistent state, tile-contiguous: env i lives in block i / 128 of kTileBytes bytes,
+     * [float4 rec_a[128] {vx, vy, vz, bits} | double2 rec_b[128] {z_pos, yaw} | double trem[128]],
+     * so the state of a tile of 128 envs is one contiguous 5 KB bulk copy */
+    unsigned char *state;
     double *stamps;         /* stamp mode: (num_keys, n) f64 last key press time (env:200) */
     uint32_t *epoch;        /* reset count per env: RNG stream position, touched by resets only */
     double *ep_return;      /* TRACK only: running f64 episode return */
     double *metrics;        /* TRACK only: [zs_sum, zs_count, sum, count, max-as-ordered-bits] */
 };
+
+constexpr int kTile = 128;                          /* envs per state block / per CTA tile */
+constexpr int kTileRecA = 0;                        /* byte offsets inside a state block */
+constexpr int kTileRecB = 16 * kTile;
+constexpr int kTileTrem = 32 * kTile;
+constexpr int kTileBytes = 40 * kTile;
 
 /* One env in registers. */
 struct Env {
@@ -144,8 +152,18 @@ __device__ __forceinline__ double rcp_rn(double b)
 /* a / b given y = RN(1 / b) (same theorem as div_const). */
 __device__ __forceinline__ double div_rcp(double a, double b, double y) { return div_const(a, b, y); }
 
-/* f32 quotient a / b, b a constant with y = RN32(1 / b); a exactly representable, |a| < 2^24. */
+/* f32 quotient a / b for the two observation divisors (b = 200 with a a multiple of 16, b = 100
+ * with a a multiple of 1/8; y = RN32(1 / b)).  One residual correction is exact on those whole
+ * domains (|a / 16| <= 2^20, |8 a| <= 2^24): q1_selftest_division checks every value against the
+ * reference's f64 division rounded to f32. */
 __device__ __forceinline__ float div_const32(float a, float b, float y)
+{
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
+/* two corrections (Markstein, as div_const): the self-test reports it beside the short form */
+__device__ __forceinline__ float div_const32_long(float a, float b, float y)
 {
     float q = __fmul_rn(a, y);
     float r = __fmaf_rn(-b, q, a);
@@ -237,18 +255,6 @@ __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
  * binary expansion of period <= 20: it can never sit within 2^-53 of an f32 rounding boundary, and
  * rounding the exact quotient once to f32 equals rounding the f64 quotient to f32. */
 template <bool LEAN>
-__device__ __forceinline__ float obs_vel(float v)
-{
-    float q = truncf(mul32(v, 0.0625f)); /* (v / 16).astype(int): exact scaling, toward zero */
-    if (fabsf(q) < 1048576.0f) {
-        if (LEAN)
-            return div_const32(mul32(q, 16.0f), 200.0f, 1.0f / 200.0f);
-        return __fdiv_rn(mul32(q, 16.0f), 200.0f);
-    }
-    return __double2float_rn(div64(mul64((double)(long long)q, 16.0), 200.0));
-}
-
-template <bool LEAN>
 __device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6])
 {
     if (LEAN) {
@@ -258,16 +264,33 @@ __device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6
         o[0] = __double2float_rn(div64(e.trem, P.time_limit));
         o[1] = __double2float_rn(div64(e.yaw, 90.0));
     }
-    double r = rint(mul64(e.z, 8.0)); /* np.round: half to even (env:390) */
-    if (fabs(r) < 16777216.0) {
-        float zq = mul32((float)r, 0.125f);
-        o[2] = LEAN ? div_const32(zq, 100.0f, 1.0f / 100.0f) : __fdiv_rn(zq, 100.0f);
+    const double r = rint(mul64(e.z, 8.0));          /* np.round: half to even (env:390) */
+    const float qx = truncf(mul32(e.vx, 0.0625f));   /* (v / 16).astype(int): exact scaling, */
+    const float qy = truncf(mul32(e.vy, 0.0625f));   /* toward zero (env:383)                */
+    const float qz = truncf(mul32(e.vz, 0.0625f));
+    const bool small = (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) < 1048576.0f) &
+                       (fabs(r) < 16777216.0);
+    if (__builtin_expect(small, 1)) {
+        /* numerators exactly representable in f32: one rounding of the exact quotient */
+        const float zq = mul32((float)r, 0.125f);
+        if (LEAN) {
+            o[2] = div_const32(zq, 100.0f, 1.0f / 100.0f);
+            o[3] = div_const32(mul32(qx, 16.0f), 200.0f, 1.0f / 200.0f);
+            o[4] = div_const32(mul32(qy, 16.0f), 200.0f, 1.0f / 200.0f);
+            o[5] = div_const32(mul32(qz, 16.0f), 200.0f, 1.0f / 200.0f);
+        } else {
+            o[2] = __fdiv_rn(zq, 100.0f);
+            o[3] = __fdiv_rn(mul32(qx, 16.0f), 200.0f);
+            o[4] = __fdiv_rn(mul32(qy, 16.0f), 200.0f);
+            o[5] = __fdiv_rn(mul32(qz, 16.0f), 200.0f);
+        }
     } else {
+        /* the reference's own arithmetic: int64 * 16 -> f64, divided in f64 */
         o[2] = __double2float_rn(div64(mul64(r, 0.125), 100.0));
+        o[3] = __double2float_rn(div64(mul64((double)(long long)qx, 16.0), 200.0));
+        o[4] = __double2float_rn(div64(mul64((double)(long long)qy, 16.0), 200.0));
+        o[5] = __double2float_rn(div64(mul64((double)(long long)qz, 16.0), 200.0));
     }
-    o[3] = obs_vel<LEAN>(e.vx);
-    o[4] = obs_vel<LEAN>(e.vy);
-    o[5] = obs_vel<LEAN>(e.vz);
 }
 
 /* ------------------------------------------------------------------ phys.apply, one row ------ */
@@ -361,19 +384,26 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
 /* env.VectorPhysEnv.vector_step (env:482-510) for one env: hover override, ActionDecoder.map
  * (env:225-269), phys.apply, reward, time, done.  keybits: bit k = key action k; mouse: the raw
  * mouse action as f64 (continuous value or the discrete index). */
-template <bool STAMPS, bool LEAN>
+/* COMMON: the configuration every shipped setup uses (mouse action present and continuous, no
+ * hover, reward = y velocity) is compiled in; otherwise those switches are read from Params. */
+template <bool STAMPS, bool LEAN, bool COMMON>
 __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, double mouse,
                                      float &reward, bool &done)
 {
-    if (P.hover) { /* env:483-485 */
+    const bool hover = COMMON ? false : (bool)P.hover;
+    const bool allow_yaw = COMMON ? true : (bool)P.allow_yaw;
+    const bool discrete_yaw = COMMON ? false : (bool)P.discrete_yaw;
+    const bool speed_reward = COMMON ? false : (bool)P.speed_reward;
+
+    if (hover) { /* env:483-485 */
         e.vz = 0.0f;
         e.z = 100.0;
     }
 
     /* ---- ActionDecoder.map ---- */
     double mouse_x = 0.0;
-    if (P.allow_yaw) {
-        if (!P.discrete_yaw) {                                                           /* env:236 */
+    if (allow_yaw) {
+        if (!discrete_yaw) {                                                             /* env:236 */
             double t = mul64(mouse, P.max_yaw_delta);
             mouse_x = LEAN ? div_const(t, P.action_range, P.rcp_action_range) : div64(t, P.action_range);
         } else {                                                                         /* env:238 */
@@ -394,14 +424,12 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
             if (k < P.num_keys)
                 elapsed |= (now >= add64(e.stamp[k], P.key_delay) ? 1u : 0u) << k;
     } else {
-        /* four 5-bit "ticks until allowed" counters in one word: saturating decrement (a tick has
-         * passed since the last test), then gather the four is-zero bits */
-        uint32_t t = e.bits & TIMER_FIELD_MASK;
-        uint32_t nz = ((t | ((t | TIMER_HIGH) - TIMER_LOW)) >> 4) & TIMER_LOW;   /* field != 0 */
-        t -= nz;
-        uint32_t z = (((t | ((t | TIMER_HIGH) - TIMER_LOW)) >> 4) & TIMER_LOW) ^ TIMER_LOW;
+        /* four 5-bit counters "ticks this key stays blocked" in one word: gather the is-zero bit
+         * of each field (= elapsed), then decrement the non-zero fields by one */
+        const uint32_t t = e.bits & TIMER_FIELD_MASK;
+        const uint32_t z = ~((t | ((t | TIMER_HIGH) - TIMER_LOW)) >> 4) & TIMER_LOW; /* field == 0 */
         elapsed = ((z * 0x1111u) >> 12) & 0xFu;
-        e.bits = (e.bits & ~TIMER_FIELD_MASK) | t;
+        e.bits = e.bits - TIMER_LOW + z;           /* fields only: no borrow can leave a field */
     }
     const uint32_t down = keybits & (elapsed | last) & key_mask;                        /* env:243 */
     const uint32_t rising = down & ~last;                                               /* env:244 */
@@ -411,34 +439,25 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
             if ((rising >> k) & 1u)
                 e.stamp[k] = now;                                                        /* env:246 */
     } else {
-        uint32_t m = ((rising * 0x1111u) & TIMER_LOW) * TIMER_MAX;      /* bit k -> 5-bit field k mask */
-        e.bits = (e.bits & ~m) | (((uint32_t)P.delay_ticks * TIMER_LOW) & m);
+        const uint32_t m = ((rising * 0x1111u) & TIMER_LOW) * TIMER_MAX;   /* bit k -> field k mask */
+        e.bits = (e.bits & ~m) | (((uint32_t)P.press_ticks * TIMER_LOW) & m);
     }
 
     /* env:251-261: smoothed keys in {0, 1/2, 1}; fmove / smove are truncations of f32(max) * that,
-     * i.e. one of three / five values fixed by the config (tabulated in Params). */
-    int f2, s2; /* twice the smoothed forward key, twice (right - left) */
-    {
-        int dl = (down >> KEY_LEFT) & 1, dr = (down >> KEY_RIGHT) & 1, df = (down >> KEY_FORWARD) & 1;
-        if (P.smooth_keys) {
-            int ll = (last >> KEY_LEFT) & 1, lr = (last >> KEY_RIGHT) & 1, lf = (last >> KEY_FORWARD) & 1;
-            f2 = df + lf;
-            s2 = (dr + lr) - (dl + ll);
-        } else {
-            f2 = 2 * df;
-            s2 = 2 * (dr - dl);
-        }
-    }
+     * i.e. one of three / five values fixed by the config (tabulated in Params).  With prev = last
+     * keys (smooth_keys) or prev = keys (no smoothing) twice the smoothed key is key + prev. */
+    const uint32_t prev = P.smooth_keys ? last : down;
+    const uint32_t both = down | (prev << 4);
+    const int f2 = __popc(both & (0x11u << KEY_FORWARD));
+    const int s2 = __popc(both & (0x11u << KEY_RIGHT)) - __popc(both & (0x11u << KEY_LEFT));
     const double fmove = P.fmove_tab[f2];
     const double smove = P.smove_tab[s2 + 2];
 
-    bool jump;
-    if (P.auto_jump)
+    bool jump = false;                                                                  /* env:267 */
+    if (P.jump_mode == 2)
         jump = e.vz <= 16.0f;                                                           /* env:263 */
-    else if (P.allow_jump)
+    else if (P.jump_mode == 1)
         jump = (down >> KEY_JUMP) & 1u;                                                 /* env:265 */
-    else
-        jump = false;                                                                   /* env:267 */
 
     e.yaw = add64(e.yaw, mouse_x);                                                       /* env:258 */
     e.bits = (e.bits & ~(0xFu << F_LAST_KEY_SHIFT)) | (down << F_LAST_KEY_SHIFT);       /* env:256 */
@@ -459,7 +478,7 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
               (jr ? F_JUMP_RELEASED : 0u);
 
     /* ---- reward, time, done (env:500-506) ---- */
-    if (P.speed_reward)
+    if (speed_reward)
         reward = mul32(P.dt_f32, __fsqrt_rn(add32(mul32(e.vx, e.vx), mul32(e.vy, e.vy))));
     else
         reward = mul32(P.dt_f32, e.vy);

@@ -1,15 +1,16 @@
 /*
  * q1phys.cu -- sm_100a kernels and the C ABI (include/q1phys.h) of the q1physrl_env movement step.
  *
- * Data layout in HBM, per env (every array 256-byte aligned inside one pool allocation):
- *   rec_a  float4  {vx, vy, vz, bits}   bits = four 5-bit key timers | on_ground, jump_released,
- *                                       zero_start, last_keys[4], done_seen
- *   rec_b  double2 {z_pos, yaw}
- *   trem   double  time_remaining
+ * Data layout in HBM.  The state is tile-contiguous: envs are grouped in blocks of 128 and block b
+ * is 5120 contiguous bytes
+ *   float4  rec_a[128]  {vx, vy, vz, bits}   bits = four 5-bit key timers | on_ground,
+ *                                            jump_released, zero_start, last_keys[4], done_seen
+ *   double2 rec_b[128]  {z_pos, yaw}
+ *   double  trem[128]   time_remaining
+ * = 40 B per env, read once and written once per tick as ONE bulk copy per tile each way.  Beside it:
  *   [stamp mode only: (nk, n) f64 key-press time stamps]
- *   epoch  u32     reset count (RNG stream position), touched by resets only
- *   [TRACK only: f64 running episode return]
- * = 40 B per env in counter mode, read once and written once per tick with 16-byte accesses.
+ *   epoch  u32 (n,)   reset count (RNG stream position), touched by resets only
+ *   [TRACK only: f64 (n,) running episode return]
  *
  * Citations: phys = q1physrl_env/q1physrl_env/phys.py, env = q1physrl_env/q1physrl_env/env.py.
  */
@@ -31,24 +32,31 @@ using namespace q1;
 
 namespace {
 
-constexpr int kBlock = 128;        /* threads per CTA: one env per thread and tile */
+constexpr int kBlock = kTile;      /* threads per CTA: one env per thread, one state block per CTA tile */
 #ifndef Q1_STEP_CTAS
 #define Q1_STEP_CTAS 8
 #endif
 constexpr int kStepCtasPerSm = Q1_STEP_CTAS; /* resident CTAs per SM the persistent step kernel is sized for */
 
+__device__ __forceinline__ unsigned char *state_block(const Params &P, int64_t i)
+{
+    return P.state + (i / kTile) * kTileBytes;
+}
+
 template <bool STAMPS>
 __device__ __forceinline__ void load_env(const Params &P, int64_t i, Env &e)
 {
-    const float4 a = P.rec_a[i];
-    const double2 b = P.rec_b[i];
+    const unsigned char *blk = state_block(P, i);
+    const int l = (int)(i % kTile);
+    const float4 a = reinterpret_cast<const float4 *>(blk + kTileRecA)[l];
+    const double2 b = reinterpret_cast<const double2 *>(blk + kTileRecB)[l];
     e.vx = a.x;
     e.vy = a.y;
     e.vz = a.z;
     e.bits = __float_as_uint(a.w);
     e.z = b.x;
     e.yaw = b.y;
-    e.trem = P.trem[i];
+    e.trem = reinterpret_cast<const double *>(blk + kTileTrem)[l];
     if (STAMPS) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -59,9 +67,12 @@ __device__ __forceinline__ void load_env(const Params &P, int64_t i, Env &e)
 template <bool STAMPS>
 __device__ __forceinline__ void store_env(const Params &P, int64_t i, const Env &e)
 {
-    P.rec_a[i] = make_float4(e.vx, e.vy, e.vz, __uint_as_float(e.bits));
-    P.rec_b[i] = make_double2(e.z, e.yaw);
-    P.trem[i] = e.trem;
+    unsigned char *blk = state_block(P, i);
+    const int l = (int)(i % kTile);
+    reinterpret_cast<float4 *>(blk + kTileRecA)[l] =
+        make_float4(e.vx, e.vy, e.vz, __uint_as_float(e.bits));
+    reinterpret_cast<double2 *>(blk + kTileRecB)[l] = make_double2(e.z, e.yaw);
+    reinterpret_cast<double *>(blk + kTileTrem)[l] = e.trem;
     if (STAMPS) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -146,22 +157,21 @@ __device__ __forceinline__ void report_episodes(const Params &P, bool finished, 
     }
 }
 
-/* -- TMA (cp.async.bulk) + mbarrier plumbing ------------------------------------------------------ */
+/* -- TMA (cp.async.bulk) + mbarrier plumbing, shared-memory accesses by 32-bit window address ----- */
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-                 : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile("{\n"
                  ".reg .pred p;\n"
@@ -170,21 +180,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                  "@p bra DONE_%=;\n"
                  "bra WAIT_%=;\n"
                  "DONE_%=:\n"
-                 "}" ::"r"(smem_addr(bar)), "r"(parity)
+                 "}" ::"r"(bar), "r"(parity)
                  : "memory");
 }
 /* global -> shared bulk copy that signals `bar` with the byte count when it lands */
-__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
 }
 /* shared -> global bulk copy, tracked by this thread's bulk async-group */
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"(smem_addr(ssrc)), "r"(bytes)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -198,63 +207,117 @@ __device__ __forceinline__ void fence_smem_to_async_proxy()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float x, float y)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts_d2(uint32_t a, double x, double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts_d(uint32_t a, double x)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory");
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float x)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t x)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+}
 
 /* -- env.VectorPhysEnv.vector_step (env:482-510): one lockstep tick ---------------------------- */
 
-/* One tile = kBlock envs.  Shared-memory image of a tile in flight: the three state records and
- * the action arrays as they lie in HBM (inputs), the results as they will lie in HBM (outputs). */
-struct __align__(128) StepStage {
-    float4 rec_a[kBlock];          /* in, rewritten in place -> out */
-    double2 rec_b[kBlock];         /* in, rewritten in place -> out */
-    double trem[kBlock];           /* in, rewritten in place -> out */
-    double mouse[kBlock];          /* in: f32 / i32 use the first half */
-    uint8_t keys[kBlock * 4];      /* in: kBlock x num_keys */
-    float obs[kBlock * 6];         /* out */
-    float reward[kBlock];          /* out */
-    uint8_t done[kBlock];          /* out */
-    uint8_t zero_start[kBlock];    /* out */
+/* One tile = kTile envs.  Shared-memory image of a tile in flight: the state block and the action
+ * arrays as they lie in HBM (inputs; the state is rewritten in place), then the results as they
+ * will lie in HBM (outputs).  Byte offsets inside one stage: */
+enum : uint32_t {
+    ST_STATE = 0,                                  /* one state block: rec_a | rec_b | trem */
+    ST_MOUSE = ST_STATE + kTileBytes,              /* in: f32 / i32 use the first half */
+    ST_KEYS = ST_MOUSE + 8 * kTile,                /* in: kTile x num_keys bytes */
+    ST_OBS = ST_KEYS + 4 * kTile,                  /* out: float[kTile][6] */
+    ST_REWARD = ST_OBS + 24 * kTile,               /* out */
+    ST_DONE = ST_REWARD + 4 * kTile,               /* out */
+    ST_ZS = ST_DONE + kTile,                       /* out */
+    ST_BYTES = ST_ZS + kTile
 };
+static_assert(ST_BYTES % 128 == 0, "stage size keeps every sub-buffer 16-byte aligned");
 constexpr int kStages = 2;
 
 /* Persistent, TMA-pipelined step kernel (counter mode, full tiles, 16-byte aligned buffers).
  * gridDim.x = #SMs x kStepCtasPerSm; CTA c walks tiles c, c + grid, ...  All global traffic is bulk
- * copies issued by one elected thread: the next tile's records and actions stream into one stage
- * (completion on an mbarrier) while the CTA computes the current tile from the other; results
- * are written back in place in shared memory and leave as bulk stores.  Threads touch only shared
- * memory (16-byte LDS/STS, 32-bit addresses), so there is no per-thread global address arithmetic
- * and no load latency on the compute warps' scoreboard. */
-template <bool TRACK, bool LEAN>
+ * copies issued by one elected thread: the next tile's state block and actions stream into one
+ * stage (3 copies, completion on an mbarrier) while the CTA computes the current tile from the
+ * other; results are written back in place in shared memory and leave as 4-5 bulk stores.
+ * Threads touch only shared memory (16-byte LDS/STS, 32-bit addresses), so there is no per-thread
+ * global address arithmetic and no load latency on the compute warps' scoreboard. */
+template <bool TRACK, bool LEAN, bool COMMON>
 __global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
 k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
            const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
            float *__restrict__ reward, uint8_t *__restrict__ done,
            uint8_t *__restrict__ zero_start, int auto_reset, int64_t tiles)
 {
-    __shared__ StepStage stage[kStages];
+    __shared__ __align__(128) unsigned char stage_mem[kStages * ST_BYTES];
     __shared__ __align__(8) uint64_t full_bar[kStages];
-    const int tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x;
     const uint32_t nk = (uint32_t)P.num_keys;
-    const uint32_t mouse_bytes = P.allow_yaw ? (mouse_kind == Q1_MOUSE_F64 ? 8u : 4u) * kBlock : 0u;
-    const uint32_t in_bytes = sizeof(float4) * kBlock + sizeof(double2) * kBlock +
-                              sizeof(double) * kBlock + nk * kBlock + mouse_bytes;
+    const bool has_mouse = COMMON ? true : (bool)P.allow_yaw;
+    const uint32_t mouse_elt = COMMON ? 4u : (mouse_kind == Q1_MOUSE_F64 ? 8u : 4u);
+    const uint32_t mouse_bytes = has_mouse ? mouse_elt * kTile : 0u;
+    const uint32_t in_bytes = kTileBytes + nk * kTile + mouse_bytes;
+    const uint32_t smem0 = smem_addr(stage_mem);
+    const uint32_t bar0 = smem_addr(full_bar);
 
-    auto issue_loads = [&](int s, int64_t tile) {
-        StepStage &st = stage[s];
-        const int64_t base = tile * kBlock;
-        mbar_expect_tx(&full_bar[s], in_bytes);
-        bulk_load(st.rec_a, P.rec_a + base, sizeof(float4) * kBlock, &full_bar[s]);
-        bulk_load(st.rec_b, P.rec_b + base, sizeof(double2) * kBlock, &full_bar[s]);
-        bulk_load(st.trem, P.trem + base, sizeof(double) * kBlock, &full_bar[s]);
-        bulk_load(st.keys, keys + base * nk, nk * kBlock, &full_bar[s]);
+    auto issue_loads = [&](uint32_t s, int64_t tile) {
+        const uint32_t st = smem0 + s * ST_BYTES, bar = bar0 + s * 8u;
+        mbar_expect_tx(bar, in_bytes);
+        bulk_load(st + ST_STATE, P.state + tile * kTileBytes, kTileBytes, bar);
+        bulk_load(st + ST_KEYS, keys + tile * (nk * kTile), nk * kTile, bar);
         if (mouse_bytes)
-            bulk_load(st.mouse, static_cast<const char *>(mouse) + base * (mouse_bytes / kBlock),
-                      mouse_bytes, &full_bar[s]);
+            bulk_load(st + ST_MOUSE, static_cast<const char *>(mouse) + tile * mouse_bytes, mouse_bytes, bar);
     };
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; s++)
-            mbar_init(&full_bar[s], 1);
+            mbar_init(bar0 + s * 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_smem_to_async_proxy();
 #pragma unroll
@@ -266,57 +329,56 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     }
     __syncthreads();
 
-    int s = 0;
-    uint32_t parity = 0;
+    uint32_t s = 0, parity = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        StepStage &st = stage[s];
-        const int64_t i = tile * kBlock + tid;
-        mbar_wait(&full_bar[s], parity);
+        const uint32_t sb = smem0 + s * ST_BYTES;
+        mbar_wait(bar0 + s * 8u, parity);
 
         Env e;
         {
-            const float4 a = st.rec_a[tid];
-            const double2 b = st.rec_b[tid];
+            const float4 a = lds_f4(sb + ST_STATE + kTileRecA + tid * 16u);
+            const double2 b = lds_d2(sb + ST_STATE + kTileRecB + tid * 16u);
             e.vx = a.x;
             e.vy = a.y;
             e.vz = a.z;
             e.bits = __float_as_uint(a.w);
             e.z = b.x;
             e.yaw = b.y;
-            e.trem = st.trem[tid];
+            e.trem = lds_d(sb + ST_STATE + kTileTrem + tid * 8u);
         }
         uint32_t keybits;
         if (nk == 4) {
-            const uint32_t w = reinterpret_cast<const uint32_t *>(st.keys)[tid];
+            const uint32_t w = lds_u32(sb + ST_KEYS + tid * 4u);
             keybits = (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
         } else {
-            const uint8_t *k = st.keys + 3 * tid;
-            keybits = (k[0] & 1u) | ((k[1] & 1u) << 1) | ((k[2] & 1u) << 2);
+            const uint32_t ka = sb + ST_KEYS + tid * 3u;
+            keybits = (lds_u8(ka) & 1u) | ((lds_u8(ka + 1) & 1u) << 1) | ((lds_u8(ka + 2) & 1u) << 2);
         }
         double m = 0.0;
-        if (P.allow_yaw) {
-            if (mouse_kind == Q1_MOUSE_F32)
-                m = (double)reinterpret_cast<const float *>(st.mouse)[tid];
+        if (has_mouse) {
+            if (COMMON || mouse_kind == Q1_MOUSE_F32)
+                m = (double)__uint_as_float(lds_u32(sb + ST_MOUSE + tid * 4u));
             else if (mouse_kind == Q1_MOUSE_I32)
-                m = (double)reinterpret_cast<const int32_t *>(st.mouse)[tid];
+                m = (double)(int32_t)lds_u32(sb + ST_MOUSE + tid * 4u);
             else
-                m = st.mouse[tid];
+                m = lds_d(sb + ST_MOUSE + tid * 8u);
         }
         float r;
         bool d;
-        tick<false, LEAN>(P, e, keybits, m, r, d);
+        tick<false, LEAN, COMMON>(P, e, keybits, m, r, d);
         const bool zs = e.bits & F_ZERO_START;
         bool finished = false;
         double ret = 0.0;
+        const int64_t i = tile * kTile + tid;
         if (TRACK) {
             ret = add64(P.ep_return[i], (double)r);
             finished = d && !(e.bits & F_DONE_SEEN);
             if (finished)
                 e.bits |= F_DONE_SEEN;
         }
-        st.reward[tid] = r;
-        st.done[tid] = d ? 1 : 0;
-        st.zero_start[tid] = zs ? 1 : 0;
+        sts_f(sb + ST_REWARD + tid * 4u, r);
+        sts_u8(sb + ST_DONE + tid, d ? 1u : 0u);
+        sts_u8(sb + ST_ZS + tid, zs ? 1u : 0u);
         if (d && auto_reset) {
             uint32_t ep = P.epoch[i] + 1u;
             P.epoch[i] = ep;
@@ -328,27 +390,21 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         }
         float o[6];
         observe<LEAN>(P, e, o);
-        {
-            float2 *row = reinterpret_cast<float2 *>(&st.obs[tid * 6]);
-            row[0] = make_float2(o[0], o[1]);
-            row[1] = make_float2(o[2], o[3]);
-            row[2] = make_float2(o[4], o[5]);
-            st.rec_a[tid] = make_float4(e.vx, e.vy, e.vz, __uint_as_float(e.bits));
-            st.rec_b[tid] = make_double2(e.z, e.yaw);
-            st.trem[tid] = e.trem;
-        }
+        sts_f2(sb + ST_OBS + tid * 24u, o[0], o[1]);
+        sts_f2(sb + ST_OBS + tid * 24u + 8u, o[2], o[3]);
+        sts_f2(sb + ST_OBS + tid * 24u + 16u, o[4], o[5]);
+        sts_f4(sb + ST_STATE + kTileRecA + tid * 16u, e.vx, e.vy, e.vz, __uint_as_float(e.bits));
+        sts_d2(sb + ST_STATE + kTileRecB + tid * 16u, e.z, e.yaw);
+        sts_d(sb + ST_STATE + kTileTrem + tid * 8u, e.trem);
         fence_smem_to_async_proxy();
         __syncthreads();
         if (tid == 0) {
-            const int64_t base = tile * kBlock;
-            bulk_store(P.rec_a + base, st.rec_a, sizeof(float4) * kBlock);
-            bulk_store(P.rec_b + base, st.rec_b, sizeof(double2) * kBlock);
-            bulk_store(P.trem + base, st.trem, sizeof(double) * kBlock);
-            bulk_store(obs + base * 6, st.obs, sizeof(float) * 6 * kBlock);
-            bulk_store(reward + base, st.reward, sizeof(float) * kBlock);
-            bulk_store(done + base, st.done, kBlock);
+            bulk_store(P.state + tile * kTileBytes, sb + ST_STATE, kTileBytes);
+            bulk_store(obs + tile * (6 * kTile), sb + ST_OBS, 24 * kTile);
+            bulk_store(reward + tile * kTile, sb + ST_REWARD, 4 * kTile);
+            bulk_store(done + tile * kTile, sb + ST_DONE, kTile);
             if (zero_start)
-                bulk_store(zero_start + base, st.zero_start, kBlock);
+                bulk_store(zero_start + tile * kTile, sb + ST_ZS, kTile);
             bulk_commit();
             const int64_t next = tile + (int64_t)kStages * gridDim.x;
             if (next < tiles) {
@@ -368,7 +424,7 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
 }
 
 /* The same tick, one env per thread with plain loads and stores: f64-stamp mode, ragged tails
- * (n not a multiple of kBlock) and buffers that are not 16-byte aligned.  Covers envs [first, n). */
+ * (n not a multiple of kTile) and buffers that are not 16-byte aligned.  Covers envs [first, n). */
 template <bool STAMPS, bool TRACK, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
@@ -389,7 +445,7 @@ k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             m = load_mouse(mouse, mouse_kind, i);
         float r;
         bool d;
-        tick<STAMPS, LEAN>(P, e, keybits, m, r, d);
+        tick<STAMPS, LEAN, false>(P, e, keybits, m, r, d);
         zs = e.bits & F_ZERO_START;
         if (TRACK) {
             ret = add64(P.ep_return[i], (double)r);
@@ -481,7 +537,7 @@ k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick
         policy_action(P, policy, policy_seed, gidx, tick_base + (uint32_t)t, keybits, m);
         float r;
         bool d;
-        tick<STAMPS, LEAN>(P, e, keybits, m, r, d);
+        tick<STAMPS, LEAN, false>(P, e, keybits, m, r, d);
         rsum = add32(rsum, r);
         if (TRACK) {
             ret = add64(ret, (double)r);
@@ -634,7 +690,7 @@ __global__ void __launch_bounds__(256)
 k_selftest(uint64_t iters, uint64_t seed, unsigned long long *__restrict__ out)
 {
     uint64_t rng = seed * 0x2545F4914F6CDD1Dull + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2 + 1;
-    unsigned long long bad[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long bad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const double consts[8] = {10.0, (double)10.08f, 180.0, 90.0, 5.0, 7.0, 4.0, 0.013888888888888};
     for (uint64_t it = 0; it < iters; it++) {
         /* 0: reciprocal, wide range */
@@ -666,13 +722,17 @@ k_selftest(uint64_t iters, uint64_t seed, unsigned long long *__restrict__ out)
         float v = q * 16.0f;
         bad[5] += __float_as_uint(div_const32(v, 200.0f, 1.0f / 200.0f)) !=
                   __float_as_uint(__double2float_rn(__ddiv_rn((double)v, 200.0)));
+        bad[6] += __float_as_uint(div_const32_long(v, 200.0f, 1.0f / 200.0f)) !=
+                  __float_as_uint(__double2float_rn(__ddiv_rn((double)v, 200.0)));
     }
     for (uint64_t m = tid; m < (1ull << 25); m += nth) {
         float zq = (float)((long long)m - (1ll << 24)) * 0.125f;
         bad[5] += __float_as_uint(div_const32(zq, 100.0f, 1.0f / 100.0f)) !=
                   __float_as_uint(__double2float_rn(__ddiv_rn((double)zq, 100.0)));
+        bad[7] += __float_as_uint(div_const32_long(zq, 100.0f, 1.0f / 100.0f)) !=
+                  __float_as_uint(__double2float_rn(__ddiv_rn((double)zq, 100.0)));
     }
-    for (int k = 0; k < 6; k++)
+    for (int k = 0; k < 8; k++)
         if (bad[k])
             atomicAdd(&out[k], bad[k]);
 }
@@ -792,6 +852,8 @@ int derive_params(const q1_config &c, Params &P, bool &counters_exact)
      * only for time_limit >= 1; below that the f64 stamps are kept. */
     counters_exact = counters_exact && c.time_limit >= 1.0;
     P.delay_ticks = counters_exact ? (int32_t)std::ceil(q) : 0;
+    P.press_ticks = P.delay_ticks > 0 ? P.delay_ticks - 1 : 0;
+    P.jump_mode = c.auto_jump ? 2 : (c.allow_jump ? 1 : 0);
     return Q1_OK;
 }
 
@@ -926,7 +988,8 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
         off = align_up(off + bytes);
         return o;
     };
-    size_t o_a = take(16 * n), o_b = take(16 * n), o_trem = take(8 * n);
+    const size_t blocks = (n + kTile - 1) / kTile;
+    size_t o_state = take(blocks * kTileBytes);
     size_t o_stamps = env->stamps ? take(8 * n * nk) : 0;
     size_t o_epoch = take(4 * n);
     size_t o_ret = env->track ? take(8 * n) : 0;
@@ -943,10 +1006,14 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     if (env->sm_count <= 0)
         env->sm_count = 148;
     /* kStepCtasPerSm CTAs x 21 KB of staging must fit: ask for the large shared-memory carveout */
-    cudaFuncSetAttribute(k_step_tma<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_step_tma<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_step_tma<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_step_tma<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    {
+        const void *fns[] = {(const void *)k_step_tma<false, false, false>, (const void *)k_step_tma<false, false, true>,
+                             (const void *)k_step_tma<false, true, false>,  (const void *)k_step_tma<false, true, true>,
+                             (const void *)k_step_tma<true, false, false>,  (const void *)k_step_tma<true, false, true>,
+                             (const void *)k_step_tma<true, true, false>,   (const void *)k_step_tma<true, true, true>};
+        for (const void *f : fns)
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
     cudaError_t err = cudaMalloc(&env->pool, env->pool_bytes);
     if (err != cudaSuccess) {
         delete env;
@@ -960,9 +1027,7 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
         return fail(Q1_ECUDA, std::string("cudaMemset: ") + cudaGetErrorString(err));
     }
     char *base = static_cast<char *>(env->pool);
-    P.rec_a = reinterpret_cast<float4 *>(base + o_a);
-    P.rec_b = reinterpret_cast<double2 *>(base + o_b);
-    P.trem = reinterpret_cast<double *>(base + o_trem);
+    P.state = reinterpret_cast<unsigned char *>(base + o_state);
     P.stamps = env->stamps ? reinterpret_cast<double *>(base + o_stamps) : nullptr;
     P.epoch = reinterpret_cast<uint32_t *>(base + o_epoch);
     P.ep_return = env->track ? reinterpret_cast<double *>(base + o_ret) : nullptr;
@@ -1122,15 +1187,24 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
         (!zero_start || aligned16(zero_start)) && (!env->P.allow_yaw || aligned16(mouse)))
         tma_tiles = n / kBlock;
     int rc = Q1_OK;
-    if (tma_tiles > 0)
+    if (tma_tiles > 0) {
+        /* the compiled-in configuration: continuous f32 mouse action, no hover, y-velocity reward */
+        const bool common = env->P.allow_yaw && !env->P.discrete_yaw && !env->P.hover &&
+                            !env->P.speed_reward && mouse_kind == Q1_MOUSE_F32;
         rc = dispatch(env, [&](auto, auto tr, auto ln) {
             unsigned grid = (unsigned)std::min<int64_t>(tma_tiles,
                                                         (int64_t)env->sm_count * kStepCtasPerSm);
-            k_step_tma<decltype(tr)::value, decltype(ln)::value><<<grid, kBlock, 0, s>>>(
-                env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset,
-                tma_tiles);
+            if (common)
+                k_step_tma<decltype(tr)::value, decltype(ln)::value, true><<<grid, kBlock, 0, s>>>(
+                    env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset,
+                    tma_tiles);
+            else
+                k_step_tma<decltype(tr)::value, decltype(ln)::value, false><<<grid, kBlock, 0, s>>>(
+                    env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset,
+                    tma_tiles);
             return check_launch("k_step_tma");
         });
+    }
     const int64_t first = tma_tiles * kBlock;
     if (rc == Q1_OK && first < n)
         rc = dispatch(env, [&](auto st, auto tr, auto ln) {
@@ -1265,38 +1339,35 @@ int q1_get_state_host(q1_env *env, const q1_state_view *v)
     const Params &P = env->P;
     const size_t n = (size_t)P.n;
     const int nk = P.num_keys;
-    std::vector<float4> ra;
-    if (v->vel || v->on_ground || v->jump_released || v->zero_start || v->last_keys ||
-        (v->last_press && !env->stamps)) {
-        ra.resize(n);
-        Q1_CUDA(cudaMemcpy(ra.data(), P.rec_a, 16 * n, cudaMemcpyDeviceToHost));
-    }
+    const size_t blocks = (n + kTile - 1) / kTile;
+    std::vector<unsigned char> st(blocks * kTileBytes);
+    Q1_CUDA(cudaMemcpy(st.data(), P.state, st.size(), cudaMemcpyDeviceToHost));
+    auto rec_a = [&](size_t i) {
+        return reinterpret_cast<float4 *>(st.data() + (i / kTile) * kTileBytes + kTileRecA) + i % kTile;
+    };
+    auto rec_b = [&](size_t i) {
+        return reinterpret_cast<double2 *>(st.data() + (i / kTile) * kTileBytes + kTileRecB) + i % kTile;
+    };
+    auto trem_of = [&](size_t i) {
+        return reinterpret_cast<double *>(st.data() + (i / kTile) * kTileBytes + kTileTrem) + i % kTile;
+    };
     if (v->vel)
         for (size_t i = 0; i < n; i++) {
-            v->vel[3 * i] = ra[i].x;
-            v->vel[3 * i + 1] = ra[i].y;
-            v->vel[3 * i + 2] = ra[i].z;
+            v->vel[3 * i] = rec_a(i)->x;
+            v->vel[3 * i + 1] = rec_a(i)->y;
+            v->vel[3 * i + 2] = rec_a(i)->z;
         }
-    if (v->z_pos || v->yaw) {
-        std::vector<double2> rb(n);
-        Q1_CUDA(cudaMemcpy(rb.data(), P.rec_b, 16 * n, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; i++) {
-            if (v->z_pos)
-                v->z_pos[i] = rb[i].x;
-            if (v->yaw)
-                v->yaw[i] = rb[i].y;
-        }
-    }
-    std::vector<double> trem;
-    if (v->time_remaining || (v->last_press && !env->stamps)) {
-        trem.resize(n);
-        Q1_CUDA(cudaMemcpy(trem.data(), P.trem, 8 * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) {
+        if (v->z_pos)
+            v->z_pos[i] = rec_b(i)->x;
+        if (v->yaw)
+            v->yaw[i] = rec_b(i)->y;
         if (v->time_remaining)
-            memcpy(v->time_remaining, trem.data(), 8 * n);
+            v->time_remaining[i] = *trem_of(i);
     }
     auto bits_of = [&](size_t i) {
         uint32_t w;
-        memcpy(&w, &ra[i].w, 4);
+        memcpy(&w, &rec_a(i)->w, 4);
         return w;
     };
     if (v->on_ground || v->jump_released || v->zero_start || v->last_keys) {
@@ -1315,22 +1386,22 @@ int q1_get_state_host(q1_env *env, const q1_state_view *v)
     }
     if (v->last_press) {
         if (env->stamps) {
-            std::vector<double> st(n * nk);
-            Q1_CUDA(cudaMemcpy(st.data(), P.stamps, 8 * n * nk, cudaMemcpyDeviceToHost));
+            std::vector<double> sp(n * nk);
+            Q1_CUDA(cudaMemcpy(sp.data(), P.stamps, 8 * n * nk, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < n; i++)
                 for (int k = 0; k < nk; k++)
-                    v->last_press[i * nk + k] = st[(size_t)k * n + i];
+                    v->last_press[i * nk + k] = sp[(size_t)k * n + i];
         } else {
-            /* Counter mode keeps "ticks until the key may be pressed again"; the stamp handed back
+            /* Counter mode keeps "ticks this key stays blocked"; the stamp handed back
              * is the one that yields the same future decode decisions (exact stamps need
              * Q1_F_FORCE_F64_STAMPS). */
             for (size_t i = 0; i < n; i++) {
-                double now = P.time_limit - trem[i];
+                double now = P.time_limit - *trem_of(i);
                 uint32_t w = bits_of(i);
                 for (int k = 0; k < nk; k++) {
                     int r = (w >> (TIMER_BITS * k)) & TIMER_MAX;
                     v->last_press[i * nk + k] =
-                        r == 0 ? -P.key_delay : now - (double)(P.delay_ticks - r + 1) * P.dt;
+                        r == 0 ? -P.key_delay : now - (double)(P.delay_ticks - r) * P.dt;
                 }
             }
         }
@@ -1352,36 +1423,29 @@ int q1_set_state_host(q1_env *env, const q1_state_view *v)
     const Params &P = env->P;
     const size_t n = (size_t)P.n;
     const int nk = P.num_keys;
-    if (v->z_pos || v->yaw) {
-        std::vector<double2> rb(n);
-        Q1_CUDA(cudaMemcpy(rb.data(), P.rec_b, 16 * n, cudaMemcpyDeviceToHost));
+    {
+        const size_t blocks = (n + kTile - 1) / kTile;
+        std::vector<unsigned char> st(blocks * kTileBytes);
+        Q1_CUDA(cudaMemcpy(st.data(), P.state, st.size(), cudaMemcpyDeviceToHost));
+        const bool counters = v->last_press && !env->stamps;
         for (size_t i = 0; i < n; i++) {
-            if (v->z_pos)
-                rb[i].x = v->z_pos[i];
-            if (v->yaw)
-                rb[i].y = v->yaw[i];
-        }
-        Q1_CUDA(cudaMemcpy(P.rec_b, rb.data(), 16 * n, cudaMemcpyHostToDevice));
-    }
-    if (v->time_remaining)
-        Q1_CUDA(cudaMemcpy(P.trem, v->time_remaining, 8 * n, cudaMemcpyHostToDevice));
-    const bool counters = v->last_press && !env->stamps;
-    if (v->vel || v->on_ground || v->jump_released || v->zero_start || v->last_keys || counters) {
-        std::vector<float4> ra(n);
-        Q1_CUDA(cudaMemcpy(ra.data(), P.rec_a, 16 * n, cudaMemcpyDeviceToHost));
-        std::vector<double> trem;
-        if (counters) {
-            trem.resize(n);
-            Q1_CUDA(cudaMemcpy(trem.data(), P.trem, 8 * n, cudaMemcpyDeviceToHost));
-        }
-        for (size_t i = 0; i < n; i++) {
+            unsigned char *blk = st.data() + (i / kTile) * kTileBytes;
+            float4 *ra = reinterpret_cast<float4 *>(blk + kTileRecA) + i % kTile;
+            double2 *rb = reinterpret_cast<double2 *>(blk + kTileRecB) + i % kTile;
+            double *tr = reinterpret_cast<double *>(blk + kTileTrem) + i % kTile;
             if (v->vel) {
-                ra[i].x = v->vel[3 * i];
-                ra[i].y = v->vel[3 * i + 1];
-                ra[i].z = v->vel[3 * i + 2];
+                ra->x = v->vel[3 * i];
+                ra->y = v->vel[3 * i + 1];
+                ra->z = v->vel[3 * i + 2];
             }
+            if (v->z_pos)
+                rb->x = v->z_pos[i];
+            if (v->yaw)
+                rb->y = v->yaw[i];
+            if (v->time_remaining)
+                *tr = v->time_remaining[i];
             uint32_t x;
-            memcpy(&x, &ra[i].w, 4);
+            memcpy(&x, &ra->w, 4);
             if (v->on_ground)
                 x = (x & ~F_ON_GROUND) | (v->on_ground[i] ? F_ON_GROUND : 0u);
             if (v->jump_released)
@@ -1394,13 +1458,13 @@ int q1_set_state_host(q1_env *env, const q1_state_view *v)
                     x |= (uint32_t)(v->last_keys[i * nk + k] & 1u) << (F_LAST_KEY_SHIFT + k);
             }
             if (counters) {
-                /* ticks until now_j >= stamp + delay holds, now_j = now + j * dt (env:241-242);
-                 * +1 because the kernel decrements before it tests */
-                double now = P.time_limit - trem[i];
+                /* number of coming ticks j = 0, 1, .. for which now + j * dt >= stamp + delay
+                 * (env:241-242) still fails */
+                double now = P.time_limit - *tr;
                 x &= ~TIMER_FIELD_MASK;
                 for (int k = 0; k < nk; k++) {
                     double need = (v->last_press[i * nk + k] + P.key_delay - now) / P.dt;
-                    double r = std::ceil(need - 1e-9) + 1.0;
+                    double r = std::ceil(need - 1e-9);
                     if (!(r > 0))
                         r = 0;
                     if (r > TIMER_MAX)
@@ -1408,9 +1472,9 @@ int q1_set_state_host(q1_env *env, const q1_state_view *v)
                     x |= (uint32_t)r << (TIMER_BITS * k);
                 }
             }
-            memcpy(&ra[i].w, &x, 4);
+            memcpy(&ra->w, &x, 4);
         }
-        Q1_CUDA(cudaMemcpy(P.rec_a, ra.data(), 16 * n, cudaMemcpyHostToDevice));
+        Q1_CUDA(cudaMemcpy(P.state, st.data(), st.size(), cudaMemcpyHostToDevice));
     }
     if (v->last_press && env->stamps) {
         std::vector<double> st(n * nk);
@@ -1595,7 +1659,7 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n, uint8_t *last_ke
     return Q1_OK;
 }
 
-int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[6])
+int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[8])
 {
     if (!mismatches)
         return fail(Q1_EINVAL, "mismatches is NULL");
@@ -1603,14 +1667,14 @@ int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t m
     if (!guard.ok)
         return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
     unsigned long long *d_out = nullptr;
-    Q1_CUDA(cudaMalloc(&d_out, 6 * sizeof(unsigned long long)));
-    Q1_CUDA(cudaMemset(d_out, 0, 6 * sizeof(unsigned long long)));
+    Q1_CUDA(cudaMalloc(&d_out, 8 * sizeof(unsigned long long)));
+    Q1_CUDA(cudaMemset(d_out, 0, 8 * sizeof(unsigned long long)));
     const unsigned blocks = 148 * 8;
     uint64_t iters = (samples + (uint64_t)blocks * 256 - 1) / ((uint64_t)blocks * 256);
     k_selftest<<<blocks, 256>>>(iters, seed, d_out);
     int rc = check_launch("k_selftest");
     if (rc == Q1_OK) {
-        cudaError_t err = cudaMemcpy(mismatches, d_out, 6 * sizeof(unsigned long long),
+        cudaError_t err = cudaMemcpy(mismatches, d_out, 8 * sizeof(unsigned long long),
                                      cudaMemcpyDeviceToHost);
         if (err != cudaSuccess)
             rc = fail(Q1_ECUDA, std::string("k_selftest: ") + cudaGetErrorString(err));
