@@ -201,6 +201,18 @@ __device__ __forceinline__ double unit53(uint32_t a, uint32_t b)
 /* Minimax coefficients of sin(r) = r + r^3 S(r^2) and cos(r) = 1 - r^2/2 + r^4 C(r^2) on
  * |r| <= pi/4 (the fdlibm k_sin / k_cos sets), kept in the constant bank so the FP64 pipe reads
  * them as operands instead of building each 64-bit immediate from two moves. */
+/* Other 64-bit constants of the tick, read from the constant bank as well. */
+__constant__ double kTickConst[10] = {
+    3.14159265358979323846,       /* 0: np.pi */
+    1.0 / 180.0,                  /* 1 */
+    1.0 / 90.0,                   /* 2 */
+    6.36619772367581382433e-01,   /* 3: 2 / pi */
+    6755399441055744.0,           /* 4: 1.5 * 2^52 */
+    -1.57079632679489655800e+00,  /* 5: -pi/2 high */
+    -6.12323399573676603587e-17,  /* 6: -pi/2 middle */
+    1.4973849048591698e-33,       /* 7: -pi/2 low (the third term is negative) */
+    1.0e5,                        /* 8: sincos fast-path bound */
+    0.0};
 __constant__ double kSinCosCoef[12] = {
     -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
     2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
@@ -212,17 +224,17 @@ __constant__ double kSinCosCoef[12] = {
  * reduction with fused multiply-adds, two Horner chains.  Larger arguments take libdevice's path. */
 __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
 {
-    if (__builtin_expect(!(fabs(a) < 1.0e5), 0)) {
+    if (__builtin_expect(!(fabs(a) < kTickConst[8]), 0)) {
         sincos(a, &s, &c);
         return;
     }
-    const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
-    double t = __fma_rn(a, 6.36619772367581382433e-01, magic);
+    const double magic = kTickConst[4]; /* 1.5 * 2^52 */
+    double t = __fma_rn(a, kTickConst[3], magic);
     const int q = __double2loint(t);
     const double j = __dsub_rn(t, magic);
-    double r = __fma_rn(j, -1.57079632679489655800e+00, a);
-    r = __fma_rn(j, -6.12323399573676603587e-17, r);
-    r = __fma_rn(j, 1.4973849048591698e-33, r); /* pi/2 = 1.5707963267948966 + 6.123233995736766e-17 - 1.4973849048591698e-33 */
+    double r = __fma_rn(j, kTickConst[5], a);
+    r = __fma_rn(j, kTickConst[6], r);
+    r = __fma_rn(j, kTickConst[7], r); /* pi/2 = 1.5707963267948966 + 6.123233995736766e-17 - 1.4973849048591698e-33 */
     const double z = __dmul_rn(r, r);
     double ps = kSinCosCoef[5];
     ps = __fma_rn(ps, z, kSinCosCoef[4]);
@@ -259,7 +271,7 @@ __device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6
 {
     if (LEAN) {
         o[0] = __double2float_rn(div_const(e.trem, P.time_limit, P.rcp_time_limit));
-        o[1] = __double2float_rn(div_const(e.yaw, 90.0, 1.0 / 90.0));
+        o[1] = __double2float_rn(div_const(e.yaw, 90.0, kTickConst[2]));
     } else {
         o[0] = __double2float_rn(div64(e.trem, P.time_limit));
         o[1] = __double2float_rn(div64(e.yaw, 90.0));
@@ -464,13 +476,10 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
 
     /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
     double sy, cy;
-    {
-        double t = mul64(e.yaw, kPi);                                                    /* phys:58-59 */
-        if (LEAN)
-            sincos_rad(div_const(t, 180.0, 1.0 / 180.0), sy, cy);
-        else
-            sincos(div64(t, 180.0), &sy, &cy);
-    }
+    if (LEAN)                                                                            /* phys:58-59 */
+        sincos_rad(div_const(mul64(e.yaw, kTickConst[0]), 180.0, kTickConst[1]), sy, cy);
+    else
+        sincos(div64(mul64(e.yaw, kPi), 180.0), &sy, &cy);
     bool og = e.bits & F_ON_GROUND, jr = e.bits & F_JUMP_RELEASED;
     move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,
                     P.accel_dt, P.gravity_dt);

@@ -302,10 +302,12 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     const uint32_t mouse_elt = COMMON ? 4u : (mouse_kind == Q1_MOUSE_F64 ? 8u : 4u);
     const uint32_t mouse_bytes = has_mouse ? mouse_elt * kTile : 0u;
     const uint32_t in_bytes = kTileBytes + nk * kTile + mouse_bytes;
-    const uint32_t smem0 = smem_addr(stage_mem);
-    const uint32_t bar0 = smem_addr(full_bar);
+    uint32_t smem0 = smem_addr(stage_mem);
+    uint32_t bar0 = smem_addr(full_bar);
+    asm volatile("" : "+r"(smem0), "+r"(bar0)); /* keep both in registers: no re-derivation per tile */
 
     auto issue_loads = [&](uint32_t s, int64_t tile) {
+        asm volatile("" : "+l"(tile)); /* address arithmetic stays inside the elected thread's branch */
         const uint32_t st = smem0 + s * ST_BYTES, bar = bar0 + s * 8u;
         mbar_expect_tx(bar, in_bytes);
         bulk_load(st + ST_STATE, P.state + tile * kTileBytes, kTileBytes, bar);
@@ -399,14 +401,16 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         fence_smem_to_async_proxy();
         __syncthreads();
         if (tid == 0) {
-            bulk_store(P.state + tile * kTileBytes, sb + ST_STATE, kTileBytes);
-            bulk_store(obs + tile * (6 * kTile), sb + ST_OBS, 24 * kTile);
-            bulk_store(reward + tile * kTile, sb + ST_REWARD, 4 * kTile);
-            bulk_store(done + tile * kTile, sb + ST_DONE, kTile);
+            int64_t t = tile;
+            asm volatile("" : "+l"(t));
+            bulk_store(P.state + t * kTileBytes, sb + ST_STATE, kTileBytes);
+            bulk_store(obs + t * (6 * kTile), sb + ST_OBS, 24 * kTile);
+            bulk_store(reward + t * kTile, sb + ST_REWARD, 4 * kTile);
+            bulk_store(done + t * kTile, sb + ST_DONE, kTile);
             if (zero_start)
-                bulk_store(zero_start + tile * kTile, sb + ST_ZS, kTile);
+                bulk_store(zero_start + t * kTile, sb + ST_ZS, kTile);
             bulk_commit();
-            const int64_t next = tile + (int64_t)kStages * gridDim.x;
+            const int64_t next = t + (int64_t)kStages * gridDim.x;
             if (next < tiles) {
                 bulk_wait_read_all(); /* the stores have drained this stage: refill it */
                 issue_loads(s, next);
