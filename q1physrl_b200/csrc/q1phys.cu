@@ -264,29 +264,35 @@ __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t x)
 
 /* -- env.VectorPhysEnv.vector_step (env:482-510): one lockstep tick ---------------------------- */
 
-/* One tile = kTile envs.  Shared-memory image of a tile in flight: the state block and the action
- * arrays as they lie in HBM (inputs; the state is rewritten in place), then the results as they
- * will lie in HBM (outputs).  Byte offsets inside one stage: */
+/* One tile = kTile envs.  Shared-memory image of a tile in flight.  Inputs (a ring of kInStages):
+ * the state block and the action arrays as they lie in HBM; the state is rewritten in place and
+ * stored back from there.  Outputs (a ring of kOutStages): the results as they will lie in HBM. */
 enum : uint32_t {
-    ST_STATE = 0,                                  /* one state block: rec_a | rec_b | trem */
-    ST_MOUSE = ST_STATE + kTileBytes,              /* in: f32 / i32 use the first half */
-    ST_KEYS = ST_MOUSE + 8 * kTile,                /* in: kTile x num_keys bytes */
-    ST_OBS = ST_KEYS + 4 * kTile,                  /* out: float[kTile][6] */
-    ST_REWARD = ST_OBS + 24 * kTile,               /* out */
-    ST_DONE = ST_REWARD + 4 * kTile,               /* out */
-    ST_ZS = ST_DONE + kTile,                       /* out */
-    ST_BYTES = ST_ZS + kTile
+    IN_STATE = 0,                                  /* one state block: rec_a | rec_b | trem */
+    IN_MOUSE = IN_STATE + kTileBytes,              /* f32 / i32 mouse actions */
+    IN_KEYS = IN_MOUSE + 4 * kTile,                /* kTile x num_keys bytes */
+    IN_BYTES = IN_KEYS + 4 * kTile,
+    OUT_OBS = 0,                                   /* float[kTile][6] */
+    OUT_REWARD = OUT_OBS + 24 * kTile,
+    OUT_DONE = OUT_REWARD + 4 * kTile,
+    OUT_ZS = OUT_DONE + kTile,
+    OUT_BYTES = OUT_ZS + kTile
 };
-static_assert(ST_BYTES % 128 == 0, "stage size keeps every sub-buffer 16-byte aligned");
-constexpr int kStages = 2;
+static_assert(IN_BYTES % 128 == 0 && OUT_BYTES % 128 == 0, "every sub-buffer stays 16-byte aligned");
+constexpr int kInStages = 3;
+constexpr int kOutStages = 2;
 
-/* Persistent, TMA-pipelined step kernel (counter mode, full tiles, 16-byte aligned buffers).
- * gridDim.x = #SMs x kStepCtasPerSm; CTA c walks tiles c, c + grid, ...  All global traffic is bulk
- * copies issued by one elected thread: the next tile's state block and actions stream into one
- * stage (3 copies, completion on an mbarrier) while the CTA computes the current tile from the
- * other; results are written back in place in shared memory and leave as 4-5 bulk stores.
- * Threads touch only shared memory (16-byte LDS/STS, 32-bit addresses), so there is no per-thread
- * global address arithmetic and no load latency on the compute warps' scoreboard. */
+/* Persistent, TMA-pipelined step kernel (counter mode, full tiles, 16-byte aligned buffers, f32 or
+ * i32 mouse).  gridDim.x = #SMs x kStepCtasPerSm; CTA c walks tiles c, c + grid, ...
+ *
+ * All global traffic is bulk copies (cp.async.bulk, the TMA engine): a tile's state block and
+ * actions stream into an input stage two tiles ahead (3 copies, completion on an mbarrier); the
+ * threads read their env from shared memory, run the fused tick, write the new state back in place
+ * and the results into an output stage; after one CTA barrier the tile leaves as 5 bulk stores.
+ * The issue work is spread over the four warps' lane 0 (state store / obs+reward / done+zs / next
+ * loads), and every wait on an earlier bulk group sits one full tile after its issue, so no warp
+ * ever blocks on the TMA engine.  Threads touch only shared memory (16-byte LDS/STS, 32-bit
+ * addresses): no per-thread global address arithmetic, no load latency on the compute warps. */
 template <bool TRACK, bool LEAN, bool COMMON>
 __global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
 k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
@@ -294,76 +300,77 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
            float *__restrict__ reward, uint8_t *__restrict__ done,
            uint8_t *__restrict__ zero_start, int auto_reset, int64_t tiles)
 {
-    __shared__ __align__(128) unsigned char stage_mem[kStages * ST_BYTES];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(128) unsigned char in_mem[kInStages * IN_BYTES];
+    __shared__ __align__(128) unsigned char out_mem[kOutStages * OUT_BYTES];
+    __shared__ __align__(8) uint64_t full_bar[kInStages];
     const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const bool issuer = (tid & 31u) == 0;
     const uint32_t nk = (uint32_t)P.num_keys;
     const bool has_mouse = COMMON ? true : (bool)P.allow_yaw;
-    const uint32_t mouse_elt = COMMON ? 4u : (mouse_kind == Q1_MOUSE_F64 ? 8u : 4u);
-    const uint32_t mouse_bytes = has_mouse ? mouse_elt * kTile : 0u;
+    const uint32_t mouse_bytes = has_mouse ? 4u * kTile : 0u;
     const uint32_t in_bytes = kTileBytes + nk * kTile + mouse_bytes;
-    uint32_t smem0 = smem_addr(stage_mem);
-    uint32_t bar0 = smem_addr(full_bar);
-    asm volatile("" : "+r"(smem0), "+r"(bar0)); /* keep both in registers: no re-derivation per tile */
+    uint32_t in0 = smem_addr(in_mem), out0 = smem_addr(out_mem), bar0 = smem_addr(full_bar);
+    asm volatile("" : "+r"(in0), "+r"(out0), "+r"(bar0)); /* pinned: no re-derivation per tile */
 
     auto issue_loads = [&](uint32_t s, int64_t tile) {
-        asm volatile("" : "+l"(tile)); /* address arithmetic stays inside the elected thread's branch */
-        const uint32_t st = smem0 + s * ST_BYTES, bar = bar0 + s * 8u;
+        asm volatile("" : "+l"(tile)); /* address arithmetic stays inside the issuing lane's branch */
+        const uint32_t st = in0 + s * IN_BYTES, bar = bar0 + s * 8u;
         mbar_expect_tx(bar, in_bytes);
-        bulk_load(st + ST_STATE, P.state + tile * kTileBytes, kTileBytes, bar);
-        bulk_load(st + ST_KEYS, keys + tile * (nk * kTile), nk * kTile, bar);
+        bulk_load(st + IN_STATE, P.state + tile * kTileBytes, kTileBytes, bar);
+        bulk_load(st + IN_KEYS, keys + tile * (nk * kTile), nk * kTile, bar);
         if (mouse_bytes)
-            bulk_load(st + ST_MOUSE, static_cast<const char *>(mouse) + tile * mouse_bytes, mouse_bytes, bar);
+            bulk_load(st + IN_MOUSE, static_cast<const char *>(mouse) + tile * mouse_bytes, mouse_bytes, bar);
     };
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; s++)
+        for (int s = 0; s < kInStages; s++)
             mbar_init(bar0 + s * 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_smem_to_async_proxy();
+    }
+    __syncthreads();
+    if (warp == 3 && issuer) { /* the loading lane primes two stages; the third fills after tile 0 */
 #pragma unroll
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < 2; s++) {
             const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
             if (tile < tiles)
                 issue_loads(s, tile);
         }
     }
-    __syncthreads();
 
-    uint32_t s = 0, parity = 0;
+    uint32_t s = 0, parity = 0, so = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint32_t sb = smem0 + s * ST_BYTES;
+        const uint32_t sb = in0 + s * IN_BYTES, ob = out0 + so * OUT_BYTES;
         mbar_wait(bar0 + s * 8u, parity);
 
         Env e;
         {
-            const float4 a = lds_f4(sb + ST_STATE + kTileRecA + tid * 16u);
-            const double2 b = lds_d2(sb + ST_STATE + kTileRecB + tid * 16u);
+            const float4 a = lds_f4(sb + IN_STATE + kTileRecA + tid * 16u);
+            const double2 b = lds_d2(sb + IN_STATE + kTileRecB + tid * 16u);
             e.vx = a.x;
             e.vy = a.y;
             e.vz = a.z;
             e.bits = __float_as_uint(a.w);
             e.z = b.x;
             e.yaw = b.y;
-            e.trem = lds_d(sb + ST_STATE + kTileTrem + tid * 8u);
+            e.trem = lds_d(sb + IN_STATE + kTileTrem + tid * 8u);
         }
         uint32_t keybits;
         if (nk == 4) {
-            const uint32_t w = lds_u32(sb + ST_KEYS + tid * 4u);
+            const uint32_t w = lds_u32(sb + IN_KEYS + tid * 4u);
             keybits = (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
         } else {
-            const uint32_t ka = sb + ST_KEYS + tid * 3u;
+            const uint32_t ka = sb + IN_KEYS + tid * 3u;
             keybits = (lds_u8(ka) & 1u) | ((lds_u8(ka + 1) & 1u) << 1) | ((lds_u8(ka + 2) & 1u) << 2);
         }
         double m = 0.0;
         if (has_mouse) {
             if (COMMON || mouse_kind == Q1_MOUSE_F32)
-                m = (double)__uint_as_float(lds_u32(sb + ST_MOUSE + tid * 4u));
-            else if (mouse_kind == Q1_MOUSE_I32)
-                m = (double)(int32_t)lds_u32(sb + ST_MOUSE + tid * 4u);
+                m = (double)__uint_as_float(lds_u32(sb + IN_MOUSE + tid * 4u));
             else
-                m = lds_d(sb + ST_MOUSE + tid * 8u);
+                m = (double)(int32_t)lds_u32(sb + IN_MOUSE + tid * 4u);
         }
         float r;
         bool d;
@@ -378,9 +385,9 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             if (finished)
                 e.bits |= F_DONE_SEEN;
         }
-        sts_f(sb + ST_REWARD + tid * 4u, r);
-        sts_u8(sb + ST_DONE + tid, d ? 1u : 0u);
-        sts_u8(sb + ST_ZS + tid, zs ? 1u : 0u);
+        sts_f(ob + OUT_REWARD + tid * 4u, r);
+        sts_u8(ob + OUT_DONE + tid, d ? 1u : 0u);
+        sts_u8(ob + OUT_ZS + tid, zs ? 1u : 0u);
         if (d && auto_reset) {
             uint32_t ep = P.epoch[i] + 1u;
             P.epoch[i] = ep;
@@ -392,38 +399,50 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         }
         float o[6];
         observe<LEAN>(P, e, o);
-        sts_f2(sb + ST_OBS + tid * 24u, o[0], o[1]);
-        sts_f2(sb + ST_OBS + tid * 24u + 8u, o[2], o[3]);
-        sts_f2(sb + ST_OBS + tid * 24u + 16u, o[4], o[5]);
-        sts_f4(sb + ST_STATE + kTileRecA + tid * 16u, e.vx, e.vy, e.vz, __uint_as_float(e.bits));
-        sts_d2(sb + ST_STATE + kTileRecB + tid * 16u, e.z, e.yaw);
-        sts_d(sb + ST_STATE + kTileTrem + tid * 8u, e.trem);
+        sts_f2(ob + OUT_OBS + tid * 24u, o[0], o[1]);
+        sts_f2(ob + OUT_OBS + tid * 24u + 8u, o[2], o[3]);
+        sts_f2(ob + OUT_OBS + tid * 24u + 16u, o[4], o[5]);
+        sts_f4(sb + IN_STATE + kTileRecA + tid * 16u, e.vx, e.vy, e.vz, __uint_as_float(e.bits));
+        sts_d2(sb + IN_STATE + kTileRecB + tid * 16u, e.z, e.yaw);
+        sts_d(sb + IN_STATE + kTileTrem + tid * 8u, e.trem);
         fence_smem_to_async_proxy();
+        /* the stores this lane issued one tile ago have long finished reading shared memory; the
+         * wait makes that a guarantee before the barrier lets anyone reuse those buffers */
+        if (issuer)
+            bulk_wait_read_all();
         __syncthreads();
-        if (tid == 0) {
+        if (issuer) {
             int64_t t = tile;
             asm volatile("" : "+l"(t));
-            bulk_store(P.state + t * kTileBytes, sb + ST_STATE, kTileBytes);
-            bulk_store(obs + t * (6 * kTile), sb + ST_OBS, 24 * kTile);
-            bulk_store(reward + t * kTile, sb + ST_REWARD, 4 * kTile);
-            bulk_store(done + t * kTile, sb + ST_DONE, kTile);
-            if (zero_start)
-                bulk_store(zero_start + t * kTile, sb + ST_ZS, kTile);
-            bulk_commit();
-            const int64_t next = t + (int64_t)kStages * gridDim.x;
-            if (next < tiles) {
-                bulk_wait_read_all(); /* the stores have drained this stage: refill it */
-                issue_loads(s, next);
+            if (warp == 0) {
+                bulk_store(P.state + t * kTileBytes, sb + IN_STATE, kTileBytes);
+                bulk_commit();
+            } else if (warp == 1) {
+                bulk_store(obs + t * (6 * kTile), ob + OUT_OBS, 24 * kTile);
+                bulk_store(reward + t * kTile, ob + OUT_REWARD, 4 * kTile);
+                bulk_commit();
+            } else if (warp == 2) {
+                bulk_store(done + t * kTile, ob + OUT_DONE, kTile);
+                if (zero_start)
+                    bulk_store(zero_start + t * kTile, ob + OUT_ZS, kTile);
+                bulk_commit();
+            } else {
+                /* refill the stage of the previous tile: all warps left it a barrier ago and its
+                 * state store was drained before this barrier */
+                const int64_t next = t + 2 * (int64_t)gridDim.x;
+                if (next < tiles)
+                    issue_loads(s >= 1 ? s - 1 : kInStages - 1, next);
             }
         }
         if (TRACK)
             report_episodes(P, finished, zs, ret);
-        if (++s == kStages) {
+        if (++s == kInStages) {
             s = 0;
             parity ^= 1u;
         }
+        so ^= 1u;
     }
-    if (tid == 0)
+    if (issuer)
         bulk_wait_all();
 }
 
@@ -1187,7 +1206,8 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
     /* full tiles go through the TMA-pipelined kernel when every buffer it bulk-copies is 16-byte
      * aligned (tile strides are multiples of 16 by construction); the rest takes the plain kernel */
     int64_t tma_tiles = 0;
-    if (!env->stamps && aligned16(keys) && aligned16(obs) && aligned16(reward) && aligned16(done) &&
+    if (!env->stamps && mouse_kind != Q1_MOUSE_F64 && aligned16(keys) && aligned16(obs) &&
+        aligned16(reward) && aligned16(done) &&
         (!zero_start || aligned16(zero_start)) && (!env->P.allow_yaw || aligned16(mouse)))
         tma_tiles = n / kBlock;
     int rc = Q1_OK;
