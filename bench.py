@@ -52,6 +52,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_step_tma launch, from the committed
+    `ncu --set full` capture of this workload (profiles/r1_step_tma_ncu.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_step_tma_ncu.json")) as f:
+            d = json.load(f)
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------ CPU arm / baseline
 
 def cpu_port_throughput(num_envs, ticks, threads, seed=0):
@@ -262,15 +273,12 @@ def run_cuda_arm(args, rank, world, local_rank):
     d2h = n * (24 + 4 + 1 + 1)
 
     # ---- the metric reduction (the one collective of this path): zero_start_total_reward_mean
+    from q1physrl_b200 import sharding
     tracked = benv.VectorPhysEnv(workload_config(1 << 14), device=local_rank, seed=args.seed,
                                  env_index_base=rank << 14, track_returns=True)
     tracked.rollout("strafe_jump", 722, policy_seed=1)
-    m = tracked.metrics()
-    red = torch.tensor([m["zero_start_total_reward_sum"], float(m["zero_start_episodes"])],
-                       dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.SUM)
-    zs_mean = float(red[0].item() / max(1.0, red[1].item()))
+    red = sharding.reduce_metrics(tracked.metrics(), device=dev)
+    zs_mean, zs_episodes = red["zero_start_total_reward_mean"], red["zero_start_episodes"]
 
     if rank == 0:
         info = envs[0].info
@@ -287,22 +295,25 @@ def run_cuda_arm(args, rank, world, local_rank):
                        "l2_policy": f"inputs larger than L2: ring of {ring} env shards x "
                                     f"{(2 * state_b + nk + 34) * n / 1e6:.0f} MB touched per step",
                        "state_bytes_per_env": state_b, "key_timers": "f64" if info.f64_stamps else "u8",
-                       "launch": "stream (one q1_step call per step)"},
+                       "launch": "one q1_step call (k_step_tma launch, programmatic dependent launch) per "
+                                 "step on torch's current stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "VectorPhysEnv.vector_step((keys, mouse)) with page-locked NumPy arrays"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "k_step<false,false>",
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "kernel": "k_step_tma",
                          "bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src},
             "clocks": clocks.summary(),
-            "zero_start_total_reward_mean": {"value": zs_mean, "episodes": int(red[1].item()),
+            "zero_start_total_reward_mean": {"value": zs_mean, "episodes": zs_episodes,
                                              "policy": "scripted strafe_jump, 722 ticks, 16384 envs/GPU",
                                              "collective": "all_reduce(sum) of (sum, count)" if world > 1 else "none (1 GPU)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample_envs, sample_ticks = 1 << 17, 200
+            sample_envs = NUM_ENVS
+            v0, dt0 = cpu_port_throughput(sample_envs, 8, threads)           # calibrate: ~10 s of work
+            sample_ticks = int(min(4000, max(16, 10.0 * v0 / sample_envs)))
             v, dt = cpu_port_throughput(sample_envs, sample_ticks, threads)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -323,6 +323,10 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             bulk_load(st + IN_MOUSE, static_cast<const char *>(mouse) + tile * mouse_bytes, mouse_bytes, bar);
     };
 
+    /* Programmatic dependent launch: the next kernel in the stream may start placing its CTAs as
+     * ours retire and run its own prologue; every kernel of this library waits for the full
+     * completion (and memory visibility) of its predecessor before it touches global memory. */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kInStages; s++)
@@ -331,6 +335,7 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         fence_smem_to_async_proxy();
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp == 3 && issuer) { /* the loading lane primes two stages; the third fills after tile 0 */
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -792,6 +797,7 @@ struct q1_env {
     uint64_t ticks = 0;
     /* device scratch + stream of the *_host entry points */
     int sm_count = 148;
+    bool pdl = true; /* launch the step kernel with programmatic stream serialization */
     cudaStream_t host_stream = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -995,6 +1001,7 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     }
     env->stamps = (flags & Q1_F_FORCE_F64_STAMPS) || !counters_exact;
     env->track = flags & Q1_F_TRACK_RETURNS;
+    env->pdl = getenv("Q1PHYS_NO_PDL") == nullptr;
     /* the reciprocal sequences assume positive divisors in a sane exponent range */
     auto sane = [](double v) { return v > 1e-100 && v < 1e100; };
     env->P.ieee_div = (flags & Q1_F_IEEE_DIVISION) || !sane(cfg->time_limit) ||
@@ -1218,14 +1225,24 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
         rc = dispatch(env, [&](auto, auto tr, auto ln) {
             unsigned grid = (unsigned)std::min<int64_t>(tma_tiles,
                                                         (int64_t)env->sm_count * kStepCtasPerSm);
-            if (common)
-                k_step_tma<decltype(tr)::value, decltype(ln)::value, true><<<grid, kBlock, 0, s>>>(
-                    env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset,
-                    tma_tiles);
-            else
-                k_step_tma<decltype(tr)::value, decltype(ln)::value, false><<<grid, kBlock, 0, s>>>(
-                    env->P, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset,
-                    tma_tiles);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(kBlock);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = env->pdl ? 1 : 0;
+            cudaError_t err =
+                common ? cudaLaunchKernelEx(&cfg, k_step_tma<decltype(tr)::value, decltype(ln)::value, true>,
+                                            env->P, keys, mouse, mouse_kind, obs, reward, done,
+                                            zero_start, auto_reset, tma_tiles)
+                       : cudaLaunchKernelEx(&cfg, k_step_tma<decltype(tr)::value, decltype(ln)::value, false>,
+                                            env->P, keys, mouse, mouse_kind, obs, reward, done,
+                                            zero_start, auto_reset, tma_tiles);
+            if (err != cudaSuccess)
+                return fail(Q1_ECUDA, std::string("k_step_tma launch: ") + cudaGetErrorString(err));
             return check_launch("k_step_tma");
         });
     }

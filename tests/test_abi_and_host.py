@@ -1,0 +1,161 @@
+"""CPU: the C-ABI library loads and exports every symbol include/q1phys.h declares; host-side
+logic of the Python mirror (Config, action normalisation, spaces, sharding) without a GPU."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "q1phys.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(q1_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from q1physrl_b200 import _build, _lib
+    _build.build()
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in q1phys.h but not exported"
+    assert set(_lib.SIGNATURES) == set(declared), set(_lib.SIGNATURES) ^ set(declared)
+    assert lib.q1_abi_version() == _lib.Q1_ABI_VERSION
+
+
+def test_pod_layouts_match_header():
+    from q1physrl_b200 import _lib
+    assert ctypes.sizeof(_lib.Q1Config) == 8 * 11 + 4 * 8          # q1_config
+    assert ctypes.sizeof(_lib.Q1EnvInfo) == 8 + 6 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.Q1StateView) == 10 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.Q1Metrics) == 5 * 8
+
+
+def test_no_device_is_a_loud_error():
+    """No CPU fallback: without a CUDA device q1_create fails with Q1_ENODEV."""
+    from q1physrl_b200 import _lib, env as benv
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.Q1Error) as ei:
+        benv.VectorPhysEnv(dict(num_envs=2, zero_start_prob=1, initial_yaw_range=(0, 360),
+                                max_initial_speed=0))
+    assert ei.value.code == _lib.Q1_ENODEV and "no CPU implementation" in str(ei.value)
+    from q1physrl_b200 import phys
+    with pytest.raises(_lib.Q1Error):
+        phys.apply(phys.Inputs(*(np.zeros(1) for _ in range(5)), np.zeros(1, bool), np.full(1, 0.014)),
+                   phys.PlayerState(np.zeros(1), np.zeros((1, 3), np.float32), np.zeros(1, bool),
+                                    np.ones(1, bool)))
+
+
+def test_num_keys_and_null_arguments():
+    from q1physrl_b200 import _lib, env as benv
+    lib = _lib.load()
+    for auto, allow, want in ((False, True, 4), (True, True, 3), (False, False, 3), (True, False, 3)):
+        cfg = benv._pod_config(benv.Config(num_envs=1, zero_start_prob=1, initial_yaw_range=(0, 1),
+                                           max_initial_speed=0, auto_jump=auto, allow_jump=allow), 1)
+        assert lib.q1_num_keys(ctypes.byref(cfg)) == want
+    assert lib.q1_num_keys(None) == _lib.Q1_EINVAL
+    assert b"NULL" in lib.q1_last_error()
+    assert lib.q1_create(None, 0, 0, 0, 0, None) == _lib.Q1_EINVAL
+    assert lib.q1_destroy(None) == 0
+
+
+def test_config_matches_reference_dataclass():
+    from q1physrl_b200 import env as benv
+    c = benv.Config.get_default()
+    assert c.num_envs is None and c.time_delta == 1. / 72 and c.smove_max == 1060 and c.smooth_keys
+    assert c.conforms_to_rules() and not dataclasses.replace(c, hover=True).conforms_to_rules()
+    assert isinstance(c.action_range, np.float32) and c.action_range == np.float32(720) * np.float32(0.014)
+    with pytest.raises(dataclasses.FrozenInstanceError):
+        c.num_envs = 3
+    d = dataclasses.asdict(c)
+    assert benv.Config(**d) == c                                  # dict round trip (train.py:141)
+    assert [f.name for f in dataclasses.fields(c)][:4] == ["num_envs", "zero_start_prob",
+                                                           "initial_yaw_range", "max_initial_speed"]
+    assert benv.get_obs_scale(c) == [10., 90., 100, 200, 200, 200]
+    assert benv.INITIAL_YAW_ZERO == np.float32(90) and len(benv.Key) == 4 and len(benv.Obs) == 6
+    try:
+        from oracle import refshim
+    except Exception:
+        return
+    if refshim.available():
+        ref_env, _ = refshim.load()
+        rf = {f.name: f.default for f in dataclasses.fields(ref_env.Config)}
+        mf = {f.name: f.default for f in dataclasses.fields(benv.Config)}
+        assert list(rf) == list(mf)
+        for k in rf:
+            assert rf[k] is dataclasses.MISSING and mf[k] is dataclasses.MISSING or rf[k] == mf[k], k
+        assert dataclasses.asdict(ref_env.Config.get_default()) == d
+        assert [k.name for k in ref_env.Key] == [k.name for k in benv.Key]
+        assert [k.name for k in ref_env.Obs] == [k.name for k in benv.Obs]
+
+
+def test_phys_env_rejects_num_envs_before_touching_the_gpu():
+    from q1physrl_b200 import env as benv
+    with pytest.raises(AssertionError):
+        benv.PhysEnv(dataclasses.replace(benv.Config.get_default(), num_envs=3))
+
+
+def test_action_normalisation():
+    """env.py:221-223, 228: RLLib tuples (scalars and 1-element arrays), arrays, float keys."""
+    from q1physrl_b200 import env as benv
+    cfg = benv.Config.get_default()
+    rllib = [(0, 1, 1, 0, np.array([2.5], np.float32)), (1, 0, 0, 1, np.array([-1.25], np.float32))]
+    keys, mouse = benv._split_actions(cfg, 4, rllib)
+    assert keys.dtype == np.uint8 and keys.tolist() == [[0, 1, 1, 0], [1, 0, 0, 1]]
+    assert mouse.dtype == np.float64 and mouse.tolist() == [2.5, -1.25]
+    scalars = [(0, 1, 1, 0, 2.5), (1, 0, 0, 1, -1.25)]            # compute_action() format
+    k2, m2 = benv._split_actions(cfg, 4, scalars)
+    assert np.array_equal(k2, keys) and np.array_equal(m2, mouse)
+    arr = np.array([[0.9, 1.0, 2.0, 3.7, 0.5]])                   # astype(int) truncates, & keeps bit 0
+    k3, m3 = benv._split_actions(cfg, 4, arr)
+    assert k3.tolist() == [[0, 1, 0, 1]] and m3.tolist() == [0.5]
+    noyaw = dataclasses.replace(cfg, allow_yaw=False, auto_jump=True)
+    k4, m4 = benv._split_actions(noyaw, 3, [(1, 0, 1)])
+    assert k4.tolist() == [[1, 0, 1]] and m4 is None
+
+
+def test_action_and_observation_spaces():
+    from q1physrl_b200 import env as benv
+    cfg = benv.Config.get_default()
+    sp = benv._action_space(cfg, 4)
+    assert len(sp.spaces) == 5 and all(s.n == 2 for s in sp.spaces[:4])
+    assert sp.spaces[4].shape == (1,) and sp.spaces[4].dtype == np.float32
+    a = sp.sample()
+    assert len(a) == 5 and -10.08 <= float(a[4][0]) <= 10.08
+    disc = benv._action_space(dataclasses.replace(cfg, discrete_yaw_steps=5, auto_jump=True), 3)
+    assert len(disc.spaces) == 4 and disc.spaces[3].n == 11
+    assert len(benv._action_space(dataclasses.replace(cfg, allow_yaw=False), 4).spaces) == 4
+
+
+def test_standalone_decoder_reset_semantics():
+    """ActionDecoder.vector_reset / reset_at are host-side bookkeeping (env.py:271-291)."""
+    from q1physrl_b200 import env as benv
+    cfg = dataclasses.replace(benv.Config.get_default(), num_envs=3)
+    dec = benv.ActionDecoder(cfg)
+    dec.vector_reset(np.array([10., 20., 30.]))
+    assert dec._last_key_press_time.shape == (3, 4) and np.all(dec._last_key_press_time == -0.3)
+    assert dec._last_keys.dtype == np.bool_ and not dec._last_keys.any()
+    dec._last_keys[1] = True
+    dec._last_key_press_time[1] = 1.0
+    dec.reset_at(1, 99.0)
+    assert not dec._last_keys[1].any() and np.all(dec._last_key_press_time[1] == -0.3)
+    assert dec._yaw.tolist() == [10., 99., 30.]
+
+
+def test_shard_ranges_partition_the_population():
+    from q1physrl_b200 import sharding
+    for n, w in ((1 << 20, 8), (1000, 3), (7, 8), (262144, 4)):
+        spans = [sharding.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+            assert s0 + c0 == s1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 3, 3)
