@@ -298,8 +298,9 @@ __global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
 k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
            const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
            float *__restrict__ reward, uint8_t *__restrict__ done,
-           uint8_t *__restrict__ zero_start, int auto_reset, int64_t tiles)
+           uint8_t *__restrict__ zero_start, int auto_reset, int64_t tile_begin, int64_t tiles)
 {
+    /* tiles [tile_begin, tiles) of the handle; the global buffers are indexed by absolute env */
     __shared__ __align__(128) unsigned char in_mem[kInStages * IN_BYTES];
     __shared__ __align__(128) unsigned char out_mem[kOutStages * OUT_BYTES];
     __shared__ __align__(8) uint64_t full_bar[kInStages];
@@ -339,14 +340,14 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     if (warp == 3 && issuer) { /* the loading lane primes two stages; the third fills after tile 0 */
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            const int64_t tile = tile_begin + blockIdx.x + (int64_t)s * gridDim.x;
             if (tile < tiles)
                 issue_loads(s, tile);
         }
     }
 
     uint32_t s = 0, parity = 0, so = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int64_t tile = tile_begin + blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint32_t sb = in0 + s * IN_BYTES, ob = out0 + so * OUT_BYTES;
         mbar_wait(bar0 + s * 8u, parity);
 
@@ -452,16 +453,16 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
 }
 
 /* The same tick, one env per thread with plain loads and stores: f64-stamp mode, ragged tails
- * (n not a multiple of kTile) and buffers that are not 16-byte aligned.  Covers envs [first, n). */
+ * (n not a multiple of kTile) and buffers that are not 16-byte aligned.  Covers envs [first, end). */
 template <bool STAMPS, bool TRACK, bool LEAN>
 __global__ void __launch_bounds__(kBlock)
 k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
        const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
        float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ zero_start,
-       int auto_reset, int64_t first)
+       int auto_reset, int64_t first, int64_t end)
 {
     const int64_t i = first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const bool active = i < P.n;
+    const bool active = i < end;
     bool finished = false, zs = false;
     double ret = 0.0;
     if (active) {
@@ -798,7 +799,10 @@ struct q1_env {
     /* device scratch + stream of the *_host entry points */
     int sm_count = 148;
     bool pdl = true; /* launch the step kernel with programmatic stream serialization */
+    int host_chunks = 2; /* pipeline depth of q1_step_host for large page-locked batches */
     cudaStream_t host_stream = nullptr;
+    cudaStream_t in_stream = nullptr, out_stream = nullptr; /* the chunked pipeline of q1_step_host */
+    cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
 };
@@ -1002,6 +1006,8 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     env->stamps = (flags & Q1_F_FORCE_F64_STAMPS) || !counters_exact;
     env->track = flags & Q1_F_TRACK_RETURNS;
     env->pdl = getenv("Q1PHYS_NO_PDL") == nullptr;
+    if (const char *hc = getenv("Q1PHYS_HOST_CHUNKS"))
+        env->host_chunks = std::max(1, std::min(8, atoi(hc)));
     /* the reciprocal sequences assume positive divisors in a sane exponent range */
     auto sane = [](double v) { return v > 1e-100 && v < 1e100; };
     env->P.ieee_div = (flags & Q1_F_IEEE_DIVISION) || !sane(cfg->time_limit) ||
@@ -1075,6 +1081,14 @@ int q1_destroy(q1_env *env)
         cudaFree(env->scratch);
     if (env->host_stream)
         cudaStreamDestroy(env->host_stream);
+    if (env->in_stream) {
+        cudaStreamDestroy(env->in_stream);
+        cudaStreamDestroy(env->out_stream);
+        for (int c = 0; c < 8; c++) {
+            cudaEventDestroy(env->ev_in[c]);
+            cudaEventDestroy(env->ev_done[c]);
+        }
+    }
     if (env->pool)
         cudaFree(env->pool);
     delete env;
@@ -1197,33 +1211,28 @@ int q1_reset_at_host(q1_env *env, int64_t index, float *obs6_host)
     return Q1_OK;
 }
 
-int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
-            float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream)
+/* One tick for envs [begin, end) of the handle (begin a multiple of kTile); the buffers are the
+ * full-size arrays, indexed by absolute env. */
+static int step_range(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
+                      float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset,
+                      int64_t begin, int64_t end, cudaStream_t s)
 {
-    if (mouse_kind != Q1_MOUSE_F32 && mouse_kind != Q1_MOUSE_I32 && mouse_kind != Q1_MOUSE_F64)
-        return fail(Q1_EINVAL, "unknown mouse_kind");
-    if (!env || !keys || !obs || !reward || !done)
-        return fail(Q1_EINVAL, "env / keys / obs / reward / done is NULL");
-    if (env->P.allow_yaw && !mouse)
-        return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
-    DeviceGuard guard(env->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int64_t n = env->P.n;
     auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     /* full tiles go through the TMA-pipelined kernel when every buffer it bulk-copies is 16-byte
      * aligned (tile strides are multiples of 16 by construction); the rest takes the plain kernel */
-    int64_t tma_tiles = 0;
+    const int64_t tile_begin = begin / kBlock;
+    int64_t tile_end = tile_begin;
     if (!env->stamps && mouse_kind != Q1_MOUSE_F64 && aligned16(keys) && aligned16(obs) &&
         aligned16(reward) && aligned16(done) &&
         (!zero_start || aligned16(zero_start)) && (!env->P.allow_yaw || aligned16(mouse)))
-        tma_tiles = n / kBlock;
+        tile_end = end / kBlock;
     int rc = Q1_OK;
-    if (tma_tiles > 0) {
+    if (tile_end > tile_begin) {
         /* the compiled-in configuration: continuous f32 mouse action, no hover, y-velocity reward */
         const bool common = env->P.allow_yaw && !env->P.discrete_yaw && !env->P.hover &&
                             !env->P.speed_reward && mouse_kind == Q1_MOUSE_F32;
         rc = dispatch(env, [&](auto, auto tr, auto ln) {
-            unsigned grid = (unsigned)std::min<int64_t>(tma_tiles,
+            unsigned grid = (unsigned)std::min<int64_t>(tile_end - tile_begin,
                                                         (int64_t)env->sm_count * kStepCtasPerSm);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
@@ -1237,23 +1246,39 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
             cudaError_t err =
                 common ? cudaLaunchKernelEx(&cfg, k_step_tma<decltype(tr)::value, decltype(ln)::value, true>,
                                             env->P, keys, mouse, mouse_kind, obs, reward, done,
-                                            zero_start, auto_reset, tma_tiles)
+                                            zero_start, auto_reset, tile_begin, tile_end)
                        : cudaLaunchKernelEx(&cfg, k_step_tma<decltype(tr)::value, decltype(ln)::value, false>,
                                             env->P, keys, mouse, mouse_kind, obs, reward, done,
-                                            zero_start, auto_reset, tma_tiles);
+                                            zero_start, auto_reset, tile_begin, tile_end);
             if (err != cudaSuccess)
                 return fail(Q1_ECUDA, std::string("k_step_tma launch: ") + cudaGetErrorString(err));
             return check_launch("k_step_tma");
         });
     }
-    const int64_t first = tma_tiles * kBlock;
-    if (rc == Q1_OK && first < n)
+    const int64_t first = tile_end > tile_begin ? tile_end * kBlock : begin;
+    if (rc == Q1_OK && first < end)
         rc = dispatch(env, [&](auto st, auto tr, auto ln) {
             k_step<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
-                <<<grid_for(n - first), kBlock, 0, s>>>(env->P, keys, mouse, mouse_kind, obs,
-                                                       reward, done, zero_start, auto_reset, first);
+                <<<grid_for(end - first), kBlock, 0, s>>>(env->P, keys, mouse, mouse_kind, obs,
+                                                         reward, done, zero_start, auto_reset, first,
+                                                         end);
             return check_launch("k_step");
         });
+    return rc;
+}
+
+int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
+            float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream)
+{
+    if (mouse_kind != Q1_MOUSE_F32 && mouse_kind != Q1_MOUSE_I32 && mouse_kind != Q1_MOUSE_F64)
+        return fail(Q1_EINVAL, "unknown mouse_kind");
+    if (!env || !keys || !obs || !reward || !done)
+        return fail(Q1_EINVAL, "env / keys / obs / reward / done is NULL");
+    if (env->P.allow_yaw && !mouse)
+        return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
+    DeviceGuard guard(env->device);
+    int rc = step_range(env, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset, 0,
+                        env->P.n, static_cast<cudaStream_t>(stream));
     if (rc == Q1_OK)
         env->ticks += 1;
     return rc;
@@ -1278,6 +1303,17 @@ int q1_host_free(void *ptr)
     return Q1_OK;
 }
 
+/* Is `p` page-locked (cudaHostAlloc / cudaHostRegister) memory, i.e. can a copy be truly async? */
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
                  float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset)
 {
@@ -1297,22 +1333,77 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
     if (rc != Q1_OK)
         return rc;
     char *d = static_cast<char *>(env->scratch);
+    uint8_t *d_keys = reinterpret_cast<uint8_t *>(d + o_keys);
+    char *d_mouse = d + o_mouse;
+    float *d_obs = reinterpret_cast<float *>(d + o_obs), *d_rew = reinterpret_cast<float *>(d + o_rew);
+    uint8_t *d_done = reinterpret_cast<uint8_t *>(d + o_done);
+    uint8_t *d_zs = zero_start ? reinterpret_cast<uint8_t *>(d + o_zs) : nullptr;
     cudaStream_t s = env->host_stream;
-    Q1_CUDA(cudaMemcpyAsync(d + o_keys, keys, n * nk, cudaMemcpyHostToDevice, s));
-    if (env->P.allow_yaw)
-        Q1_CUDA(cudaMemcpyAsync(d + o_mouse, mouse, mouse_size * n, cudaMemcpyHostToDevice, s));
-    rc = q1_step(env, reinterpret_cast<uint8_t *>(d + o_keys), d + o_mouse, mouse_kind,
-                 reinterpret_cast<float *>(d + o_obs), reinterpret_cast<float *>(d + o_rew),
-                 reinterpret_cast<uint8_t *>(d + o_done),
-                 zero_start ? reinterpret_cast<uint8_t *>(d + o_zs) : nullptr, auto_reset, s);
-    if (rc != Q1_OK)
-        return rc;
-    Q1_CUDA(cudaMemcpyAsync(obs, d + o_obs, 24 * n, cudaMemcpyDeviceToHost, s));
-    Q1_CUDA(cudaMemcpyAsync(reward, d + o_rew, 4 * n, cudaMemcpyDeviceToHost, s));
-    Q1_CUDA(cudaMemcpyAsync(done, d + o_done, n, cudaMemcpyDeviceToHost, s));
-    if (zero_start)
-        Q1_CUDA(cudaMemcpyAsync(zero_start, d + o_zs, n, cudaMemcpyDeviceToHost, s));
+
+    /* Large batches in page-locked memory run as a pipeline over env chunks: the action upload of
+     * chunk c+1, the tick of chunk c and the result download of chunk c-1 overlap (the two PCIe
+     * directions are independent copy engines), so a step costs about max(H2D, D2H), not the sum. */
+    constexpr int kMaxChunks = 8;
+    int chunks = 1;
+    if (n >= (size_t)1 << 16 && is_pinned(keys) && is_pinned(obs) && is_pinned(reward) &&
+        is_pinned(done) && (!env->P.allow_yaw || is_pinned(mouse)) && (!zero_start || is_pinned(zero_start)))
+        chunks = env->host_chunks;
+    if (chunks <= 1) {
+        Q1_CUDA(cudaMemcpyAsync(d_keys, keys, n * nk, cudaMemcpyHostToDevice, s));
+        if (env->P.allow_yaw)
+            Q1_CUDA(cudaMemcpyAsync(d_mouse, mouse, mouse_size * n, cudaMemcpyHostToDevice, s));
+        rc = step_range(env, d_keys, d_mouse, mouse_kind, d_obs, d_rew, d_done, d_zs, auto_reset, 0,
+                        (int64_t)n, s);
+        if (rc != Q1_OK)
+            return rc;
+        Q1_CUDA(cudaMemcpyAsync(obs, d_obs, 24 * n, cudaMemcpyDeviceToHost, s));
+        Q1_CUDA(cudaMemcpyAsync(reward, d_rew, 4 * n, cudaMemcpyDeviceToHost, s));
+        Q1_CUDA(cudaMemcpyAsync(done, d_done, n, cudaMemcpyDeviceToHost, s));
+        if (zero_start)
+            Q1_CUDA(cudaMemcpyAsync(zero_start, d_zs, n, cudaMemcpyDeviceToHost, s));
+        Q1_CUDA(cudaStreamSynchronize(s));
+        env->ticks += 1;
+        return Q1_OK;
+    }
+    if (!env->in_stream) {
+        Q1_CUDA(cudaStreamCreateWithFlags(&env->in_stream, cudaStreamNonBlocking));
+        Q1_CUDA(cudaStreamCreateWithFlags(&env->out_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < kMaxChunks; c++) {
+            Q1_CUDA(cudaEventCreateWithFlags(&env->ev_in[c], cudaEventDisableTiming));
+            Q1_CUDA(cudaEventCreateWithFlags(&env->ev_done[c], cudaEventDisableTiming));
+        }
+    }
+    /* chunk boundaries on 2 * kTile envs so that every sub-array offset stays 16-byte aligned */
+    const size_t grain = 2 * kTile;
+    const size_t per = ((n / chunks) / grain) * grain;
+    auto chunk_begin = [&](int c) { return c == 0 ? (size_t)0 : (c >= chunks ? n : per * c); };
+    for (int c = 0; c < chunks; c++) {
+        const size_t b = chunk_begin(c), e = chunk_begin(c + 1);
+        Q1_CUDA(cudaMemcpyAsync(d_keys + b * nk, keys + b * nk, (e - b) * nk, cudaMemcpyHostToDevice,
+                                env->in_stream));
+        if (env->P.allow_yaw)
+            Q1_CUDA(cudaMemcpyAsync(d_mouse + b * mouse_size, static_cast<const char *>(mouse) + b * mouse_size,
+                                    (e - b) * mouse_size, cudaMemcpyHostToDevice, env->in_stream));
+        Q1_CUDA(cudaEventRecord(env->ev_in[c], env->in_stream));
+    }
+    for (int c = 0; c < chunks; c++) {
+        const size_t b = chunk_begin(c), e = chunk_begin(c + 1);
+        Q1_CUDA(cudaStreamWaitEvent(s, env->ev_in[c], 0));
+        rc = step_range(env, d_keys, d_mouse, mouse_kind, d_obs, d_rew, d_done, d_zs, auto_reset,
+                        (int64_t)b, (int64_t)e, s);
+        if (rc != Q1_OK)
+            return rc;
+        Q1_CUDA(cudaEventRecord(env->ev_done[c], s));
+        Q1_CUDA(cudaStreamWaitEvent(env->out_stream, env->ev_done[c], 0));
+        Q1_CUDA(cudaMemcpyAsync(obs + 6 * b, d_obs + 6 * b, 24 * (e - b), cudaMemcpyDeviceToHost, env->out_stream));
+        Q1_CUDA(cudaMemcpyAsync(reward + b, d_rew + b, 4 * (e - b), cudaMemcpyDeviceToHost, env->out_stream));
+        Q1_CUDA(cudaMemcpyAsync(done + b, d_done + b, e - b, cudaMemcpyDeviceToHost, env->out_stream));
+        if (zero_start)
+            Q1_CUDA(cudaMemcpyAsync(zero_start + b, d_zs + b, e - b, cudaMemcpyDeviceToHost, env->out_stream));
+    }
+    Q1_CUDA(cudaStreamSynchronize(env->out_stream));
     Q1_CUDA(cudaStreamSynchronize(s));
+    env->ticks += 1;
     return Q1_OK;
 }
 

@@ -354,3 +354,29 @@ def test_full_size_properties():
     sa, sb = a.get_state(), b.get_state()
     for f in harness.STATE_FIELDS:
         assert np.array_equal(sa[f], sb[f]), f
+
+
+def test_host_pipeline_matches_single_shot():
+    """q1_step_host runs large page-locked batches as a chunked upload / tick / download pipeline;
+    results must equal the single-shot path (pageable arrays), ragged tail included."""
+    from q1physrl_b200 import env as benv
+    n = 65536 * 3 + 300
+    cfg = dict(harness.PARAMS_100M, num_envs=n, time_limit=1.0, zero_start_prob=0.5)
+    a = benv.VectorPhysEnv(cfg, seed=5, reuse_output_buffers=True)
+    b = benv.VectorPhysEnv(cfg, seed=5, reuse_output_buffers=False)
+    pk = a._pinned.empty((n, 4), np.uint8)
+    pm = a._pinned.empty((n,), np.float32)
+    rng = np.random.default_rng(3)
+    for t in range(80):
+        keys, mouse = harness.random_actions(cfg, rng, n, 4)
+        pk[...] = keys
+        pm[...] = mouse
+        oa = a.vector_step((pk, pm), auto_reset=True)
+        ob = b.vector_step((keys, mouse), auto_reset=True)
+        for x, y in zip(oa[:3], ob[:3]):
+            assert np.array_equal(x, y), t
+        assert np.array_equal(np.asarray(oa[3]._zero_start), np.asarray(ob[3]._zero_start))
+    sa, sb = a.get_state(), b.get_state()
+    for f in harness.STATE_FIELDS:
+        assert np.array_equal(sa[f], sb[f]), f
+    assert a.info.ticks == b.info.ticks == 80
