@@ -186,11 +186,14 @@ int q1_set_state_host(q1_env *env, const q1_state_view *view);
 int q1_get_metrics_host(q1_env *env, int clear, q1_metrics *out);
 
 /* phys.apply (phys:184-197) on explicit arrays: a pure function, no handle.  All (n,) except
- * vel (n,3); pitch / roll may be NULL (= 0).  Output arrays must not alias the inputs. */
+ * vel (n,3); pitch / roll may be NULL (= 0).  Output arrays must not alias the inputs.
+ * time_delta_f32 != 0: the caller's time_delta array was float32 (values passed widened); NumPy
+ * then keeps friction, gravity and dt * z_vel in f32 (q1physrl/analyse.py:110 does this), and
+ * the library reproduces those widths. */
 int q1_phys_apply(int device, int64_t n,
                   const double *yaw, const double *pitch, const double *roll,
                   const double *fmove, const double *smove, const uint8_t *button2,
-                  const double *time_delta,
+                  const double *time_delta, int time_delta_f32,
                   const double *z_pos, const float *vel, const uint8_t *on_ground,
                   const uint8_t *jump_released,
                   double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
@@ -199,11 +202,21 @@ int q1_phys_apply(int device, int64_t n,
 int q1_phys_apply_host(int device, int64_t n,
                        const double *yaw, const double *pitch, const double *roll,
                        const double *fmove, const double *smove, const uint8_t *button2,
-                       const double *time_delta,
+                       const double *time_delta, int time_delta_f32,
                        const double *z_pos, const float *vel, const uint8_t *on_ground,
                        const uint8_t *jump_released,
                        double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
                        uint8_t *jump_released_out);
+
+/* EvalSimResult.hypothetical_delta_speeds (q1physrl/analyse.py:92-118) in one launch instead of
+ * num_angles phys.apply calls: delta_speed[a * n + t] = |v'_xy| - |v_xy| (f32) of one phys.apply
+ * tick on row t with yaw = base_yaw[t] + rel_angles[a] and constant fmove / smove / time_delta.
+ * HOST arrays; state arrays as for q1_phys_apply. */
+int q1_delta_speed_sweep_host(int device, int64_t n, int64_t num_angles, const double *base_yaw,
+                              const double *rel_angles, double fmove, double smove,
+                              const uint8_t *button2, double time_delta, int time_delta_f32,
+                              const double *z_pos, const float *vel, const uint8_t *on_ground,
+                              const uint8_t *jump_released, float *delta_speed);
 
 /* env.ActionDecoder.map (env:225-269) on explicit decoder state, HOST arrays: last_keys
  * (n,num_keys) u8, last_press (n,num_keys) f64 and yaw (n,) f64 are updated in place; mouse is f64

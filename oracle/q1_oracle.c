@@ -46,9 +46,12 @@ typedef struct {
 
 /* phys.apply for one row.  (fwd_x, fwd_y, right_x, right_y) is the 2x2 block _angle_vectors
  * returns (phys:56-66). */
+/* dt32: the reference's time_delta array was float32 (analyse.py:110); NumPy then keeps friction
+ * (phys:87-90), gravity (phys:122) and dt * z_vel (phys:127) in f32 and forms 10 * dt in f32. */
 static void move_body(body_t *b, double fwd_x, double right_x, double fwd_y, double right_y,
-                      double fmove, double smove, int jump, double dt)
+                      double fmove, double smove, int jump, double dt, int dt32)
 {
+    const float dtf = (float)dt;
     const int was_on_ground = b->on_ground; /* phys:191 passes the OLD flag */
 
     /* phys:95-101: einsum('ijk,ik->ij') is mul, mul, add per component; norm is sqrt(x*x+y*y). */
@@ -70,13 +73,24 @@ static void move_body(body_t *b, double fwd_x, double right_x, double fwd_y, dou
     if (was_on_ground) {
         float speed = sqrtf(b->vx * b->vx + b->vy * b->vy);            /* f32 norm, phys:85 */
         float control = speed > Q_STOP_SPEED ? speed : Q_STOP_SPEED;   /* phys:86 */
-        double new_speed = (double)speed - dt * (double)control * (double)Q_FRICTION; /* phys:87 */
-        if (!(new_speed > 0))
-            new_speed = 0;                                             /* phys:88 */
-        if (speed > 0) {
-            double ratio = new_speed / (double)speed;                  /* phys:90 */
-            hx = (double)b->vx * ratio;
-            hy = (double)b->vy * ratio;
+        if (dt32) {
+            float ns = speed - dtf * control * Q_FRICTION;             /* all f32 */
+            if (!(ns > 0))
+                ns = 0;
+            if (speed > 0) {
+                float ratio = ns / speed;
+                hx = (double)(b->vx * ratio);
+                hy = (double)(b->vy * ratio);
+            }
+        } else {
+            double new_speed = (double)speed - dt * (double)control * (double)Q_FRICTION; /* phys:87 */
+            if (!(new_speed > 0))
+                new_speed = 0;                                         /* phys:88 */
+            if (speed > 0) {
+                double ratio = new_speed / (double)speed;              /* phys:90 */
+                hx = (double)b->vx * ratio;
+                hy = (double)b->vy * ratio;
+            }
         }
     }
 
@@ -86,7 +100,7 @@ static void move_body(body_t *b, double fwd_x, double right_x, double fwd_y, dou
     double add = clipped - current;
     if (!(add > 0))
         add = 0;
-    double accel = (double)Q_ACCELERATE * dt * wish_speed;
+    double accel = (dt32 ? (double)(Q_ACCELERATE * dtf) : (double)Q_ACCELERATE * dt) * wish_speed;
     if (add < accel)
         accel = add;
     hx = hx + accel * wdx;
@@ -100,8 +114,14 @@ static void move_body(body_t *b, double fwd_x, double right_x, double fwd_y, dou
     b->jump_released = b->jump_released | !jump;
     int do_jump = was_on_ground && jump && b->jump_released;
     float vz = b->vz + (do_jump ? Q_JUMP_SPEED : 0.0f);                /* phys:119, f32 */
-    vz = (float)((double)vz - (double)Q_GRAVITY * dt);                 /* phys:122, f64 then store */
-    double z = b->z + dt * (double)vz;                                 /* phys:127 */
+    double z;
+    if (dt32) {
+        vz = vz - Q_GRAVITY * dtf;                                     /* f32 -= f32 */
+        z = b->z + (double)(dtf * vz);
+    } else {
+        vz = (float)((double)vz - (double)Q_GRAVITY * dt);             /* phys:122, f64 then store */
+        z = b->z + dt * (double)vz;                                    /* phys:127 */
+    }
     int og = z < (double)Q_FLOOR_HEIGHT;                               /* phys:128 */
     b->z = og ? (double)Q_FLOOR_HEIGHT : z;                            /* phys:129 */
     b->vz = og ? 0.0f : vz;                                            /* phys:130 */
@@ -111,7 +131,7 @@ static void move_body(body_t *b, double fwd_x, double right_x, double fwd_y, dou
 void q1o_phys_apply(int64_t n,
                     const double *yaw, const double *pitch, const double *roll,
                     const double *fmove, const double *smove, const uint8_t *button2,
-                    const double *time_delta,
+                    const double *time_delta, int dt_f32,
                     const double *z_in, const float *vel_in,
                     const uint8_t *og_in, const uint8_t *jr_in,
                     double *z_out, float *vel_out, uint8_t *og_out, uint8_t *jr_out)
@@ -132,7 +152,7 @@ void q1o_phys_apply(int64_t n,
         body_t b = { z_in[i], vel_in[3 * i], vel_in[3 * i + 1], vel_in[3 * i + 2],
                      og_in[i] != 0, jr_in[i] != 0 };
         move_body(&b, fwd_x, right_x, fwd_y, right_y, fmove[i], smove[i], button2[i] != 0,
-                  time_delta[i]);
+                  time_delta[i], dt_f32);
         z_out[i] = b.z;
         vel_out[3 * i] = b.vx;
         vel_out[3 * i + 1] = b.vy;
@@ -256,7 +276,7 @@ void q1o_step(const q1o_config *cfg, int64_t n, q1o_state *st,
         body_t b = { st->z_pos[i], st->vel[3 * i], st->vel[3 * i + 1], st->vel[3 * i + 2],
                      st->on_ground[i] != 0, st->jump_released[i] != 0 };
         move_body(&b, cy, sy, sy, -cy, (double)cmd.fmove, (double)cmd.smove, cmd.jump,
-                  cfg->time_delta);
+                  cfg->time_delta, 0);
         st->z_pos[i] = b.z;
         st->vel[3 * i] = b.vx;
         st->vel[3 * i + 1] = b.vy;

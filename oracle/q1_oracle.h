@@ -73,11 +73,12 @@ void q1o_decode(const q1o_config *cfg, int64_t n,
                 const float *z_vel, const double *time_remaining,
                 double *yaw_out, int64_t *smove, int64_t *fmove, uint8_t *jump);
 
-/* phys.apply (phys:184-197) with arbitrary per-row inputs. */
+/* phys.apply (phys:184-197) with arbitrary per-row inputs.  dt_f32: the time_delta array was
+ * float32 (the f32 widths NumPy then uses for friction / gravity, see q1_oracle.c). */
 void q1o_phys_apply(int64_t n,
                     const double *yaw, const double *pitch, const double *roll,
                     const double *fmove, const double *smove, const uint8_t *button2,
-                    const double *time_delta,
+                    const double *time_delta, int dt_f32,
                     const double *z_in, const float *vel_in,
                     const uint8_t *og_in, const uint8_t *jr_in,
                     double *z_out, float *vel_out, uint8_t *og_out, uint8_t *jr_out);

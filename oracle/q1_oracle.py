@@ -214,8 +214,10 @@ def decode(cfg, last_keys, last_press, yaw, keys, mouse, z_vel, time_remaining):
 
 def phys_apply(yaw, pitch, roll, fmove, smove, button2, time_delta, z_pos, vel, on_ground,
                jump_released):
-    """`phys.apply` on explicit arrays; returns (z_pos, vel, on_ground, jump_released)."""
+    """`phys.apply` on explicit arrays; returns (z_pos, vel, on_ground, jump_released).  A float32
+    `time_delta` array selects the f32 widths NumPy uses in that case."""
     n = int(np.asarray(yaw).shape[0])
+    dt_f32 = int(np.asarray(time_delta).dtype == np.float32)
     f64 = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (n,)))
     u8 = lambda a: np.ascontiguousarray(np.asarray(a).astype(bool), np.uint8)
     yaw, pitch, roll, fmove, smove, dt, z = map(f64, (yaw, pitch, roll, fmove, smove,
@@ -227,7 +229,8 @@ def phys_apply(yaw, pitch, roll, fmove, smove, button2, time_delta, z_pos, vel, 
     og_out = np.empty(n, np.uint8)
     jr_out = np.empty(n, np.uint8)
     lib().q1o_phys_apply(ctypes.c_int64(n), _ptr(yaw), _ptr(pitch), _ptr(roll), _ptr(fmove),
-                         _ptr(smove), _ptr(b2), _ptr(dt), _ptr(z), _ptr(vel), _ptr(og), _ptr(jr),
+                         _ptr(smove), _ptr(b2), _ptr(dt), ctypes.c_int(dt_f32), _ptr(z), _ptr(vel),
+                         _ptr(og), _ptr(jr),
                          _ptr(z_out), _ptr(vel_out), _ptr(og_out), _ptr(jr_out))
     return z_out, vel_out, og_out.astype(bool), jr_out.astype(bool)
 

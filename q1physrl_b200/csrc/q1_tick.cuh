@@ -308,7 +308,11 @@ __device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6
 /* ------------------------------------------------------------------ phys.apply, one row ------ */
 
 /* phys:184-197 for one env.  (fx, rx, fy, ry) is the 2x2 block of _angle_vectors (phys:56-66). */
-template <bool LEAN>
+/* DT32: `time_delta` arrived as a float32 array (analyse.py:110 builds it with np.full_like of an
+ * f32 array).  NumPy then keeps friction, gravity and dt * z_vel in f32 (phys:87-90, 122, 127)
+ * and forms 10 * dt in f32 (phys:78); with the f64 array env.vector_step passes (env:493) they
+ * are f64.  Both width sets are reproduced. */
+template <bool LEAN, bool DT32 = false>
 __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, double &z,
                                           bool &on_ground, bool &jump_released,
                                           double fx, double rx, double fy, double ry,
@@ -351,15 +355,26 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
     if (was_on_ground) {
         float speed = __fsqrt_rn(add32(mul32(vx, vx), mul32(vy, vy)));
         float control = speed > kStopSpeed ? speed : kStopSpeed;
-        double new_speed = sub64((double)speed, mul64(mul64(dt, (double)control), (double)kFriction));
-        if (!(new_speed > 0.0))
-            new_speed = 0.0;
-        if (speed > 0.0f) {
-            double sd = (double)speed;
-            double ratio = (LEAN && speed > 1e-30f) ? div_rcp(new_speed, sd, rcp_rn(sd))
-                                                    : div64(new_speed, sd);
-            hx = mul64(hx, ratio);
-            hy = mul64(hy, ratio);
+        if (DT32) {
+            float ns = __fsub_rn(speed, mul32(mul32((float)dt, control), kFriction));
+            if (!(ns > 0.0f))
+                ns = 0.0f;
+            if (speed > 0.0f) {
+                float ratio = __fdiv_rn(ns, speed);
+                hx = (double)mul32(vx, ratio);
+                hy = (double)mul32(vy, ratio);
+            }
+        } else {
+            double new_speed = sub64((double)speed, mul64(mul64(dt, (double)control), (double)kFriction));
+            if (!(new_speed > 0.0))
+                new_speed = 0.0;
+            if (speed > 0.0f) {
+                double sd = (double)speed;
+                double ratio = (LEAN && speed > 1e-30f) ? div_rcp(new_speed, sd, rcp_rn(sd))
+                                                        : div64(new_speed, sd);
+                hx = mul64(hx, ratio);
+                hy = mul64(hy, ratio);
+            }
         }
     }
 
@@ -383,8 +398,14 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
     jump_released = jump_released | !jump;
     bool do_jump = was_on_ground && jump && jump_released;
     float v = add32(vz, do_jump ? kJumpSpeed : 0.0f);
-    v = __double2float_rn(sub64((double)v, gravity_dt));
-    double zn = add64(z, mul64(dt, (double)v));
+    double zn;
+    if (DT32) {
+        v = __fsub_rn(v, (float)gravity_dt);                 /* f32 -= f32(800) * f32(dt) */
+        zn = add64(z, (double)mul32((float)dt, v));
+    } else {
+        v = __double2float_rn(sub64((double)v, gravity_dt));
+        zn = add64(z, mul64(dt, (double)v));
+    }
     bool og = zn < (double)kFloorHeight;
     z = og ? (double)kFloorHeight : zn;
     vz = og ? 0.0f : v;

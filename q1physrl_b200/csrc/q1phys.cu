@@ -595,11 +595,39 @@ k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick
 
 /* -- phys.apply on explicit arrays (phys:184-197) ----------------------------------------------- */
 
+/* One row of phys.apply with general pitch / roll; dt_f32: the time_delta array was float32. */
+__device__ __forceinline__ void phys_apply_row(double yaw, double pitch, double roll, bool has_pitch,
+                                               bool has_roll, double fmove, double smove, bool jump,
+                                               double dt, bool dt_f32, float &vx, float &vy,
+                                               float &vz, double &z, bool &og, bool &jr)
+{
+    /* phys:58-66 */
+    double sy, cy, sp = 0.0, cp = 1.0, sr = 0.0, cr = 1.0;
+    sincos(div64(mul64(yaw, kPi), 180.0), &sy, &cy);
+    if (has_pitch)
+        sincos(div64(mul64(pitch, kPi), 180.0), &sp, &cp);
+    if (has_roll)
+        sincos(div64(mul64(roll, kPi), 180.0), &sr, &cr);
+    double fx = mul64(cp, cy);
+    double rx = add64(mul64(mul64(mul64(-1.0, sr), sp), cy), mul64(mul64(-1.0, cr), -sy));
+    double fy = mul64(cp, sy);
+    double ry = add64(mul64(mul64(mul64(-1.0, sr), sp), sy), mul64(mul64(-1.0, cr), cy));
+    if (dt_f32) {
+        /* phys:78 f32(10) * f32(dt), phys:122 f32(800) * f32(dt): f32 products */
+        const float dtf = (float)dt;
+        move_body<false, true>(vx, vy, vz, z, og, jr, fx, rx, fy, ry, fmove, smove, jump, dt,
+                               (double)mul32(10.0f, dtf), (double)mul32(800.0f, dtf));
+    } else {
+        move_body<false, false>(vx, vy, vz, z, og, jr, fx, rx, fy, ry, fmove, smove, jump, dt,
+                                mul64(10.0, dt), mul64(800.0, dt));
+    }
+}
+
 __global__ void __launch_bounds__(kBlock)
 k_phys_apply(int64_t n, const double *__restrict__ yaw, const double *__restrict__ pitch,
              const double *__restrict__ roll, const double *__restrict__ fmove,
              const double *__restrict__ smove, const uint8_t *__restrict__ button2,
-             const double *__restrict__ time_delta, const double *__restrict__ z_pos,
+             const double *__restrict__ time_delta, int dt_f32, const double *__restrict__ z_pos,
              const float *__restrict__ vel, const uint8_t *__restrict__ on_ground,
              const uint8_t *__restrict__ jump_released, double *__restrict__ z_out,
              float *__restrict__ vel_out, uint8_t *__restrict__ og_out, uint8_t *__restrict__ jr_out)
@@ -607,31 +635,43 @@ k_phys_apply(int64_t n, const double *__restrict__ yaw, const double *__restrict
     int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
-    /* phys:58-66, general pitch / roll */
-    double sy, cy, sp = 0.0, cp = 1.0, sr = 0.0, cr = 1.0;
-    sincos(div64(mul64(yaw[i], kPi), 180.0), &sy, &cy);
-    if (pitch)
-        sincos(div64(mul64(pitch[i], kPi), 180.0), &sp, &cp);
-    if (roll)
-        sincos(div64(mul64(roll[i], kPi), 180.0), &sr, &cr);
-    double fx = mul64(cp, cy);
-    double rx = add64(mul64(mul64(mul64(-1.0, sr), sp), cy), mul64(mul64(-1.0, cr), -sy));
-    double fy = mul64(cp, sy);
-    double ry = add64(mul64(mul64(mul64(-1.0, sr), sp), sy), mul64(mul64(-1.0, cr), cy));
-
     float vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
     double z = z_pos[i];
     bool og = on_ground[i] != 0, jr = jump_released[i] != 0;
-    double dt = time_delta[i];
-    /* phys:78 f32(10) * dt, phys:122 f32(800) * dt */
-    move_body<false>(vx, vy, vz, z, og, jr, fx, rx, fy, ry, fmove[i], smove[i], button2[i] != 0, dt,
-              mul64(10.0, dt), mul64(800.0, dt));
+    phys_apply_row(yaw[i], pitch ? pitch[i] : 0.0, roll ? roll[i] : 0.0, pitch != nullptr,
+                   roll != nullptr, fmove[i], smove[i], button2[i] != 0, time_delta[i], dt_f32 != 0,
+                   vx, vy, vz, z, og, jr);
     z_out[i] = z;
     vel_out[3 * i] = vx;
     vel_out[3 * i + 1] = vy;
     vel_out[3 * i + 2] = vz;
     og_out[i] = og;
     jr_out[i] = jr;
+}
+
+/* q1physrl/analyse.py:92-118 `hypothetical_delta_speeds` in one launch: for every frame t and every
+ * relative wish angle a, the ground-speed change of one phys.apply tick with yaw = base_yaw[t] +
+ * rel_angle[a] and constant fmove / smove / time_delta.  out[a * n + t] = |v'| - |v| in f32. */
+__global__ void __launch_bounds__(kBlock)
+k_delta_speed_sweep(int64_t n, int64_t num_angles, const double *__restrict__ base_yaw,
+                    const double *__restrict__ rel_angle, double fmove, double smove,
+                    const uint8_t *__restrict__ button2, double time_delta, int dt_f32,
+                    const double *__restrict__ z_pos, const float *__restrict__ vel,
+                    const uint8_t *__restrict__ on_ground, const uint8_t *__restrict__ jump_released,
+                    float *__restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t a = blockIdx.y;
+    if (t >= n || a >= num_angles)
+        return;
+    float vx = vel[3 * t], vy = vel[3 * t + 1], vz = vel[3 * t + 2];
+    double z = z_pos[t];
+    bool og = on_ground[t] != 0, jr = jump_released[t] != 0;
+    const float before = __fsqrt_rn(add32(mul32(vx, vx), mul32(vy, vy)));
+    phys_apply_row(add64(base_yaw[t], rel_angle[a]), 0.0, 0.0, true, true, fmove, smove,
+                   button2[t] != 0, time_delta, dt_f32 != 0, vx, vy, vz, z, og, jr);
+    const float after = __fsqrt_rn(add32(mul32(vx, vx), mul32(vy, vy)));
+    out[a * n + t] = __fsub_rn(after, before);
 }
 
 /* -- env.ActionDecoder.map on explicit decoder state (env:225-269), f64 stamps ------------------- */
@@ -1652,7 +1692,7 @@ int q1_get_metrics_host(q1_env *env, int clear, q1_metrics *out)
 
 int q1_phys_apply(int device, int64_t n, const double *yaw, const double *pitch, const double *roll,
                   const double *fmove, const double *smove, const uint8_t *button2,
-                  const double *time_delta, const double *z_pos, const float *vel,
+                  const double *time_delta, int time_delta_f32, const double *z_pos, const float *vel,
                   const uint8_t *on_ground, const uint8_t *jump_released, double *z_pos_out,
                   float *vel_out, uint8_t *on_ground_out, uint8_t *jump_released_out, void *stream)
 {
@@ -1667,7 +1707,7 @@ int q1_phys_apply(int device, int64_t n, const double *yaw, const double *pitch,
     if (!guard.ok)
         return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
     k_phys_apply<<<grid_for(n), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-        n, yaw, pitch, roll, fmove, smove, button2, time_delta, z_pos, vel, on_ground,
+        n, yaw, pitch, roll, fmove, smove, button2, time_delta, time_delta_f32, z_pos, vel, on_ground,
         jump_released, z_pos_out, vel_out, on_ground_out, jump_released_out);
     return check_launch("k_phys_apply");
 }
@@ -1675,7 +1715,8 @@ int q1_phys_apply(int device, int64_t n, const double *yaw, const double *pitch,
 
 int q1_phys_apply_host(int device, int64_t n, const double *yaw, const double *pitch,
                        const double *roll, const double *fmove, const double *smove,
-                       const uint8_t *button2, const double *time_delta, const double *z_pos,
+                       const uint8_t *button2, const double *time_delta, int time_delta_f32,
+                       const double *z_pos,
                        const float *vel, const uint8_t *on_ground, const uint8_t *jump_released,
                        double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
                        uint8_t *jump_released_out)
@@ -1718,14 +1759,56 @@ int q1_phys_apply_host(int device, int64_t n, const double *yaw, const double *p
     Q1_CUDA(up(d_b2, button2, N));
     Q1_CUDA(up(d_og, on_ground, N));
     Q1_CUDA(up(d_jr, jump_released, N));
-    rc = q1_phys_apply(device, n, d_yaw, d_pitch, d_roll, d_fm, d_sm, d_b2, d_dt, d_z, d_vel, d_og,
-                       d_jr, d_zo, d_velo, d_ogo, d_jro, nullptr);
+    rc = q1_phys_apply(device, n, d_yaw, d_pitch, d_roll, d_fm, d_sm, d_b2, d_dt, time_delta_f32, d_z,
+                       d_vel, d_og, d_jr, d_zo, d_velo, d_ogo, d_jro, nullptr);
     if (rc != Q1_OK)
         return rc;
     Q1_CUDA(cudaMemcpy(z_pos_out, d_zo, 8 * N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(vel_out, d_velo, 12 * N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(on_ground_out, d_ogo, N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(jump_released_out, d_jro, N, cudaMemcpyDeviceToHost));
+    return Q1_OK;
+}
+
+int q1_delta_speed_sweep_host(int device, int64_t n, int64_t num_angles, const double *base_yaw,
+                              const double *rel_angles, double fmove, double smove,
+                              const uint8_t *button2, double time_delta, int time_delta_f32,
+                              const double *z_pos, const float *vel, const uint8_t *on_ground,
+                              const uint8_t *jump_released, float *delta_speed)
+{
+    if (n < 0 || num_angles < 0 || num_angles > 65535)
+        return fail(Q1_EINVAL, "n must be >= 0 and num_angles in [0, 65535]");
+    if (n == 0 || num_angles == 0)
+        return Q1_OK;
+    if (!base_yaw || !rel_angles || !button2 || !z_pos || !vel || !on_ground || !jump_released ||
+        !delta_speed)
+        return fail(Q1_EINVAL, "a required array is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    const size_t N = (size_t)n, A = (size_t)num_angles;
+    Staging st;
+    int rc = st.reserve(align_up(8 * N) * 2 + align_up(8 * A) + align_up(12 * N) + align_up(N) * 3 +
+                        align_up(4 * N * A) + 4096);
+    if (rc != Q1_OK)
+        return rc;
+    double *d_yaw = st.take<double>(N), *d_rel = st.take<double>(A), *d_z = st.take<double>(N);
+    float *d_vel = st.take<float>(3 * N), *d_out = st.take<float>(N * A);
+    uint8_t *d_b2 = st.take<uint8_t>(N), *d_og = st.take<uint8_t>(N), *d_jr = st.take<uint8_t>(N);
+    Q1_CUDA(cudaMemcpy(d_yaw, base_yaw, 8 * N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_rel, rel_angles, 8 * A, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_z, z_pos, 8 * N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_vel, vel, 12 * N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_b2, button2, N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_og, on_ground, N, cudaMemcpyHostToDevice));
+    Q1_CUDA(cudaMemcpy(d_jr, jump_released, N, cudaMemcpyHostToDevice));
+    dim3 grid(grid_for(n), (unsigned)num_angles);
+    k_delta_speed_sweep<<<grid, kBlock>>>(n, num_angles, d_yaw, d_rel, fmove, smove, d_b2, time_delta,
+                                          time_delta_f32, d_z, d_vel, d_og, d_jr, d_out);
+    rc = check_launch("k_delta_speed_sweep");
+    if (rc != Q1_OK)
+        return rc;
+    Q1_CUDA(cudaMemcpy(delta_speed, d_out, 4 * N * A, cudaMemcpyDeviceToHost));
     return Q1_OK;
 }
 

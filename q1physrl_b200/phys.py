@@ -95,6 +95,8 @@ def apply(inputs: Inputs, player_state: PlayerState, device: int = 0) -> PlayerS
     roll = _f64(inputs.roll, n) if np.any(np.asarray(inputs.roll) != 0) else None
     button2, og, jr = (_u8(a, n) for a in (inputs.button2, player_state.on_ground,
                                            player_state.jump_released))
+    # NumPy computes friction / gravity in f32 when the time_delta array is float32 (analyse.py:110)
+    dt_f32 = int(np.asarray(inputs.time_delta).dtype == np.float32)
     z_out = np.empty(n, np.float64)
     vel_out = np.empty((n, 3), np.float32)
     og_out = np.empty(n, np.uint8)
@@ -102,6 +104,6 @@ def apply(inputs: Inputs, player_state: PlayerState, device: int = 0) -> PlayerS
     _lib.check(_lib.load().q1_phys_apply_host(
         device, n, _ptr(yaw), _ptr(pitch) if pitch is not None else None,
         _ptr(roll) if roll is not None else None, _ptr(fmove), _ptr(smove), _ptr(button2),
-        _ptr(dt), _ptr(z), _ptr(vel), _ptr(og), _ptr(jr),
+        _ptr(dt), dt_f32, _ptr(z), _ptr(vel), _ptr(og), _ptr(jr),
         _ptr(z_out), _ptr(vel_out), _ptr(og_out), _ptr(jr_out)))
     return PlayerState(z_out, vel_out, og_out.astype(bool), jr_out.astype(bool))

@@ -168,6 +168,72 @@ def record_phys_apply(name, n, seed):
     print(f"{name}: n={n} {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def record_phys_apply_dt32(name, n, seed):
+    """phys.apply fed as q1physrl/analyse.py:102-113 feeds it: float32 fmove / smove / time_delta."""
+    rng = np.random.default_rng(seed)
+    yaw = rng.uniform(-720, 720, n)
+    fmove = rng.choice([0., 400., 800.], n).astype(np.float32)
+    smove = rng.choice([0., 530., -530., 1060., -1060.], n).astype(np.float32)
+    button2 = rng.random(n) < 0.5
+    dt = np.full(n, 0.014, np.float32)
+    z = np.where(rng.random(n) < 0.5, np.float64(np.float32(24.03125)), rng.uniform(24.03125, 80, n))
+    vel = (rng.normal(0, 250, (n, 3)) * (rng.random((n, 1)) > 0.05)).astype(np.float32)
+    og = z <= 24.03125
+    vel[og, 2] = 0
+    jr = rng.random(n) < 0.8
+    inputs = ref_phys.Inputs(yaw=yaw, pitch=np.zeros(n, np.float32), roll=np.zeros(n, np.float32),
+                             fmove=fmove, smove=smove, button2=button2, time_delta=dt)
+    ps = ref_phys.PlayerState(z_pos=z, vel=vel, on_ground=og, jump_released=jr)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out = ref_phys.apply(inputs, ps)
+    assert out.vel.dtype == np.float32 and out.z_pos.dtype == np.float64
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, yaw=yaw, fmove=fmove, smove=smove, button2=button2, time_delta=dt,
+                        z_pos=z, vel=vel, on_ground=og, jump_released=jr, out_z_pos=out.z_pos,
+                        out_vel=out.vel, out_on_ground=out.on_ground,
+                        out_jump_released=out.jump_released)
+    print(f"{name}: n={n} {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def record_delta_speeds(name, seed):
+    """EvalSimResult.hypothetical_delta_speeds (q1physrl/analyse.py:92-118) of a scripted zero-start
+    run: the loop of 360 phys.apply calls, restated here because analyse.py itself imports cv2 / ray."""
+    cfg = ref_env.Config(**dict(PARAMS_100M, num_envs=1, zero_start_prob=1.0, time_limit=3.0))
+    np.random.seed(seed)
+    e = ref_env.VectorPhysEnv(cfg)
+    states, jumps = [], []
+    done, t = False, 0
+    while not done:
+        keys, mouse = strafe_jump_actions(cfg, 1, 4, t)
+        acts = np.concatenate([keys.astype(np.float64), mouse[:, None]], axis=1)
+        dec_jump = bool(keys[0, 3])
+        states.append(e.player_state)
+        jumps.append(dec_jump)
+        _, _, (done,), _ = e.vector_step(acts)
+        t += 1
+    ps = ref_phys.PlayerState.concatenate(states)
+    jump = np.array(jumps)
+    move_angle = 180. * np.arctan2(ps.vel[:, 1], ps.vel[:, 0]) / np.pi          # analyse.py:84
+    assert move_angle.dtype == np.float32
+    out = []
+    for rel in np.arange(-180, 180):
+        inputs = ref_phys.Inputs(yaw=move_angle + rel, pitch=np.zeros_like(move_angle),
+                                 roll=np.zeros_like(move_angle), fmove=np.full_like(move_angle, 800.),
+                                 smove=np.zeros_like(move_angle), button2=jump,
+                                 time_delta=np.full_like(move_angle, 0.014))
+        before = np.linalg.norm(ps.vel[:, :2], axis=1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            nxt = ref_phys.apply(inputs, ps)
+        out.append(np.linalg.norm(nxt.vel[:, :2], axis=1) - before)
+    out = np.stack(out)
+    assert out.dtype == np.float32
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, z_pos=ps.z_pos, vel=ps.vel, on_ground=ps.on_ground,
+                        jump_released=ps.jump_released, jump=jump, move_angle=move_angle,
+                        delta_speeds=out)
+    print(f"{name}: frames={len(jump)} {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def record_decoder(name, cfg_dict, n, ticks, seed):
     """Standalone ActionDecoder.map driven as mkdemo.py:47-64 does, with arbitrary z_vel / time."""
     cfg_dict = dict(cfg_dict, num_envs=n)
@@ -218,6 +284,8 @@ def main():
                                          time_limit=4.0), 16, 340, seed=8)
         record("noyaw_n8", dict(DEFAULT, allow_yaw=False, zero_start_prob=0.5), 8, 300, seed=9)
         record_phys_apply("phys_apply_n4096", 4096, seed=10)
+        record_phys_apply_dt32("phys_apply_dt32_n4096", 4096, seed=13)
+        record_delta_speeds("delta_speeds", seed=14)
         record_decoder("decoder_n64", PARAMS_100M, 64, 120, seed=11)
         record_decoder("decoder_discrete_n64", dict(DEFAULT, discrete_yaw_steps=7, smooth_keys=False,
                                                     auto_jump=True), 64, 120, seed=12)

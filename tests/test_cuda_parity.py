@@ -6,6 +6,8 @@ time_remaining bit-exact (pure f64 add chains), velocity within 1e-5 abs -- the 
 difference is CUDA's f64 sincos (<= 2 ulp) against glibc's; the tests report how many stored f32
 velocities are bit-identical.
 """
+import dataclasses
+
 import numpy as np
 import pytest
 
@@ -380,3 +382,68 @@ def test_host_pipeline_matches_single_shot():
     for f in harness.STATE_FIELDS:
         assert np.array_equal(sa[f], sb[f]), f
     assert a.info.ticks == b.info.ticks == 80
+
+
+def test_phys_apply_float32_time_delta_golden():
+    from q1physrl_b200 import phys
+    g = harness.load_golden("phys_apply_dt32_n4096")
+    n = g["yaw"].shape[0]
+    out = phys.apply(phys.Inputs(yaw=g["yaw"], pitch=np.zeros(n, np.float32), roll=np.zeros(n, np.float32),
+                                 fmove=g["fmove"], smove=g["smove"], button2=g["button2"],
+                                 time_delta=g["time_delta"]),
+                     phys.PlayerState(g["z_pos"], g["vel"], g["on_ground"], g["jump_released"]))
+    assert np.array_equal(out.z_pos, g["out_z_pos"]) and np.array_equal(out.on_ground, g["out_on_ground"])
+    assert np.array_equal(out.jump_released, g["out_jump_released"])
+    assert np.abs(out.vel.astype(np.float64) - g["out_vel"]).max() <= VEL_ATOL
+    print("phys.apply (f32 dt) bit-exact velocity fraction", np.mean(out.vel == g["out_vel"]))
+
+
+def test_hypothetical_delta_speeds_golden():
+    """analyse.EvalSimResult.hypothetical_delta_speeds: one sweep launch vs the reference's 360
+    phys.apply calls."""
+    from q1physrl_b200 import analyse, phys
+    g = harness.load_golden("delta_speeds")
+    n = g["jump"].shape[0]
+    res = analyse.EvalSimResult(
+        time_delta=0.013888888888888,
+        player_state=phys.PlayerState(g["z_pos"], g["vel"], g["on_ground"], g["jump_released"]),
+        action=np.zeros((n, 5)), obs=np.zeros((n, 6)), reward=np.zeros(n), yaw=np.zeros(n),
+        smove=np.zeros(n), fmove=np.zeros(n), jump=g["jump"])
+    assert np.array_equal(res.move_angle, g["move_angle"])
+    ds = res.hypothetical_delta_speeds
+    assert ds.shape == (360, n) and ds.dtype == np.float32
+    diff = np.abs(ds.astype(np.float64) - g["delta_speeds"])
+    print("delta-speed sweep: max abs", diff.max(), "bit-exact fraction", np.mean(ds == g["delta_speeds"]))
+    assert diff.max() <= 1e-4                                 # |v| up to ~700: one f32 ulp is 6e-5
+    assert np.mean(ds == g["delta_speeds"]) > 0.9999
+
+
+def test_eval_sim_matches_stepping_the_env():
+    """analyse.eval_sim with a scripted `compute_action`: the recorded yaw / smove / fmove / jump of
+    the shadow decoder and the recorded states agree with a second env stepped with the same actions."""
+    from q1physrl_b200 import analyse, env as benv
+
+    class Scripted:
+        def __init__(self):
+            self.t = 0
+
+        def compute_action(self, obs):
+            t, self.t = self.t, self.t + 1
+            return (int(t % 72 < 36), int(t % 72 >= 36), 1, t & 1, np.array([1.5 if t % 72 < 36 else -1.5], np.float32))
+
+    cfg = benv.Config(**dict(harness.PARAMS_100M, num_envs=1, zero_start_prob=1.0, time_limit=2.0))
+    res = analyse.eval_sim(Scripted(), cfg, seed=3)
+    T = res.reward.shape[0]
+    assert T == 145 and res.obs.shape == (T, 6) and res.player_state.vel.shape == (T, 3)
+    assert res.action.shape == (T, 5) and res.yaw.shape == (T,) and res.jump.dtype == np.bool_
+    e = benv.VectorPhysEnv(dataclasses.asdict(cfg), seed=3)
+    pol = Scripted()
+    o, = e.vector_reset()
+    for t in range(T):
+        assert np.array_equal(o, res.obs[t])
+        assert np.array_equal(e.player_state.vel[0], res.player_state.vel[t])
+        a = pol.compute_action(o)
+        (o,), (r,), (d,), _ = e.vector_step([a])
+        assert r == res.reward[t] and e._yaw[0] == res.yaw[t]
+    assert d and set(np.unique(res.fmove)) <= {0, 400, 800} and set(np.unique(np.abs(res.smove))) <= {0, 530, 1060}
+    assert res.hypothetical_delta_speeds.shape == (360, T)

@@ -86,3 +86,29 @@ def test_reset_distribution_quirks():
     assert ang.min() > 0.99                                   # nothing in [0, 1) rad
     assert np.all(o.z_pos == np.float64(np.float32(32.843201))) and np.all(o.vel[:, 2] == -12)
     assert not o.on_ground.any() and o.jump_released.all()
+
+
+def test_oracle_phys_apply_float32_time_delta():
+    """A float32 time_delta array makes NumPy run friction / gravity in f32 (analyse.py:110)."""
+    g = harness.load_golden("phys_apply_dt32_n4096")
+    n = g["yaw"].shape[0]
+    assert g["time_delta"].dtype == np.float32
+    z, vel, og, jr = qo.phys_apply(g["yaw"], np.zeros(n), np.zeros(n), g["fmove"], g["smove"],
+                                   g["button2"], g["time_delta"], g["z_pos"], g["vel"],
+                                   g["on_ground"], g["jump_released"])
+    assert np.array_equal(z, g["out_z_pos"]) and np.array_equal(vel, g["out_vel"])
+    assert np.array_equal(og, g["out_on_ground"]) and np.array_equal(jr, g["out_jump_released"])
+
+
+def test_oracle_hypothetical_delta_speeds():
+    """analyse.py:92-118 through the oracle: 360 phys.apply calls on the recorded episode."""
+    g = harness.load_golden("delta_speeds")
+    n = g["jump"].shape[0]
+    ma = g["move_angle"]
+    assert ma.dtype == np.float32 and g["delta_speeds"].shape == (360, n)
+    before = np.linalg.norm(g["vel"][:, :2], axis=1)
+    for a, rel in enumerate(np.arange(-180, 180)):
+        _, vel, _, _ = qo.phys_apply(ma + rel, np.zeros(n), np.zeros(n), np.full_like(ma, 800.),
+                                     np.zeros_like(ma), g["jump"], np.full_like(ma, 0.014),
+                                     g["z_pos"], g["vel"], g["on_ground"], g["jump_released"])
+        assert np.array_equal(np.linalg.norm(vel[:, :2], axis=1) - before, g["delta_speeds"][a]), rel
