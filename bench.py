@@ -272,11 +272,30 @@ def run_cuda_arm(args, rank, world, local_rank):
     h2d = n * (nk + 4)
     d2h = n * (24 + 4 + 1 + 1)
 
-    # ---- the metric reduction (the one collective of this path): zero_start_total_reward_mean
-    from q1physrl_b200 import sharding
-    tracked = benv.VectorPhysEnv(workload_config(1 << 14), device=local_rank, seed=args.seed,
-                                 env_index_base=rank << 14, track_returns=True)
-    tracked.rollout("strafe_jump", 722, policy_seed=1)
+    # ---- BASELINE config 5 + the one collective of this path: zero_start_total_reward_mean of the
+    # reference's shipped policy (data/checkpoints/wr, weights in tests/golden/wr_policy.npz), rolled
+    # out closed-loop on the device over 32768 envs per GPU (262144 over 8), metric all-reduced.
+    from q1physrl_b200 import policy as bpolicy, sharding
+    policy_path = os.path.join(ROOT, "tests", "golden", "wr_policy.npz")
+    n5, ticks5 = 1 << 15, 1500
+    if os.path.exists(policy_path):
+        pol, env_cfg = bpolicy.MLPPolicy.from_npz(policy_path, device=local_rank, seed=args.seed)
+        cfg5 = dict(env_cfg, initial_yaw_range=tuple(env_cfg["initial_yaw_range"]), num_envs=n5)
+        tracked = benv.VectorPhysEnv(cfg5, device=local_rank, seed=args.seed,
+                                     env_index_base=rank * n5, track_returns=True)
+        torch.cuda.synchronize(dev)
+        t5 = time.perf_counter()
+        bpolicy.rollout(tracked, pol, ticks5)
+        torch.cuda.synchronize(dev)
+        t5 = time.perf_counter() - t5
+        policy_desc = (f"reference checkpoint data/checkpoints/wr (stochastic Q1PhysActionDist), params.json "
+                       f"env_config, {n5} envs/GPU x {ticks5} ticks closed loop on the device, "
+                       f"{world * n5 * ticks5 / t5:.3e} env-steps/s incl. the policy MLP")
+    else:
+        tracked = benv.VectorPhysEnv(workload_config(n5), device=local_rank, seed=args.seed,
+                                     env_index_base=rank * n5, track_returns=True)
+        tracked.rollout("strafe_jump", 722, policy_seed=1)
+        policy_desc = f"scripted strafe_jump, 722 ticks, {n5} envs/GPU"
     red = sharding.reduce_metrics(tracked.metrics(), device=dev)
     zs_mean, zs_episodes = red["zero_start_total_reward_mean"], red["zero_start_episodes"]
 
@@ -306,7 +325,7 @@ def run_cuda_arm(args, rank, world, local_rank):
                          "bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src},
             "clocks": clocks.summary(),
             "zero_start_total_reward_mean": {"value": zs_mean, "episodes": zs_episodes,
-                                             "policy": "scripted strafe_jump, 722 ticks, 16384 envs/GPU",
+                                             "policy": policy_desc,
                                              "collective": "all_reduce(sum) of (sum, count)" if world > 1 else "none (1 GPU)"},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -227,6 +227,15 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n,
                    const float *z_vel, const double *time_remaining,
                    int64_t *smove, int64_t *fmove, uint8_t *jump);
 
+/* Q1PhysActionDist (q1physrl/action_dist.py:199-243) on a batch of policy outputs, DEVICE arrays:
+ * logits (n, 2 * num_keys + 2) f32 = per key (logit of 0, logit of 1), then (mean, log_std) of the
+ * mouse action.  Writes keys (n, num_keys) u8 and mouse (n,) f32 in the layout q1_step consumes.
+ * deterministic != 0: argmax keys and squash(mean) (action_dist.py:84-88); otherwise Categorical and
+ * Gaussian draws from a counter-based generator keyed by (seed, env_index_base + i, step). */
+int q1_sample_actions(int device, int64_t n, int num_keys, const float *logits, double action_low,
+                      double action_high, int deterministic, uint64_t seed, uint64_t step,
+                      uint64_t env_index_base, uint8_t *keys, float *mouse, void *stream);
+
 /* Self-check of the branch-free reciprocal-multiply division sequences the kernels use against the
  * CUDA IEEE intrinsics, on ~`samples` random operand pairs per class (bit comparison):
  *   [0] reciprocal  [1] a / variable b  [2] a / constant  [3] wish_vel / wish_speed range

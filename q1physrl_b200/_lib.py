@@ -113,6 +113,8 @@ SIGNATURES = {
     "q1_phys_apply_host": (c_int, [c_int, c_i64] + [c_void_p] * 7 + [c_int] + [c_void_p] * 8),
     "q1_delta_speed_sweep_host": (c_int, [c_int, c_i64, c_i64, c_void_p, c_void_p, c_double, c_double,
                                           c_void_p, c_double, c_int] + [c_void_p] * 5),
+    "q1_sample_actions": (c_int, [c_int, c_i64, c_int, c_void_p, c_double, c_double, c_int, c_u64, c_u64,
+                                  c_u64, c_void_p, c_void_p, c_void_p]),
     "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 8)]),
     "q1_decode_host": (c_int, [ctypes.POINTER(Q1Config), c_int, c_i64] + [c_void_p] * 10),
 }

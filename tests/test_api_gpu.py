@@ -142,3 +142,35 @@ def test_errors_are_loud():
         e.metrics()                                          # needs track_returns
     with pytest.raises(_lib.Q1Error):
         e.reset_at(4)
+
+
+def test_shipped_policy_closed_loop():
+    """the reference's shipped checkpoint evaluated on the GPU.  Known answers
+    recorded from a NumPy evaluation on the unmodified reference env (make_policy_fixture.py)."""
+    import os
+    import torch
+    from q1physrl_b200 import analyse, env as benv, policy as bpolicy
+    path = os.path.join(harness.GOLDEN_DIR, "wr_policy.npz")
+    pol, env_config = bpolicy.MLPPolicy.from_npz(path, seed=1)
+    g = np.load(path)
+    # the MLP itself against the recorded NumPy float32 logits
+    lg = pol.logits(torch.as_tensor(g["det_obs"]).cuda()).cpu().numpy()
+    assert np.abs(lg - g["det_logits"]).max() < 2e-4
+    # deterministic zero-start episode through eval_sim: 720 ticks, sum reward 5753.04
+    cfg = benv.Config(**dict(env_config, initial_yaw_range=tuple(env_config["initial_yaw_range"]),
+                             num_envs=1, zero_start_prob=1.0))
+    res = analyse.eval_sim(pol, cfg, seed=0)
+    assert res.reward.shape[0] == int(g["det_ticks"]) == 720
+    total = float(res.reward.astype(np.float64).sum())
+    print("deterministic policy return", total, "reference", float(g["det_return"]))
+    assert abs(total - float(g["det_return"])) < 1.0
+    speed = np.hypot(res.player_state.vel[:, 0], res.player_state.vel[:, 1]).max()
+    assert abs(speed - float(g["det_max_speed"])) < 0.5
+    # stochastic closed loop on the device: zero_start_total_reward_mean ~ 5700 (README.md:54)
+    n = 4096
+    e = benv.VectorPhysEnv(dict(dataclasses.asdict(cfg), num_envs=n), seed=2, track_returns=True)
+    bpolicy.rollout(e, pol, 721)
+    m = e.metrics()
+    print("stochastic policy:", m)
+    assert m["zero_start_episodes"] == n
+    assert 5600 < m["zero_start_total_reward_mean"] < 5800
