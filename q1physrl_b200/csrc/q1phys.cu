@@ -202,7 +202,6 @@ __device__ __forceinline__ void bulk_wait_read_all()
 {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_smem_to_async_proxy()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -449,7 +448,8 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         so ^= 1u;
     }
     if (issuer)
-        bulk_wait_all();
+        bulk_wait_read_all(); /* shared memory must outlive the reads of the last bulk stores; their
+                                 global writes complete with the grid */
 }
 
 /* The same tick, one env per thread with plain loads and stores: f64-stamp mode, ragged tails
