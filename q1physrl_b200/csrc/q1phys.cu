@@ -183,18 +183,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "}" ::"r"(bar), "r"(parity)
                  : "memory");
 }
-/* global -> shared bulk copy that signals `bar` with the byte count when it lands */
-__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t bar)
+/* L2 eviction policy for data that is streamed through once per tick (state, actions, results):
+ * evict-first keeps the 126 MB L2 from filling with dirty lines that must be written back later in
+ * bursts.  Q1_L2_HINTS: bit 0 = hint the bulk loads, bit 1 = hint the bulk stores. */
+#ifndef Q1_L2_HINTS
+#define Q1_L2_HINTS 2
+#endif
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar)
-                 : "memory");
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+/* global -> shared bulk copy that signals `bar` with the byte count when it lands */
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t bar,
+                                          uint64_t policy)
+{
+    if (Q1_L2_HINTS & 1)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                     "[%0], [%1], %2, [%3], %4;" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar)
+                     : "memory");
 }
 /* shared -> global bulk copy, tracked by this thread's bulk async-group */
-__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes)
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes, uint64_t policy)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
-                 : "memory");
+    if (Q1_L2_HINTS & 2)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                     "r"(ssrc), "r"(bytes), "l"(policy)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc),
+                     "r"(bytes)
+                     : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 /* all bulk groups of this thread have finished READING shared memory */
@@ -313,14 +337,15 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     uint32_t in0 = smem_addr(in_mem), out0 = smem_addr(out_mem), bar0 = smem_addr(full_bar);
     asm volatile("" : "+r"(in0), "+r"(out0), "+r"(bar0)); /* pinned: no re-derivation per tile */
 
+    const uint64_t l2pol = Q1_L2_HINTS ? l2_evict_first_policy() : 0;
     auto issue_loads = [&](uint32_t s, int64_t tile) {
         asm volatile("" : "+l"(tile)); /* address arithmetic stays inside the issuing lane's branch */
         const uint32_t st = in0 + s * IN_BYTES, bar = bar0 + s * 8u;
         mbar_expect_tx(bar, in_bytes);
-        bulk_load(st + IN_STATE, P.state + tile * kTileBytes, kTileBytes, bar);
-        bulk_load(st + IN_KEYS, keys + tile * (nk * kTile), nk * kTile, bar);
+        bulk_load(st + IN_STATE, P.state + tile * kTileBytes, kTileBytes, bar, l2pol);
+        bulk_load(st + IN_KEYS, keys + tile * (nk * kTile), nk * kTile, bar, l2pol);
         if (mouse_bytes)
-            bulk_load(st + IN_MOUSE, static_cast<const char *>(mouse) + tile * mouse_bytes, mouse_bytes, bar);
+            bulk_load(st + IN_MOUSE, static_cast<const char *>(mouse) + tile * mouse_bytes, mouse_bytes, bar, l2pol);
     };
 
     /* Programmatic dependent launch: the next kernel in the stream may start placing its CTAs as
@@ -420,16 +445,16 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             int64_t t = tile;
             asm volatile("" : "+l"(t));
             if (warp == 0) {
-                bulk_store(P.state + t * kTileBytes, sb + IN_STATE, kTileBytes);
+                bulk_store(P.state + t * kTileBytes, sb + IN_STATE, kTileBytes, l2pol);
                 bulk_commit();
             } else if (warp == 1) {
-                bulk_store(obs + t * (6 * kTile), ob + OUT_OBS, 24 * kTile);
-                bulk_store(reward + t * kTile, ob + OUT_REWARD, 4 * kTile);
+                bulk_store(obs + t * (6 * kTile), ob + OUT_OBS, 24 * kTile, l2pol);
+                bulk_store(reward + t * kTile, ob + OUT_REWARD, 4 * kTile, l2pol);
                 bulk_commit();
             } else if (warp == 2) {
-                bulk_store(done + t * kTile, ob + OUT_DONE, kTile);
+                bulk_store(done + t * kTile, ob + OUT_DONE, kTile, l2pol);
                 if (zero_start)
-                    bulk_store(zero_start + t * kTile, ob + OUT_ZS, kTile);
+                    bulk_store(zero_start + t * kTile, ob + OUT_ZS, kTile, l2pol);
                 bulk_commit();
             } else {
                 /* refill the stage of the previous tile: all warps left it a barrier ago and its
