@@ -251,8 +251,8 @@ def run_cuda_arm(args, rank, world, local_rank):
 
     # ---- e2e: the public API with host arrays (page-locked), copies inside the timed region
     e = envs[0]
-    h_keys = e._pinned.empty((n, nk), np.uint8)
-    h_mouse = e._pinned.empty((n,), np.float32)
+    h_keys = e.pinned_empty((n, nk), np.uint8)
+    h_mouse = e.pinned_empty((n,), np.float32)
     h_keys[...] = keys[0].cpu().numpy()
     h_mouse[...] = mouse[0].cpu().numpy()
     e2e_steps = max(3, min(args.e2e_steps, args.steps))

@@ -325,6 +325,10 @@ class VectorPhysEnv(VectorEnv):
                         sequences (same results, slower; used by the self-checks)
       reuse_output_buffers  return views of two alternating page-locked buffer sets from
                         `vector_step` instead of fresh arrays (default: only for num_envs >= 65536)
+
+    Environment variables read by the library: Q1PHYS_LIB (path of libq1phys.so), Q1PHYS_NO_PDL
+    (launch the step kernel without programmatic dependent launch), Q1PHYS_HOST_CHUNKS (pipeline
+    depth of the NumPy-facing step for large page-locked batches, default 2).
     """
     _step_num: int
 
@@ -393,6 +397,12 @@ class VectorPhysEnv(VectorEnv):
         return self._handle
 
     # ------------------------------------------------------------------ buffers
+    def pinned_empty(self, shape, dtype):
+        """A page-locked NumPy array (freed with the env).  Actions handed to `vector_step` from
+        such arrays, together with `reuse_output_buffers`, let `q1_step_host` run its chunked
+        upload / tick / download pipeline by DMA."""
+        return self._pinned.empty(shape, dtype)
+
     def _outputs(self):
         n = self.num_envs
         if not self._reuse:
@@ -633,6 +643,15 @@ class VectorPhysEnv(VectorEnv):
     @_zero_start.setter
     def _zero_start(self, value):
         self.set_state({"zero_start": value})
+
+    @property
+    def _action_decoder(self):
+        """Read-only view of the decoder state the reference keeps in `env._action_decoder`
+        (env:200-202, 420): `_last_keys`, `_last_key_press_time`, `_yaw`, `_num_keys`."""
+        s = self.get_state(("last_keys", "last_press", "yaw"))
+        view = ActionDecoder(self._config, self._device)
+        view._last_keys, view._last_key_press_time, view._yaw = s["last_keys"], s["last_press"], s["yaw"]
+        return view
 
     def _get_obs(self):
         """Observation of the current state without stepping (env:392-400)."""

@@ -75,6 +75,7 @@ def test_eval_sim_style_usage():
         yaws.append(yaw)
         (o,), (r,), (done,), _ = e.vector_step([a])
         assert yaw == e._yaw[0]                               # shadow decoder tracks the env's yaw
+        assert np.array_equal(e._action_decoder._last_keys, dec._last_keys)
         t += 1
     assert t == 73                                            # 1.0 s at dt=0.0138888 -> 73 ticks
     ps = phys.PlayerState.concatenate(states)

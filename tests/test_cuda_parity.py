@@ -366,8 +366,8 @@ def test_host_pipeline_matches_single_shot():
     cfg = dict(harness.PARAMS_100M, num_envs=n, time_limit=1.0, zero_start_prob=0.5)
     a = benv.VectorPhysEnv(cfg, seed=5, reuse_output_buffers=True)
     b = benv.VectorPhysEnv(cfg, seed=5, reuse_output_buffers=False)
-    pk = a._pinned.empty((n, 4), np.uint8)
-    pm = a._pinned.empty((n,), np.float32)
+    pk = a.pinned_empty((n, 4), np.uint8)
+    pm = a.pinned_empty((n,), np.float32)
     rng = np.random.default_rng(3)
     for t in range(80):
         keys, mouse = harness.random_actions(cfg, rng, n, 4)
@@ -447,3 +447,40 @@ def test_eval_sim_matches_stepping_the_env():
         assert r == res.reward[t] and e._yaw[0] == res.yaw[t]
     assert d and set(np.unique(res.fmove)) <= {0, 400, 800} and set(np.unique(np.abs(res.smove))) <= {0, 530, 1060}
     assert res.hypothetical_delta_speeds.shape == (360, T)
+
+
+def test_division_sequences_selftest():
+    """The branch-free reciprocal-multiply divisions the kernels use, bit for bit against
+    __ddiv_rn / __drcp_rn on 2e9 random operands (1 in 64 with an all-ones significand) and
+    exhaustively for the f32 observation quotients."""
+    import ctypes
+    from q1physrl_b200 import _lib
+    out = (ctypes.c_uint64 * 8)()
+    _lib.check(_lib.load().q1_selftest_division(0, 2 * 10 ** 9, 7, ctypes.byref(out)))
+    assert list(out) == [0] * 8, list(out)
+
+
+def test_lean_arithmetic_equals_ieee_intrinsics_at_full_size():
+    """A/B at BASELINE size: a handle stepping with the reciprocal sequences + own sincos and one
+    using the CUDA IEEE division intrinsics + libdevice sincos; flags, z, yaw, time must be
+    identical, velocities may differ only through the two sincos implementations (both < 1 ulp)."""
+    import torch
+    from q1physrl_b200 import env as benv
+    n = 1 << 20
+    cfg = dict(harness.PARAMS_100M, num_envs=n)
+    a = benv.VectorPhysEnv(cfg, seed=12)
+    b = benv.VectorPhysEnv(cfg, seed=12, ieee_division=True)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    dev = torch.device("cuda", 0)
+    for t in range(60):
+        keys = torch.randint(0, 2, (n, 4), generator=g, device=dev, dtype=torch.uint8)
+        mouse = torch.rand(n, generator=g, device=dev, dtype=torch.float32) * 20 - 10
+        oa = a.step_tensors(keys, mouse, auto_reset=True)
+        ob = b.step_tensors(keys, mouse, auto_reset=True)
+        assert torch.equal(oa[2], ob[2]) and torch.equal(oa[3], ob[3])
+    sa, sb = a.get_state(), b.get_state()
+    for f in ("z_pos", "yaw", "time_remaining", "on_ground", "jump_released", "zero_start", "last_keys"):
+        assert np.array_equal(sa[f], sb[f]), f
+    same = np.mean(sa["vel"] == sb["vel"])
+    print("lean vs IEEE/libdevice: identical f32 velocity stores", same)
+    assert np.abs(sa["vel"].astype(np.float64) - sb["vel"]).max() <= 1e-4 and same > 0.99999
