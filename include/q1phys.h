@@ -231,10 +231,29 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n,
  * logits (n, 2 * num_keys + 2) f32 = per key (logit of 0, logit of 1), then (mean, log_std) of the
  * mouse action.  Writes keys (n, num_keys) u8 and mouse (n,) f32 in the layout q1_step consumes.
  * deterministic != 0: argmax keys and squash(mean) (action_dist.py:84-88); otherwise Categorical and
- * Gaussian draws from a counter-based generator keyed by (seed, env_index_base + i, step). */
+ * Gaussian draws from a counter-based generator keyed by (seed, env_index_base + i, step).
+ * step_device (DEVICE pointer, may be NULL) overrides `step` with the value it points to, so a
+ * captured CUDA graph can advance the noise stream between replays. */
 int q1_sample_actions(int device, int64_t n, int num_keys, const float *logits, double action_low,
                       double action_high, int deterministic, uint64_t seed, uint64_t step,
-                      uint64_t env_index_base, uint8_t *keys, float *mouse, void *stream);
+                      const uint64_t *step_device, uint64_t env_index_base, uint8_t *keys,
+                      float *mouse, void *stream);
+
+/* The shipped policy network fused into one kernel: RLLib fcnet obs(6) -> tanh 256
+ * -> tanh 256 -> 2 * num_keys + 2 outputs (checkpoint arrays default_policy/fc_1, fc_2, fc_out), then
+ * q1_sample_actions' sampling.  Layer 1 in fp32, layers 2 and 3 on the tensor cores (tcgen05, bf16
+ * operands, fp32 accumulation in TMEM).  Weights are HOST arrays in the checkpoint's (in, out)
+ * layout: w1 (6, 256), w2 (256, 256), w3 (256, 2 * num_keys + 2). */
+typedef struct q1_policy q1_policy; /* opaque */
+int q1_policy_create(int device, int num_keys, const float *w1, const float *b1, const float *w2,
+                     const float *b2, const float *w3, const float *b3, q1_policy **out);
+int q1_policy_destroy(q1_policy *policy);
+/* obs (n, 6) f32, keys (n, num_keys) u8, mouse (n,) f32, logits_out (n, 2 * num_keys + 2) f32 or
+ * NULL: DEVICE arrays.  Other arguments as q1_sample_actions. */
+int q1_policy_act(q1_policy *policy, int64_t n, const float *obs, double action_low,
+                  double action_high, int deterministic, uint64_t seed, uint64_t step,
+                  const uint64_t *step_device, uint64_t env_index_base, uint8_t *keys, float *mouse,
+                  float *logits_out, void *stream);
 
 /* Self-check of the branch-free reciprocal-multiply division sequences the kernels use against the
  * CUDA IEEE intrinsics, on ~`samples` random operand pairs per class (bit comparison):

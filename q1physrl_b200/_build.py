@@ -10,8 +10,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libq1phys.so")
-SOURCES = [os.path.join(_HERE, "csrc", "q1phys.cu")]
-DEPENDS = SOURCES + [os.path.join(_HERE, "csrc", "q1_tick.cuh"),
+SOURCES = [os.path.join(_HERE, "csrc", "q1phys.cu"), os.path.join(_HERE, "csrc", "q1_policy.cu")]
+DEPENDS = SOURCES + [os.path.join(_HERE, "csrc", "q1_tick.cuh"), os.path.join(_HERE, "csrc", "q1_sample.cuh"),
                      os.path.join(REPO_ROOT, "include", "q1phys.h")]
 
 NVCC_FLAGS = [

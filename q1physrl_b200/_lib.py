@@ -114,7 +114,11 @@ SIGNATURES = {
     "q1_delta_speed_sweep_host": (c_int, [c_int, c_i64, c_i64, c_void_p, c_void_p, c_double, c_double,
                                           c_void_p, c_double, c_int] + [c_void_p] * 5),
     "q1_sample_actions": (c_int, [c_int, c_i64, c_int, c_void_p, c_double, c_double, c_int, c_u64, c_u64,
-                                  c_u64, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_u64, c_void_p, c_void_p, c_void_p]),
+    "q1_policy_create": (c_int, [c_int, c_int] + [c_void_p] * 6 + [ctypes.POINTER(c_void_p)]),
+    "q1_policy_destroy": (c_int, [c_void_p]),
+    "q1_policy_act": (c_int, [c_void_p, c_i64, c_void_p, c_double, c_double, c_int, c_u64, c_u64, c_void_p,
+                              c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 8)]),
     "q1_decode_host": (c_int, [ctypes.POINTER(Q1Config), c_int, c_i64] + [c_void_p] * 10),
 }

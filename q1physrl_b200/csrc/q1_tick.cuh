@@ -202,7 +202,7 @@ __device__ __forceinline__ double unit53(uint32_t a, uint32_t b)
  * |r| <= pi/4 (the fdlibm k_sin / k_cos sets), kept in the constant bank so the FP64 pipe reads
  * them as operands instead of building each 64-bit immediate from two moves. */
 /* Other 64-bit constants of the tick, read from the constant bank as well. */
-__constant__ double kTickConst[10] = {
+static __constant__ double kTickConst[10] = {
     3.14159265358979323846,       /* 0: np.pi */
     1.0 / 180.0,                  /* 1 */
     1.0 / 90.0,                   /* 2 */
@@ -213,7 +213,7 @@ __constant__ double kTickConst[10] = {
     1.4973849048591698e-33,       /* 7: -pi/2 low (the third term is negative) */
     1.0e5,                        /* 8: sincos fast-path bound */
     0.0};
-__constant__ double kSinCosCoef[12] = {
+static __constant__ double kSinCosCoef[12] = {
     -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
     2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,

@@ -16,6 +16,7 @@
  */
 #include "../../include/q1phys.h"
 #include "q1_tick.cuh"
+#include "q1_sample.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -840,46 +841,25 @@ k_selftest(uint64_t iters, uint64_t seed, unsigned long long *__restrict__ out)
  * Noise: Philox4x32-10 keyed by `seed`, counter (env index, step). */
 __global__ void __launch_bounds__(256)
 k_sample_actions(int64_t n, int num_keys, const float *__restrict__ logits, float low, float high,
-                 int deterministic, uint64_t seed, uint64_t step, uint64_t env_index_base,
+                 int deterministic, uint64_t seed, uint64_t step,
+                 const uint64_t *__restrict__ step_device, uint64_t env_index_base,
                  uint8_t *__restrict__ keys, float *__restrict__ mouse)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n)
         return;
+    if (step_device)
+        step = *step_device; /* a replayed CUDA graph advances the noise stream through memory */
+    float row[10];
     const int width = 2 * num_keys + 2;
-    const float *row = logits + i * width;
-    uint32_t w[8];
-    const uint64_t g = env_index_base + (uint64_t)i;
-    if (!deterministic) {
-        philox4x32((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x504F4C00u,
-                   (uint32_t)seed, (uint32_t)(seed >> 32), w);
-        philox4x32((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x504F4C01u,
-                   (uint32_t)seed, (uint32_t)(seed >> 32), w + 4);
-    }
-    for (int k = 0; k < num_keys; k++) {
-        const float l0 = row[2 * k], l1 = row[2 * k + 1];
-        uint8_t key;
-        if (deterministic) {
-            key = l1 > l0;
-        } else {
-            const float p1 = 1.0f / (1.0f + expf(l0 - l1));               /* softmax over two logits */
-            const float u = ((float)(w[k] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            key = u < p1;
-        }
-        keys[i * num_keys + k] = key;
-    }
-    float raw = fminf(fmaxf(row[2 * num_keys], -3.0f), 3.0f);             /* clipped mean */
-    if (!deterministic) {
-        const float log_std = fminf(fmaxf(row[2 * num_keys + 1], -20.0f), 2.0f);
-        const float u1 = ((float)(w[4] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float u2 = ((float)(w[5] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float eps = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);     /* Box-Muller */
-        raw = raw + expf(log_std) * eps;
-    }
-    const float scale = 0.5f * 1.8137f;
-    float cdf = 0.5f * erfcf(-(raw / scale) * 0.70710678118654752440f);   /* NormalCDF */
-    cdf = fminf(fmaxf(cdf, 1e-6f), 1.0f - 1e-6f);
-    mouse[i] = cdf * (high - low) + low;
+    for (int k = 0; k < width; k++)
+        row[k] = logits[i * width + k];
+    float m;
+    const uint32_t kb = sample_action_row(row, num_keys, low, high, deterministic != 0, seed, step,
+                                          env_index_base + (uint64_t)i, &m);
+    for (int k = 0; k < num_keys; k++)
+        keys[i * num_keys + k] = (kb >> k) & 1u;
+    mouse[i] = m;
 }
 
 } // namespace
@@ -893,6 +873,9 @@ static int fail(int code, const std::string &msg)
     g_error = msg;
     return code;
 }
+
+/* the other translation units of the library report errors through the same thread-local slot */
+int q1_set_error(int code, const std::string &msg) { return fail(code, msg); }
 
 #define Q1_CUDA(call)                                                                             \
     do {                                                                                          \
@@ -1976,7 +1959,8 @@ int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t m
 
 int q1_sample_actions(int device, int64_t n, int num_keys, const float *logits, double action_low,
                       double action_high, int deterministic, uint64_t seed, uint64_t step,
-                      uint64_t env_index_base, uint8_t *keys, float *mouse, void *stream)
+                      const uint64_t *step_device, uint64_t env_index_base, uint8_t *keys,
+                      float *mouse, void *stream)
 {
     if (n < 0 || (num_keys != 3 && num_keys != 4))
         return fail(Q1_EINVAL, "n must be >= 0 and num_keys 3 or 4");
@@ -1989,7 +1973,7 @@ int q1_sample_actions(int device, int64_t n, int num_keys, const float *logits, 
         return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
     k_sample_actions<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         n, num_keys, logits, (float)action_low, (float)action_high, deterministic, seed, step,
-        env_index_base, keys, mouse);
+        step_device, env_index_base, keys, mouse);
     return check_launch("k_sample_actions");
 }
 

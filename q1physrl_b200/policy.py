@@ -25,6 +25,7 @@ class MLPPolicy:
         self.low, self.high = -float(action_range), float(action_range)
         self.seed = int(seed)
         self.step_count = 0
+        self._step_dev = None  # device-side step counter, used while a CUDA graph is replayed
         t = lambda a, dt: torch.as_tensor(np.asarray(a, np.float32)).to(self.device, dt).contiguous()
         self.w1, self.b1 = t(weights["fc_1_kernel"], self.dtype), t(weights["fc_1_bias"], self.dtype)
         self.w2, self.b2 = t(weights["fc_2_kernel"], self.dtype), t(weights["fc_2_bias"], self.dtype)
@@ -33,6 +34,7 @@ class MLPPolicy:
 
     @classmethod
     def from_npz(cls, path, **kwargs):
+        """-> (policy, env_config dict stored beside the weights)."""
         with np.load(path) as z:
             weights = {k: z[k] for k in z.files if k.startswith("fc_")}
             cfg = json.loads(str(z["env_config"])) if "env_config" in z.files else {}
@@ -59,10 +61,13 @@ class MLPPolicy:
                    torch.empty(n, dtype=torch.float32, device=self.device))
         keys, mouse = out
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        step_ptr = ctypes.c_void_p(self._step_dev.data_ptr()) if self._step_dev is not None else None
         _lib.check(_lib.load().q1_sample_actions(
             self.device.index, n, self.num_keys, ctypes.c_void_p(lg.data_ptr()), self.low, self.high,
-            int(bool(deterministic)), self.seed, self.step_count, int(env_index_base),
+            int(bool(deterministic)), self.seed, self.step_count, step_ptr, int(env_index_base),
             ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(mouse.data_ptr()), stream))
+        if self._step_dev is not None:
+            self._step_dev += 1
         self.step_count += 1
         return keys, mouse
 
@@ -76,18 +81,106 @@ class MLPPolicy:
         return tuple(int(x) for x in k) + (mouse.cpu().numpy().astype(np.float32),)
 
 
-def rollout(env, policy, ticks, deterministic=False):
+class FusedMLPPolicy(MLPPolicy):
+    """The same policy as ONE sm_100a kernel (`k_policy_act`, q1_policy.cu): layer 1 in fp32 on the
+    CUDA cores, layers 2 and 3 on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators in
+    TMEM), tanh / bias / sampling in the epilogues; the hidden activations never leave the SM."""
+
+    def __init__(self, weights, num_keys=4, action_range=10.0, device=0, seed=0):
+        super().__init__(weights, num_keys=num_keys, action_range=action_range, device=device, seed=seed)
+        f32 = lambda k: np.ascontiguousarray(weights[k], dtype=np.float32)
+        arrs = [f32(k) for k in ("fc_1_kernel", "fc_1_bias", "fc_2_kernel", "fc_2_bias",
+                                 "fc_out_kernel", "fc_out_bias")]
+        assert arrs[0].shape == (6, 256) and arrs[2].shape == (256, 256)
+        self._handle = ctypes.c_void_p()
+        _lib.check(_lib.load().q1_policy_create(
+            int(device), self.num_keys, *[ctypes.c_void_p(a.ctypes.data) for a in arrs],
+            ctypes.byref(self._handle)))
+
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            _lib.load().q1_policy_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the library module may already be gone
+            pass
+
+    def _launch(self, obs, deterministic, env_index_base, out, logits_out):
+        torch = self._torch
+        obs = obs.to(torch.float32).contiguous()
+        n = obs.shape[0]
+        if out is None:
+            out = (torch.empty((n, self.num_keys), dtype=torch.uint8, device=self.device),
+                   torch.empty(n, dtype=torch.float32, device=self.device))
+        keys, mouse = out
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        step_ptr = ctypes.c_void_p(self._step_dev.data_ptr()) if self._step_dev is not None else None
+        _lib.check(_lib.load().q1_policy_act(
+            self._handle, n, ctypes.c_void_p(obs.data_ptr()), self.low, self.high,
+            int(bool(deterministic)), self.seed, self.step_count, step_ptr, int(env_index_base),
+            ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(mouse.data_ptr()),
+            ctypes.c_void_p(logits_out.data_ptr()) if logits_out is not None else None, stream))
+        return out
+
+    def logits(self, obs):
+        torch = self._torch
+        lg = torch.empty((obs.shape[0], 2 * self.num_keys + 2), dtype=torch.float32, device=self.device)
+        self._launch(obs, True, 0, None, lg)
+        return lg
+
+    def act(self, obs, deterministic=False, env_index_base=0, out=None):
+        out = self._launch(obs, deterministic, env_index_base, out, None)
+        if self._step_dev is not None:
+            self._step_dev += 1
+        self.step_count += 1
+        return out
+
+
+def rollout(env, policy, ticks, deterministic=False, graph=True):
     """Closed loop on the device: policy -> `step_tensors` (fused auto-reset) for `ticks` ticks.
     Returns the last (obs, reward, done, zero_start) tensors; with `track_returns` the episode
-    statistics accumulate in `env.metrics()`."""
+    statistics accumulate in `env.metrics()`.
+
+    graph=True captures one tick (three GEMMs, sampling, the step kernel) in a CUDA graph and
+    replays it: the loop is launch-bound otherwise.  The sampling noise advances through a device
+    counter, so replays draw fresh actions."""
     torch = policy._torch
-    obs = torch.as_tensor(env._get_obs()).to(policy.device)
+    ticks = int(ticks)
+    dev = policy.device
     base = env.info.env_index_base
-    act_buf = step_buf = None
-    out = None
-    for _ in range(int(ticks)):
-        act_buf = policy.act(obs, deterministic=deterministic, env_index_base=base, out=act_buf)
-        out = env.step_tensors(act_buf[0], act_buf[1], auto_reset=True, out=step_buf)
-        step_buf = out
-        obs = out[0]
-    return out
+    obs = torch.as_tensor(env._get_obs()).to(dev)
+    n = obs.shape[0]
+    act_buf = (torch.empty((n, policy.num_keys), dtype=torch.uint8, device=dev),
+               torch.empty(n, dtype=torch.float32, device=dev))
+    step_buf = (obs, torch.empty(n, dtype=torch.float32, device=dev),
+                torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+
+    def tick():
+        policy.act(step_buf[0], deterministic=deterministic, env_index_base=base, out=act_buf)
+        env.step_tensors(act_buf[0], act_buf[1], auto_reset=True, out=step_buf)
+
+    if not graph or ticks < 8:
+        for _ in range(ticks):
+            tick()
+        return step_buf
+    policy._step_dev = torch.full((1,), policy.step_count, dtype=torch.int64, device=dev)
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):          # warm up allocators / cuBLAS workspaces outside the capture
+                tick()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            tick()
+        for _ in range(ticks - 4):
+            g.replay()
+        torch.cuda.current_stream(dev).synchronize()
+    finally:
+        policy.step_count = int(policy._step_dev.item())
+        policy._step_dev = None
+    return step_buf

@@ -175,3 +175,42 @@ def test_shipped_policy_closed_loop():
     print("stochastic policy:", m)
     assert m["zero_start_episodes"] == n
     assert 5600 < m["zero_start_total_reward_mean"] < 5800
+
+
+def test_fused_tcgen05_policy_kernel():
+    """k_policy_act (layers 2 and 3 on tcgen05 tensor cores, bf16 operands) against the fp32 library
+    path: logits within bf16 tolerance, identical decisions wherever the fp32 margin is clear, and the
+    same closed-loop metric."""
+    import os
+    import torch
+    from q1physrl_b200 import env as benv, policy as bpolicy
+    path = os.path.join(harness.GOLDEN_DIR, "wr_policy.npz")
+    ref, env_config = bpolicy.MLPPolicy.from_npz(path, seed=1)
+    fused, _ = bpolicy.FusedMLPPolicy.from_npz(path, seed=1)
+    g = np.load(path)
+    rng = np.random.default_rng(0)
+    for obs in (g["det_obs"], rng.uniform(-1, 5, (100000 + 77, 6)).astype(np.float32)):
+        o = torch.as_tensor(obs).cuda()
+        a, b = ref.logits(o).cpu().numpy(), fused.logits(o).cpu().numpy()
+        assert b.shape == a.shape
+        assert np.abs(a - b).max() < 0.15 and np.abs(a - b).mean() < 0.02, (np.abs(a - b).max(),)
+        ka, ma = ref.act(o, deterministic=True)
+        kb, mb = fused.act(o, deterministic=True)
+        ka, kb = ka.cpu().numpy(), kb.cpu().numpy()
+        margin = np.abs(a[:, 1:8:2] - a[:, 0:8:2])            # |logit1 - logit0| per key
+        clear = margin > 0.3
+        assert np.array_equal(ka[clear], kb[clear])
+        assert np.abs(ma.cpu().numpy() - mb.cpu().numpy()).max() < 0.25   # of a +-10 range
+    # same noise stream in both: stochastic actions agree except near decision boundaries
+    o = torch.as_tensor(g["det_obs"]).cuda()
+    ref.step_count = fused.step_count = 5
+    ka, _ = ref.act(o)
+    kb, _ = fused.act(o)
+    assert (ka != kb).float().mean().item() < 0.02
+    cfg = dict(env_config, initial_yaw_range=tuple(env_config["initial_yaw_range"]), num_envs=8192,
+               zero_start_prob=1.0)
+    e = benv.VectorPhysEnv(cfg, seed=2, track_returns=True)
+    bpolicy.rollout(e, fused, 721)
+    m = e.metrics()
+    print("fused policy:", m["zero_start_total_reward_mean"], m["zero_start_episodes"])
+    assert m["zero_start_episodes"] == 8192 and 5600 < m["zero_start_total_reward_mean"] < 5800
