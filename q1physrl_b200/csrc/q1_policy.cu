@@ -5,18 +5,23 @@
  * q1physrl/action_dist.py.
  *
  * This is the one dense contraction near the path, so it is the one place the 5th-generation
- * tensor cores are used.  Per CTA (one per SM, persistent over tiles of 128 envs):
+ * tensor cores are used.  Per CTA (one per SM, 512 threads = 128 rows x 4 column groups, persistent
+ * over tiles of 128 envs); the hidden activations live in TENSOR MEMORY only:
  *   layer 1 (K = 6)    fp32 on the CUDA cores from the fp32 observation (bf16 would quantise yaw /
- *                      90 to ~3 degrees), tanh.approx, packed to bf16 into the A operand in shared
- *                      memory (K-major, 128-byte swizzle)
- *   layer 2 (256x256)  16 x tcgen05.mma (M = 128, N = 256, K = 16, bf16 -> fp32 accumulator in TMEM),
- *                      issued by one thread, completion through tcgen05.commit on an mbarrier
- *   epilogue 2         tcgen05.ld 32 columns at a time -> + bias -> tanh.approx -> bf16 -> back into
- *                      the A operand buffer
- *   layer 3 (256x10)   16 x tcgen05.mma with N = 16 (weights zero-padded)
- *   epilogue 3         tcgen05.ld the 16 logit columns -> + bias -> sample_action_row -> keys / mouse
- * The weights (128 KB of bf16 W2^T pre-swizzled into the UMMA layout on the host, 8 KB W3^T, fp32 W1
- * and biases) are copied into shared memory once per CTA with cp.async.bulk.
+ *                      90 to ~3 degrees), tanh.approx.bf16x2, tcgen05.st into TMEM as the A operand
+ *   layer 2 (256x256)  16 x tcgen05.mma (M = 128, N = 256, K = 16; A from TMEM, B = W2^T from shared
+ *                      memory, fp32 accumulator in TMEM), issued by one thread, completion through
+ *                      tcgen05.commit on an mbarrier.  It runs while the CUDA cores compute layer 1
+ *                      of the NEXT tile into the other activation buffer.
+ *   epilogue 2         tcgen05.ld 32 columns at a time -> + bias -> tanh -> bf16 -> tcgen05.st over
+ *                      the consumed layer-1 activations
+ *   layer 3 (256x10)   16 x tcgen05.mma with N = 16 (weights zero-padded), accumulator over the
+ *                      consumed layer-2 columns
+ *   epilogue 3         tcgen05.ld the logit columns -> + bias -> sample_action_row -> keys / mouse
+ * TMEM budget (512 columns): two activation buffers of 128 columns (256 bf16 per lane) + 256
+ * accumulator columns.  The weights (128 KB of bf16 W2^T pre-swizzled into the UMMA shared-memory
+ * layout on the host, 8 KB W3^T, fp32 W1 and biases) are copied into shared memory once per CTA
+ * with cp.async.bulk.
  */
 #include "../../include/q1phys.h"
 #include "q1_sample.cuh"
@@ -38,10 +43,11 @@ constexpr int kRows = 128;   /* envs per tile = UMMA M */
 constexpr int kHidden = 256; /* hidden width = K of layers 2 and 3, N of layer 2 */
 constexpr int kOutPad = 16;  /* layer-3 N, zero-padded from 2 * num_keys + 2 = 8 or 10 */
 constexpr int kObs = 6;
+constexpr int kGroups = 4;   /* column groups: thread = (row, group); 4 warps per scheduler hide latency */
+constexpr int kThreads = kRows * kGroups;
 
 /* shared-memory image; every UMMA operand block is 1024-byte aligned (128-byte swizzle atoms) */
-constexpr uint32_t SM_A = 0;                                   /* 4 K-atoms x 128 rows x 128 B */
-constexpr uint32_t SM_B2 = SM_A + 4 * kRows * 128;             /* 4 K-atoms x 256 rows x 128 B */
+constexpr uint32_t SM_B2 = 0;                                  /* 4 K-atoms x 256 rows x 128 B */
 constexpr uint32_t SM_B3 = SM_B2 + 4 * kHidden * 128;          /* 4 K-atoms x 16 rows x 128 B */
 constexpr uint32_t SM_W1 = SM_B3 + 4 * kOutPad * 128;          /* fp32 [6][256] */
 constexpr uint32_t SM_B1 = SM_W1 + kObs * kHidden * 4;         /* fp32 [256] */
@@ -53,6 +59,9 @@ constexpr uint32_t SM_TMEM = SM_BAR + 32;                      /* TMEM base addr
 constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
 constexpr uint32_t kImageBytes = SM_WEIGHTS_END - SM_B2;        /* what the host image holds */
 static_assert(kImageBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+/* tensor-memory columns (32-bit): two activation buffers (256 bf16 per lane each), accumulators */
+constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_D = 256;
 
 /* instruction descriptor of tcgen05.mma kind::f16: D = f32, A = B = bf16, both K-major, M = 128 */
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t n)
@@ -75,15 +84,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
 
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         bool accumulate)
+/* A operand from tensor memory (lane = row, 16-bit elements packed two per column along K) */
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            bool accumulate)
 {
     asm volatile("{\n\t"
                  ".reg .pred p;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
                  "}\n" ::"r"(tmem_d),
-                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+                 "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
                  : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar)
@@ -105,17 +115,40 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
                  "}" ::"r"(bar), "r"(parity)
                  : "memory");
 }
-__device__ __forceinline__ float tanh_fast(float x)
-{
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+/* tanh of two pre-activations -> packed bf16x2.  Q1_POLICY_TANH_BF16X2 rounds the inputs to bf16
+ * first and spends one MUFU on the pair (faster, ~3x the logit error); the default keeps fp32
+ * inputs (tanh.approx.f32, relative error 2^-11) and rounds only the results. */
+#ifndef Q1_POLICY_TANH_BF16X2
+#define Q1_POLICY_TANH_BF16X2 0
+#endif
+__device__ __forceinline__ uint32_t tanh2_bf16(float lo, float hi)
+{
+#if Q1_POLICY_TANH_BF16X2
+    uint32_t x = pack_bf16(lo, hi), y;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+#else
+    float a, b;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(lo));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(hi));
+    return pack_bf16(a, b);
+#endif
+}
+/* 16 consecutive 32-bit columns of this thread's TMEM lane */
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 /* 32 consecutive fp32 accumulator columns of this thread's TMEM lane */
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32])
 {
@@ -141,14 +174,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-/* byte offset of the 16-byte chunk holding K elements [8c, 8c + 8) of row `row` inside an operand
- * whose K-atoms (64 elements = 128 B per row) are `atom_bytes` apart */
-__device__ __forceinline__ uint32_t chunk_offset(uint32_t row, uint32_t c, uint32_t atom_bytes)
-{
-    return (c >> 3) * atom_bytes + row * 128u + (((c & 7u) ^ (row & 7u)) << 4);
-}
-
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 k_policy_act(const unsigned char *__restrict__ image, int64_t n, int num_keys,
              const float *__restrict__ obs, float low, float high, int deterministic, uint64_t seed,
              uint64_t step, const uint64_t *__restrict__ step_device, uint64_t env_index_base,
@@ -156,6 +182,7 @@ k_policy_act(const unsigned char *__restrict__ image, int64_t n, int num_keys,
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t row = tid % kRows, group = tid / kRows; /* warp % 4 == row / 32: its TMEM lanes */
     const uint32_t s0 = saddr_of(smem);
     const uint32_t bar_w = s0 + SM_BAR, bar_l2 = s0 + SM_BAR + 8, bar_l3 = s0 + SM_BAR + 16;
     const int width = 2 * num_keys + 2;
@@ -187,7 +214,7 @@ k_policy_act(const unsigned char *__restrict__ image, int64_t n, int num_keys,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + SM_TMEM);
-    const uint32_t tmem_lane = tmem + ((warp * 32u) << 16); /* this warp's 32 TMEM lanes */
+    const uint32_t tmem_lane = tmem + (((warp & 3u) * 32u) << 16); /* this warp's 32 TMEM lanes */
     bar_wait(bar_w, 0);
 
     const float4 *w1 = reinterpret_cast<const float4 *>(smem + SM_W1);
@@ -195,110 +222,114 @@ k_policy_act(const unsigned char *__restrict__ image, int64_t n, int num_keys,
     const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2);
     const float *bias3 = reinterpret_cast<const float *>(smem + SM_BIAS3);
     const int64_t tiles = (n + kRows - 1) / kRows;
-    uint32_t parity = 0;
+    constexpr uint32_t kUnits = kHidden / kGroups;          /* hidden units per thread: 64 */
 
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t i = tile * kRows + tid;
-        const bool active = i < n;
-        /* ---- layer 1: fp32 on the CUDA cores, 4 hidden units at a time ---- */
+    /* layer 1 of one tile: this thread's 64 hidden units of its row -> 32 TMEM columns of buffer h */
+    auto layer1 = [&](int64_t tile, uint32_t tm_h) {
+        const int64_t i = tile * kRows + row;
         float o[kObs];
 #pragma unroll
         for (int k = 0; k < kObs; k++)
-            o[k] = active ? __ldg(obs + i * kObs + k) : 0.0f;
-#pragma unroll 4
-        for (uint32_t c = 0; c < kHidden / 8; c++) { /* one 16-byte chunk = 8 hidden units */
-            uint32_t packed[4];
+            o[k] = i < n ? __ldg(obs + i * kObs + k) : 0.0f;
 #pragma unroll
-            for (uint32_t half = 0; half < 2; half++) {
-                const uint32_t g = 2 * c + half; /* group of 4 units */
-                float4 acc = b1[g];
+        for (uint32_t half = 0; half < 2; half++) {
+            uint32_t cols[16];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) {              /* 4 units -> 2 packed columns */
+                const uint32_t g4 = (group * kUnits + half * 32u + q * 4u) / 4u;
+                float4 acc = b1[g4];
 #pragma unroll
                 for (int k = 0; k < kObs; k++) {
-                    const float4 w = w1[k * (kHidden / 4) + g];
+                    const float4 w = w1[k * (kHidden / 4) + g4];
                     acc.x = fmaf(o[k], w.x, acc.x);
                     acc.y = fmaf(o[k], w.y, acc.y);
                     acc.z = fmaf(o[k], w.z, acc.z);
                     acc.w = fmaf(o[k], w.w, acc.w);
                 }
-                packed[2 * half] = pack_bf16(tanh_fast(acc.x), tanh_fast(acc.y));
-                packed[2 * half + 1] = pack_bf16(tanh_fast(acc.z), tanh_fast(acc.w));
+                cols[2 * q] = tanh2_bf16(acc.x, acc.y);
+                cols[2 * q + 1] = tanh2_bf16(acc.z, acc.w);
             }
-            *reinterpret_cast<uint4 *>(smem + SM_A + chunk_offset(tid, c, kRows * 128u)) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            tmem_st16(tmem_lane + tm_h + group * (kUnits / 2) + half * 16u, cols);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> UMMA reads */
-        tc_fence_before();
-        __syncthreads();
-        /* ---- layer 2: D[128 x 256] = A[128 x 256] . W2 ---- */
+        tmem_st_wait();
+    };
+
+    uint32_t parity = 0, hb = 0;
+    if ((int64_t)blockIdx.x < tiles)
+        layer1(blockIdx.x, TM_H0);
+    tc_fence_before();
+    __syncthreads();
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t tm_h = hb ? TM_H1 : TM_H0, tm_hn = hb ? TM_H0 : TM_H1;
+        const int64_t i = tile * kRows + row;
+        const bool active = i < n;
+        /* ---- layer 2: D[128 x 256] = H1[128 x 256] . W2, A from tensor memory ---- */
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (uint32_t k = 0; k < kHidden / 16; k++) {
-                const uint64_t da = smem_desc(s0 + SM_A + (k >> 2) * (kRows * 128u) + (k & 3u) * 32u);
                 const uint64_t db = smem_desc(s0 + SM_B2 + (k >> 2) * (kHidden * 128u) + (k & 3u) * 32u);
-                mma_bf16(tmem, da, db, instr_desc(kHidden), k > 0);
+                mma_bf16_ts(tmem + TM_D, tmem + tm_h + k * 8u, db, instr_desc(kHidden), k > 0);
             }
             mma_commit(bar_l2);
         }
+        /* ---- meanwhile: layer 1 of the next tile into the other activation buffer ---- */
+        if (tile + gridDim.x < tiles)
+            layer1(tile + gridDim.x, tm_hn);
         bar_wait(bar_l2, parity);
         tc_fence_after();
-        /* ---- epilogue 2: + bias, tanh, bf16, back into the A operand ---- */
+        /* ---- epilogue 2: + bias, tanh, bf16, over the consumed layer-1 activations ---- */
 #pragma unroll 1
-        for (uint32_t c32 = 0; c32 < kHidden / 32; c32++) {
-            uint32_t v[32];
-            tmem_ld32(tmem_lane + c32 * 32u, v);
+        for (uint32_t c32 = group * (kHidden / 32 / kGroups); c32 < (group + 1) * (kHidden / 32 / kGroups); c32++) {
+            uint32_t v[32], cols[16];
+            tmem_ld32(tmem_lane + TM_D + c32 * 32u, v);
 #pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                uint32_t packed[4];
-#pragma unroll
-                for (uint32_t e = 0; e < 4; e++) {
-                    const uint32_t col = c32 * 32u + q * 8u + 2u * e;
-                    const float x0 = __uint_as_float(v[q * 8u + 2u * e]) + bias2[col];
-                    const float x1 = __uint_as_float(v[q * 8u + 2u * e + 1u]) + bias2[col + 1u];
-                    packed[e] = pack_bf16(tanh_fast(x0), tanh_fast(x1));
-                }
-                *reinterpret_cast<uint4 *>(smem + SM_A + chunk_offset(tid, c32 * 4u + q, kRows * 128u)) =
-                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            for (uint32_t e = 0; e < 16; e++) {
+                const uint32_t col = c32 * 32u + 2u * e;
+                cols[e] = tanh2_bf16(__uint_as_float(v[2 * e]) + bias2[col],
+                                     __uint_as_float(v[2 * e + 1]) + bias2[col + 1u]);
             }
+            tmem_st16(tmem_lane + tm_h + c32 * 16u, cols);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tmem_st_wait();
         tc_fence_before();
         __syncthreads();
-        /* ---- layer 3: D3[128 x 16] = H2[128 x 256] . W3 (padded) ---- */
+        /* ---- layer 3: D3[128 x 16] = H2[128 x 256] . W3 (padded), over the consumed columns of D ---- */
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (uint32_t k = 0; k < kHidden / 16; k++) {
-                const uint64_t da = smem_desc(s0 + SM_A + (k >> 2) * (kRows * 128u) + (k & 3u) * 32u);
                 const uint64_t db = smem_desc(s0 + SM_B3 + (k >> 2) * (kOutPad * 128u) + (k & 3u) * 32u);
-                mma_bf16(tmem + kHidden, da, db, instr_desc(kOutPad), k > 0);
+                mma_bf16_ts(tmem + TM_D, tmem + tm_h + k * 8u, db, instr_desc(kOutPad), k > 0);
             }
             mma_commit(bar_l3);
         }
         bar_wait(bar_l3, parity);
         tc_fence_after();
-        /* ---- epilogue 3: logits -> sampled action ---- */
-        {
+        /* ---- epilogue 3: logits -> sampled action (one thread per row) ---- */
+        if (group == 0) {
             uint32_t v[16];
-            tmem_ld16(tmem_lane + kHidden, v);
-            float row[10];
+            tmem_ld16(tmem_lane + TM_D, v);
+            float lg[10];
 #pragma unroll
             for (int k = 0; k < 10; k++)
-                row[k] = __uint_as_float(v[k]) + bias3[k];
+                lg[k] = __uint_as_float(v[k]) + bias3[k];
             if (active) {
                 float m;
-                const uint32_t kb = sample_action_row(row, num_keys, low, high, deterministic != 0, seed,
+                const uint32_t kb = sample_action_row(lg, num_keys, low, high, deterministic != 0, seed,
                                                       step, env_index_base + (uint64_t)i, &m);
                 for (int k = 0; k < num_keys; k++)
                     keys[i * num_keys + k] = (kb >> k) & 1u;
                 mouse[i] = m;
                 if (logits_out)
                     for (int k = 0; k < width; k++)
-                        logits_out[i * width + k] = row[k];
+                        logits_out[i * width + k] = lg[k];
             }
         }
-        tc_fence_before(); /* the next tile's MMAs overwrite the accumulators every warp just read */
+        tc_fence_before(); /* the next tile's MMAs overwrite the accumulators group 0 just read */
+        __syncthreads();
         parity ^= 1u;
+        hb ^= 1u;
     }
     __syncthreads();
     if (warp == 0)
@@ -412,7 +443,7 @@ int q1_policy_act(q1_policy *p, int64_t n, const float *obs, double action_low, 
         return q1_set_error(Q1_ECUDA, "cudaSetDevice failed");
     const int64_t tiles = (n + kRows - 1) / kRows;
     const unsigned grid = (unsigned)(tiles < p->sm_count ? tiles : p->sm_count);
-    k_policy_act<<<grid, kRows, SM_TOTAL, static_cast<cudaStream_t>(stream)>>>(
+    k_policy_act<<<grid, kThreads, SM_TOTAL, static_cast<cudaStream_t>(stream)>>>(
         p->image, n, p->num_keys, obs, (float)action_low, (float)action_high, deterministic, seed, step,
         step_device, env_index_base, keys, mouse, logits_out);
     cudaError_t err = cudaGetLastError();
