@@ -279,7 +279,7 @@ def run_cuda_arm(args, rank, world, local_rank):
     policy_path = os.path.join(ROOT, "tests", "golden", "wr_policy.npz")
     n5, ticks5 = 1 << 15, 1500
     if os.path.exists(policy_path):
-        pol, env_cfg = bpolicy.MLPPolicy.from_npz(policy_path, device=local_rank, seed=args.seed)
+        pol, env_cfg = bpolicy.FusedMLPPolicy.from_npz(policy_path, device=local_rank, seed=args.seed)
         cfg5 = dict(env_cfg, initial_yaw_range=tuple(env_cfg["initial_yaw_range"]), num_envs=n5)
         tracked = benv.VectorPhysEnv(cfg5, device=local_rank, seed=args.seed,
                                      env_index_base=rank * n5, track_returns=True)
@@ -289,8 +289,9 @@ def run_cuda_arm(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
         t5 = time.perf_counter() - t5
         policy_desc = (f"reference checkpoint data/checkpoints/wr (stochastic Q1PhysActionDist), params.json "
-                       f"env_config, {n5} envs/GPU x {ticks5} ticks closed loop on the device, "
-                       f"{world * n5 * ticks5 / t5:.3e} env-steps/s incl. the policy MLP")
+                       f"env_config, {n5} envs/GPU x {ticks5} ticks closed loop on the device (fused tcgen05 "
+                       f"policy kernel + step kernel in a CUDA graph), "
+                       f"{world * n5 * ticks5 / t5:.3e} env-steps/s incl. the policy")
     else:
         tracked = benv.VectorPhysEnv(workload_config(n5), device=local_rank, seed=args.seed,
                                      env_index_base=rank * n5, track_returns=True)
@@ -298,6 +299,23 @@ def run_cuda_arm(args, rank, world, local_rank):
         policy_desc = f"scripted strafe_jump, 722 ticks, {n5} envs/GPU"
     red = sharding.reduce_metrics(tracked.metrics(), device=dev)
     zs_mean, zs_episodes = red["zero_start_total_reward_mean"], red["zero_start_episodes"]
+
+    # ---- BASELINE config 4: 2^20 envs sharded 131072 per GPU, scripted strafe-jump policy, 10k ticks
+    # in the multi-tick in-register rollout kernel (no per-tick HBM traffic)
+    n4, ticks4 = 1 << 17, 10000
+    e4 = benv.VectorPhysEnv(dict(CONFIG_100M, num_envs=n4, zero_start_prob=1.0), device=local_rank,
+                            seed=args.seed, env_index_base=rank * n4)
+    e4.rollout("strafe_jump", 100)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    e4.rollout("strafe_jump", ticks4)
+    r1.record(stream)
+    barrier()
+    t4 = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+    rollout_value = world * n4 * ticks4 / (float(t4.item()) * 1e-3)
 
     if rank == 0:
         info = envs[0].info
@@ -324,6 +342,9 @@ def run_cuda_arm(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "kernel": "k_step_tma",
                          "bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src},
             "clocks": clocks.summary(),
+            "config4_rollout": {"value": rollout_value, "unit": UNIT, "envs_per_gpu": n4, "ticks": ticks4,
+                                "policy": "scripted strafe_jump generated on the device",
+                                "kernel": "k_rollout: one launch, state in registers for all ticks"},
             "zero_start_total_reward_mean": {"value": zs_mean, "episodes": zs_episodes,
                                              "policy": policy_desc,
                                              "collective": "all_reduce(sum) of (sum, count)" if world > 1 else "none (1 GPU)"},

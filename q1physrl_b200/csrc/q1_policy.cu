@@ -227,10 +227,18 @@ k_policy_act(const unsigned char *__restrict__ image, int64_t n, int num_keys,
     /* layer 1 of one tile: this thread's 64 hidden units of its row -> 32 TMEM columns of buffer h */
     auto layer1 = [&](int64_t tile, uint32_t tm_h) {
         const int64_t i = tile * kRows + row;
-        float o[kObs];
+        float o[kObs] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (i < n) {
+            if ((reinterpret_cast<uintptr_t>(obs) & 7u) == 0) {
+                const float2 *p2 = reinterpret_cast<const float2 *>(obs + i * kObs);
+                const float2 a = __ldg(p2), b = __ldg(p2 + 1), c = __ldg(p2 + 2);
+                o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y;
+            } else {
 #pragma unroll
-        for (int k = 0; k < kObs; k++)
-            o[k] = i < n ? __ldg(obs + i * kObs + k) : 0.0f;
+                for (int k = 0; k < kObs; k++)
+                    o[k] = __ldg(obs + i * kObs + k);
+            }
+        }
 #pragma unroll
         for (uint32_t half = 0; half < 2; half++) {
             uint32_t cols[16];

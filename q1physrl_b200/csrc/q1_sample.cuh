@@ -18,13 +18,11 @@ __device__ __forceinline__ uint32_t sample_action_row(const float *row, int num_
                                                       float high, bool deterministic, uint64_t seed,
                                                       uint64_t step, uint64_t gidx, float *mouse)
 {
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (!deterministic) {
+    /* one Philox block per (env, step): 16 bits per key draw, 2 x 32 bits for the Gaussian */
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (!deterministic)
         philox4x32((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step,
                    (uint32_t)(step >> 32) ^ 0x504F4C00u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-        philox4x32((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step,
-                   (uint32_t)(step >> 32) ^ 0x504F4C01u, (uint32_t)seed, (uint32_t)(seed >> 32), w + 4);
-    }
     uint32_t keybits = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -34,8 +32,9 @@ __device__ __forceinline__ uint32_t sample_action_row(const float *row, int num_
             if (deterministic) {
                 key = l1 > l0;
             } else {
-                const float p1 = 1.0f / (1.0f + expf(l0 - l1));           /* softmax over two logits */
-                const float u = ((float)(w[k] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float p1 = __fdividef(1.0f, 1.0f + __expf(l0 - l1));  /* softmax over two logits */
+                const uint32_t bits = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                const float u = ((float)bits + 0.5f) * (1.0f / 65536.0f);
                 key = u < p1;
             }
             keybits |= (key ? 1u : 0u) << k;
@@ -44,10 +43,10 @@ __device__ __forceinline__ uint32_t sample_action_row(const float *row, int num_
     float raw = fminf(fmaxf(row[2 * num_keys], -3.0f), 3.0f);             /* clipped mean */
     if (!deterministic) {
         const float log_std = fminf(fmaxf(row[2 * num_keys + 1], -20.0f), 2.0f);
-        const float u1 = ((float)(w[4] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float u2 = ((float)(w[5] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float eps = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);     /* Box-Muller */
-        raw = raw + expf(log_std) * eps;
+        const float u1 = ((float)(w[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((float)(w[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float eps = sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2); /* Box-Muller */
+        raw = raw + __expf(log_std) * eps;
     }
     const float scale = 0.5f * 1.8137f;
     float cdf = 0.5f * erfcf(-(raw / scale) * 0.70710678118654752440f);   /* NormalCDF */
