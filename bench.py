@@ -105,7 +105,7 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_envs = 1 << 17
+    sample_envs = 1 << 18
     from oracle import q1_oracle as qo
     qo.build()
     cpu_port_throughput(sample_envs, max(1, args.warmup), threads)
