@@ -263,6 +263,11 @@ int q1_policy_act(q1_policy *policy, int64_t n, const float *obs, double action_
  * Every count must be 0. */
 int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[8]);
 
+/* sin and cos of n HOST doubles (radians) as the kernels compute them: glibc 2.39's __sin / __cos
+ * (sysdeps/ieee754/dbl-64/s_sin.c, FMA build) restated on the device, i.e. the bits np.sin /
+ * np.cos return in the reference (phys.py:58-59, env.py:475-476).  For parity tests. */
+int q1_sincos_host(int device, int64_t n, const double *x, double *sin_out, double *cos_out);
+
 #ifdef __cplusplus
 }
 #endif

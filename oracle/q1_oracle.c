@@ -424,3 +424,13 @@ void q1o_reset_philox(const q1o_config *cfg, q1o_state *st, int64_t n, uint64_t 
         q1o_reset_env(cfg, st, i, u);
     }
 }
+
+/* np.sin / np.cos on float64 (phys.py:58-59): NumPy forwards to the C library.  Checker for the
+ * device build of q1_libm_sincos.cuh. */
+void q1o_sincos(int64_t n, const double *x, double *s, double *c)
+{
+    for (int64_t i = 0; i < n; i++) {
+        s[i] = sin(x[i]);
+        c[i] = cos(x[i]);
+    }
+}

@@ -111,4 +111,7 @@ void q1o_reset_philox(const q1o_config *cfg, q1o_state *st, int64_t n, uint64_t 
 #ifdef __cplusplus
 }
 #endif
+/* sin / cos of n doubles through the C library, as NumPy does for phys.py:58-59 */
+void q1o_sincos(int64_t n, const double *x, double *s, double *c);
+
 #endif

@@ -68,7 +68,7 @@ def lib():
         _lib.q1o_num_keys.restype = ctypes.c_int
         for name in ("q1o_step", "q1o_decode", "q1o_phys_apply", "q1o_observe", "q1o_reset_env",
                      "q1o_philox4x32", "q1o_reset_draws", "q1o_policy_action",
-                     "q1o_policy_actions", "q1o_reset_philox"):
+                     "q1o_policy_actions", "q1o_reset_philox", "q1o_sincos"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -259,3 +259,12 @@ def policy_actions(cfg, policy, seed, env_index_base, n, tick):
                              ctypes.c_uint64(int(env_index_base)), ctypes.c_int64(n),
                              ctypes.c_uint32(int(tick)), _ptr(keys), _ptr(mouse))
     return keys, mouse
+
+
+def sincos(x):
+    """(np.sin(x), np.cos(x)) through the C library's scalar sin / cos (what NumPy calls for
+    float64 on this platform; NumPy's own SIMD loops, where a CPU enables them, are not used)."""
+    x = np.ascontiguousarray(x, np.float64)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().q1o_sincos(ctypes.c_int64(x.size), _ptr(x), _ptr(s), _ptr(c))
+    return s, c

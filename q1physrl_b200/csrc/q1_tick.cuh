@@ -14,6 +14,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "q1_libm_sincos.cuh"
+
+/* 1: the branch-free polynomial sincos_rad() (< 1 ulp, NOT bit-identical to the reference's libm)
+ * in the lean kernels, for A/B timing only; 0 (default): glibc's algorithm, bit for bit. */
+#ifndef Q1_POLY_SINCOS
+#define Q1_POLY_SINCOS 0
+#endif
+
 namespace q1 {
 
 /* ------------------------------------------------------------------ constants ---------------- */
@@ -258,6 +266,15 @@ __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
     c = __hiloint2double(__double2hiint(cc) ^ cflip, __double2loint(cc));
 }
 
+/* sin and cos of a (radians) with the bits np.sin / np.cos return in the reference (phys:58-59,
+ * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh.  Beyond its main range
+ * (|a| >= 105414350, yaw past 6e9 degrees) libdevice's sincos answers instead. */
+__device__ __forceinline__ void sincos_ref(double a, double &s, double &c)
+{
+    if (__builtin_expect(!q1libm::sincos(a, s, c), 0))
+        sincos(a, &s, &c);
+}
+
 /* ------------------------------------------------------------------ observation -------------- */
 
 /* env:381-400 with get_obs_scale (env:294-296), result cast to f32 (the dtype the env declares,
@@ -497,10 +514,15 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
 
     /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
     double sy, cy;
-    if (LEAN)                                                                            /* phys:58-59 */
-        sincos_rad(div_const(mul64(e.yaw, kTickConst[0]), 180.0, kTickConst[1]), sy, cy);
-    else
-        sincos(div64(mul64(e.yaw, kPi), 180.0), &sy, &cy);
+    if (LEAN) {                                                                          /* phys:58-59 */
+        const double a = div_const(mul64(e.yaw, kTickConst[0]), 180.0, kTickConst[1]);
+        if (Q1_POLY_SINCOS)
+            sincos_rad(a, sy, cy);
+        else
+            sincos_ref(a, sy, cy);
+    } else {
+        sincos_ref(div64(mul64(e.yaw, kPi), 180.0), sy, cy);
+    }
     bool og = e.bits & F_ON_GROUND, jr = e.bits & F_JUMP_RELEASED;
     move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,
                     P.accel_dt, P.gravity_dt);
@@ -546,7 +568,7 @@ __device__ __forceinline__ void reset_env(const Params &P, Env &e, uint64_t gidx
         angle = kPi / 2;
     }
     double sa, ca;
-    sincos(angle, &sa, &ca);
+    sincos_ref(angle, sa, ca);
     e.vx = __double2float_rn(mul64(speed, ca));
     e.vy = __double2float_rn(mul64(speed, sa));
     e.bits = F_JUMP_RELEASED | (zs ? F_ZERO_START : 0u); /* timers 0: every key may be pressed */

@@ -629,11 +629,11 @@ __device__ __forceinline__ void phys_apply_row(double yaw, double pitch, double 
 {
     /* phys:58-66 */
     double sy, cy, sp = 0.0, cp = 1.0, sr = 0.0, cr = 1.0;
-    sincos(div64(mul64(yaw, kPi), 180.0), &sy, &cy);
+    sincos_ref(div64(mul64(yaw, kPi), 180.0), sy, cy);
     if (has_pitch)
-        sincos(div64(mul64(pitch, kPi), 180.0), &sp, &cp);
+        sincos_ref(div64(mul64(pitch, kPi), 180.0), sp, cp);
     if (has_roll)
-        sincos(div64(mul64(roll, kPi), 180.0), &sr, &cr);
+        sincos_ref(div64(mul64(roll, kPi), 180.0), sr, cr);
     double fx = mul64(cp, cy);
     double rx = add64(mul64(mul64(mul64(-1.0, sr), sp), cy), mul64(mul64(-1.0, cr), -sy));
     double fy = mul64(cp, sy);
@@ -779,6 +779,20 @@ __device__ __forceinline__ double random_double(uint64_t &rng, int span, bool si
     if (signed_ && (w >> 63))
         bits |= 0x8000000000000000ull;
     return __longlong_as_double((long long)bits);
+}
+
+/* sincos_ref on an array: the device build of q1_libm_sincos.cuh, exposed so that tests can compare
+ * it bit for bit with the host C library the reference calls through NumPy */
+__global__ void __launch_bounds__(256)
+k_sincos(int64_t n, const double *__restrict__ x, double *__restrict__ s, double *__restrict__ c)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    double sv, cv;
+    sincos_ref(x[i], sv, cv);
+    s[i] = sv;
+    c[i] = cv;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1954,6 +1968,35 @@ int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t m
             rc = fail(Q1_ECUDA, std::string("k_selftest: ") + cudaGetErrorString(err));
     }
     cudaFree(d_out);
+    return rc;
+}
+
+int q1_sincos_host(int device, int64_t n, const double *x, double *sin_out, double *cos_out)
+{
+    if (n < 0)
+        return fail(Q1_EINVAL, "n must be >= 0");
+    if (n == 0)
+        return Q1_OK;
+    if (!x || !sin_out || !cos_out)
+        return fail(Q1_EINVAL, "x / sin_out / cos_out is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    double *d = nullptr;
+    Q1_CUDA(cudaMalloc(&d, 3 * (size_t)n * sizeof(double)));
+    int rc = Q1_OK;
+    cudaError_t err = cudaMemcpy(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        k_sincos<<<(unsigned)((n + 255) / 256), 256>>>(n, d, d + n, d + 2 * n);
+        rc = check_launch("k_sincos");
+    }
+    if (err == cudaSuccess && rc == Q1_OK)
+        err = cudaMemcpy(sin_out, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && rc == Q1_OK)
+        err = cudaMemcpy(cos_out, d + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (err != cudaSuccess)
+        return fail(Q1_ECUDA, std::string("q1_sincos_host: ") + cudaGetErrorString(err));
     return rc;
 }
 

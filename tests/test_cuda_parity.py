@@ -1,10 +1,11 @@
 """GPU: the CUDA path (through the C ABI / the Python mirror) against the golden fixtures recorded
 from the reference and against the C oracle on identical seeded inputs.
 
-Contract (BASELINE.json north_star): done / on_ground and every other flag bit-exact, z / yaw /
-time_remaining bit-exact (pure f64 add chains), velocity within 1e-5 abs -- the only source of a
-difference is CUDA's f64 sincos (<= 2 ulp) against glibc's; the tests report how many stored f32
-velocities are bit-identical.
+Contract (BASELINE.json north_star): done / on_ground and every other flag bit-exact, velocity and
+origin within 1e-5 abs.  1e-5 is below one f32 ulp for |v| >= 128, so the tests ask for more: EVERY
+stored value -- f32 velocity, f64 z / yaw / time_remaining, observation, reward -- bit-identical.
+That holds because the kernels mirror each width and rounding of the reference and compute sin / cos
+with glibc's own algorithm (q1_libm_sincos.cuh), the reference's one inexact primitive.
 """
 import dataclasses
 
@@ -16,7 +17,7 @@ from oracle import q1_oracle as qo
 
 pytestmark = pytest.mark.gpu
 
-VEL_ATOL = 1e-5
+VEL_ATOL = 0.0    # bit-identical
 
 
 @pytest.mark.parametrize("stamps", [False, True], ids=["counters", "f64stamps"])
@@ -26,7 +27,7 @@ def test_golden_replay(name, stamps, record_property):
     stats = harness.replay(harness.CudaAdapter(g["config"], f64_key_stamps=stamps), g,
                            vel_atol=VEL_ATOL)
     record_property("vel_bit_exact_fraction", 1 - stats["vel_mismatch"] / stats["vel_values"])
-    assert stats["obs_max_abs"] <= 1e-6
+    assert stats["vel_mismatch"] == 0 and stats["obs_mismatch"] == 0 and stats["reward_mismatch"] == 0
     print(name, stats)
 
 
@@ -44,9 +45,7 @@ def test_phys_apply_golden():
     assert np.array_equal(out.z_pos, g["out_z_pos"])
     assert np.array_equal(out.on_ground, g["out_on_ground"])
     assert np.array_equal(out.jump_released, g["out_jump_released"])
-    assert np.abs(out.vel.astype(np.float64) - g["out_vel"]).max() <= VEL_ATOL
-    print("phys.apply bit-exact velocity fraction",
-          np.mean(out.vel == g["out_vel"]))
+    assert np.array_equal(out.vel, g["out_vel"])
 
 
 @pytest.mark.parametrize("name", ["decoder_n64", "decoder_discrete_n64"])
@@ -104,10 +103,9 @@ def test_free_running_vs_oracle(cfg_name):
     st = e.get_state(harness.STATE_FIELDS)
     for f in ("z_pos", "yaw", "time_remaining", "zero_start", "on_ground"):
         assert np.array_equal(st[f], o.get_state()[f].astype(st[f].dtype)), f
-    assert np.abs(st["vel"] - o.vel).max() <= VEL_ATOL   # reset velocity goes through sincos too
-    o.vel[...] = st["vel"]
+    assert np.array_equal(st["vel"], o.vel)              # reset velocity goes through sincos too
     rng = np.random.default_rng(5)
-    vel_bad = vel_tot = 0
+    vel_tot = 0
     for t in range(ticks):
         keys, mouse = harness.random_actions(cfg, rng, n, nk)
         obs, rew, done, infos = e.vector_step((keys, mouse), auto_reset=True)
@@ -125,17 +123,11 @@ def test_free_running_vs_oracle(cfg_name):
         assert np.array_equal(st["last_keys"], o.last_keys.astype(bool))
         assert np.array_equal(st["jump_released"], o.jump_released.astype(bool))
         assert np.array_equal(st["zero_start"], o.zero_start.astype(bool))
-        dv = np.abs(st["vel"].astype(np.float64) - o.vel)
-        assert dv.max() <= VEL_ATOL, f"velocity differs by {dv.max()} at tick {t}"
-        vel_bad += int(np.count_nonzero(st["vel"] != o.vel))
-        vel_tot += dv.size
-        assert np.abs(rew.astype(np.float64) - orew).max() <= VEL_ATOL
-        assert np.abs(obs.astype(np.float64) - oobs.astype(np.float32)).max() <= 0.081
-        if vel_bad == 0:
-            assert np.array_equal(obs, oobs.astype(np.float32)), f"obs differs at tick {t}"
-            assert np.array_equal(rew, orew)
-    print(cfg_name, "bit-exact f32 velocity stores:", 1 - vel_bad / vel_tot, "of", vel_tot)
-    assert vel_bad / vel_tot < 1e-5
+        assert np.array_equal(st["vel"], o.vel), f"velocity differs at tick {t}"
+        vel_tot += st["vel"].size
+        assert np.array_equal(obs, oobs.astype(np.float32)), f"obs differs at tick {t}"
+        assert np.array_equal(rew, orew), f"reward differs at tick {t}"
+    print(cfg_name, "bit-identical f32 velocity stores:", vel_tot, "of", vel_tot)
 
 
 @pytest.mark.parametrize("stamps", [False, True], ids=["counters", "f64stamps"])
@@ -168,15 +160,11 @@ def test_teacher_forced_single_tick(cfg_name, stamps):
             assert np.array_equal(st[f], getattr(o, f)), f
         if e.info.f64_stamps:
             assert np.array_equal(st["last_press"], o.last_press)
-        dv = np.abs(st["vel"].astype(np.float64) - o.vel)
-        assert dv.max() <= VEL_ATOL
-        same = np.all(st["vel"] == o.vel, axis=1)
-        assert same.mean() > 1 - 1e-4
-        assert np.array_equal(obs[same], oobs.astype(np.float32)[same])
-        assert np.array_equal(rew[same], orew[same])
+        assert np.array_equal(st["vel"], o.vel)
+        assert np.array_equal(obs, oobs.astype(np.float32))
+        assert np.array_equal(rew, orew)
         # the tick after: key timers / stamps must lead to the same decode decisions
         keys2, mouse2 = harness.random_actions(cfg, rng, n, nk)
-        o.vel[...] = st["vel"]
         e.vector_step((keys2, mouse2))
         o.step(keys2, mouse2.astype(np.float64))
         st2 = e.get_state(harness.STATE_FIELDS)
@@ -214,8 +202,8 @@ def test_edge_cases_landing_jump_and_time_crossing():
         assert np.array_equal(s["on_ground"], o.on_ground.astype(bool))
         assert np.array_equal(s["z_pos"], o.z_pos)
         assert np.array_equal(s["time_remaining"], o.time_remaining)
-        assert np.abs(s["vel"].astype(np.float64) - o.vel).max() <= VEL_ATOL
-        assert np.abs(obs - oobs.astype(np.float32)).max() <= 1e-6
+        assert np.array_equal(s["vel"], o.vel) and np.array_equal(s["yaw"], o.yaw)
+        assert np.array_equal(obs, oobs.astype(np.float32)) and np.array_equal(rew, orew)
         keys[:, 3] ^= 1
 
 
@@ -254,7 +242,7 @@ def test_rollout_kernel_vs_oracle(policy):
     o = qo.OracleEnv(cfg)
     epochs = np.ones(n, np.int64)
     o.reset_from_philox(seed, base, 1)
-    o.vel[...] = e.get_state(("vel",))["vel"]
+    assert np.array_equal(o.vel, e.get_state(("vel",))["vel"])
     pid = {"random": 0, "strafe_jump": 1}[policy]
     ret = np.zeros(n)
     rsum = np.zeros(n, np.float32)
@@ -280,8 +268,8 @@ def test_rollout_kernel_vs_oracle(policy):
             assert np.array_equal(st[f], getattr(o, f)), f
         for f in ("on_ground", "jump_released", "zero_start", "last_keys"):
             assert np.array_equal(st[f], getattr(o, f).astype(bool)), f
-        assert np.abs(st["vel"].astype(np.float64) - o.vel).max() <= VEL_ATOL
-        assert np.abs(obs_t.cpu().numpy() - o.observe().astype(np.float32)).max() <= 1e-6
+        assert np.array_equal(st["vel"], o.vel)
+        assert np.array_equal(obs_t.cpu().numpy(), o.observe().astype(np.float32))
         assert np.abs(rsum_t.cpu().numpy() - rsum).max() <= 1e-3
     m = e.metrics()
     assert m["episodes"] == len(all_returns) and m["zero_start_episodes"] == len(zs_returns)
@@ -341,8 +329,8 @@ def test_full_size_properties():
         if t % 60 == 0 or t >= 719:
             k_s, m_s = keys.cpu().numpy()[sample], mouse.cpu().numpy()[sample]
             oobs, orew, odone = o.step(k_s, m_s.astype(np.float64))
-            assert np.abs(obs.cpu().numpy()[sample] - oobs.astype(np.float32)).max() <= 1e-6
-            assert np.abs(rew.cpu().numpy()[sample].astype(np.float64) - orew).max() <= VEL_ATOL
+            assert np.array_equal(obs.cpu().numpy()[sample], oobs.astype(np.float32))
+            assert np.array_equal(rew.cpu().numpy()[sample], orew)
         else:
             o.step(keys.cpu().numpy()[sample], mouse.cpu().numpy()[sample].astype(np.float64))
     assert bool(zs.all().item())
@@ -394,8 +382,7 @@ def test_phys_apply_float32_time_delta_golden():
                      phys.PlayerState(g["z_pos"], g["vel"], g["on_ground"], g["jump_released"]))
     assert np.array_equal(out.z_pos, g["out_z_pos"]) and np.array_equal(out.on_ground, g["out_on_ground"])
     assert np.array_equal(out.jump_released, g["out_jump_released"])
-    assert np.abs(out.vel.astype(np.float64) - g["out_vel"]).max() <= VEL_ATOL
-    print("phys.apply (f32 dt) bit-exact velocity fraction", np.mean(out.vel == g["out_vel"]))
+    assert np.array_equal(out.vel, g["out_vel"])
 
 
 def test_hypothetical_delta_speeds_golden():
@@ -412,10 +399,7 @@ def test_hypothetical_delta_speeds_golden():
     assert np.array_equal(res.move_angle, g["move_angle"])
     ds = res.hypothetical_delta_speeds
     assert ds.shape == (360, n) and ds.dtype == np.float32
-    diff = np.abs(ds.astype(np.float64) - g["delta_speeds"])
-    print("delta-speed sweep: max abs", diff.max(), "bit-exact fraction", np.mean(ds == g["delta_speeds"]))
-    assert diff.max() <= 1e-4                                 # |v| up to ~700: one f32 ulp is 6e-5
-    assert np.mean(ds == g["delta_speeds"]) > 0.9999
+    assert np.array_equal(ds, g["delta_speeds"])
 
 
 def test_eval_sim_matches_stepping_the_env():
@@ -461,9 +445,8 @@ def test_division_sequences_selftest():
 
 
 def test_lean_arithmetic_equals_ieee_intrinsics_at_full_size():
-    """A/B at BASELINE size: a handle stepping with the reciprocal sequences + own sincos and one
-    using the CUDA IEEE division intrinsics + libdevice sincos; flags, z, yaw, time must be
-    identical, velocities may differ only through the two sincos implementations (both < 1 ulp)."""
+    """A/B at BASELINE size: a handle stepping with the reciprocal-multiply division sequences and
+    one using the CUDA IEEE division intrinsics must agree in every bit of the state."""
     import torch
     from q1physrl_b200 import env as benv
     n = 1 << 20
@@ -479,8 +462,36 @@ def test_lean_arithmetic_equals_ieee_intrinsics_at_full_size():
         ob = b.step_tensors(keys, mouse, auto_reset=True)
         assert torch.equal(oa[2], ob[2]) and torch.equal(oa[3], ob[3])
     sa, sb = a.get_state(), b.get_state()
-    for f in ("z_pos", "yaw", "time_remaining", "on_ground", "jump_released", "zero_start", "last_keys"):
+    for f in ("vel", "z_pos", "yaw", "time_remaining", "on_ground", "jump_released", "zero_start",
+              "last_keys"):
         assert np.array_equal(sa[f], sb[f]), f
-    same = np.mean(sa["vel"] == sb["vel"])
-    print("lean vs IEEE/libdevice: identical f32 velocity stores", same)
-    assert np.abs(sa["vel"].astype(np.float64) - sb["vel"]).max() <= 1e-4 and same > 0.99999
+
+
+def test_device_sincos_equals_libm():
+    """The device build of q1_libm_sincos.cuh against the host C library (through the oracle's
+    q1o_sincos loop) on 2^23 arguments: the yaw range of an episode in degrees -> radians, wide
+    uniform and log-uniform ranges, every branch threshold +- 2^12 ulps, multiples of pi/2."""
+    import ctypes
+    from q1physrl_b200 import _lib
+    rng = np.random.default_rng(123)
+    m = 1 << 20
+    th = np.array([0.126, 0.85546875, 0.855469, 2.4262650012969971, 2.426265, np.pi / 2, np.pi, 2.0 ** -26,
+                   2.0 ** -27, 105414350.0, 1 / 128, 0.5 / 128, 109.5 / 128])
+    near = (rng.choice(th, m).view(np.int64) + rng.integers(-4096, 4097, m)).view(np.float64)
+    parts = [
+        (rng.uniform(-8000, 8000, m) * np.pi) / 180.0,
+        (rng.uniform(-8000, 8000, m).astype(np.float32).astype(np.float64) * np.pi) / 180.0,
+        rng.uniform(-3, 3, m), rng.uniform(-1e5, 1e5, m), rng.uniform(-1.05e8, 1.05e8, m),
+        np.ldexp(rng.uniform(0.5, 1, m), rng.integers(-40, 28, m)) * rng.choice([-1.0, 1.0], m),
+        near * rng.choice([-1.0, 1.0], m),
+        rng.integers(-100000, 100001, m) * (np.pi / 2) + np.ldexp(rng.uniform(-1, 1, m), -rng.integers(0, 50, m)),
+    ]
+    x = np.ascontiguousarray(np.concatenate(parts + [np.array([0.0, -0.0, 5e-324, 1e6, -1e7, 1.2e8, 1e300])]))
+    s, c = np.empty_like(x), np.empty_like(x)
+    _lib.check(_lib.load().q1_sincos_host(0, x.size, x.ctypes.data, s.ctypes.data, c.ctypes.data))
+    ws, wc = qo.sincos(x)
+    main = np.abs(x) < 105414336.0          # high word < 0x419921FB, the bound s_sin.c tests
+    bad = main & ((s.view(np.int64) != ws.view(np.int64)) | (c.view(np.int64) != wc.view(np.int64)))
+    assert not bad.any(), [float.hex(v) for v in x[bad][:8]]
+    # beyond glibc's main range libdevice answers: accurate, not necessarily identical
+    assert np.abs(s[~main] - ws[~main]).max() < 1e-15 and np.abs(c[~main] - wc[~main]).max() < 1e-15
