@@ -158,8 +158,11 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
             float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset, void *stream);
 /* Same call with HOST buffers: copies the actions in, steps, copies the results out and
  * synchronises.  This is what PhysEnv.step / VectorPhysEnv.vector_step bind for NumPy callers.
- * Buffers from q1_host_alloc (or any page-locked memory) are transferred by DMA directly; pageable
- * memory works too, at the driver's staging speed. */
+ * With buffers from q1_host_alloc (or any page-locked, device-mapped memory) the step kernel itself
+ * bulk-loads the actions from and bulk-stores the results to host memory, so both PCIe directions
+ * run for the whole launch and a step costs max(H2D, D2H) of the wire (Q1PHYS_HOST_DIRECT=0 selects
+ * the older chunked copy / tick / copy pipeline instead); pageable memory works too, through staging
+ * copies at the driver's speed. */
 int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
                  float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset);
 

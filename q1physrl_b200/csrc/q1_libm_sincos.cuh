@@ -119,9 +119,9 @@ Q1LIBM_FN TabEntry lookup(uint32_t k)
 {
     TabEntry e;
 #if defined(__CUDACC__)
-    const double2 *p = reinterpret_cast<const double2 *>(kTab) + 2 * k;
-    const double2 a = __ldg(p), b = __ldg(p + 1);
-    e.sn = a.x; e.ssn = a.y; e.cs = b.x; e.ccs = b.y;
+    /* one 32-byte entry = one sector = one 256-bit load (sm_100: LDG.E.256) through L1 */
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+        : "=d"(e.sn), "=d"(e.ssn), "=d"(e.cs), "=d"(e.ccs) : "l"(kTab + 4 * k));
 #else
     e.sn = kTab[4 * k]; e.ssn = kTab[4 * k + 1]; e.cs = kTab[4 * k + 2]; e.ccs = kTab[4 * k + 3];
 #endif
@@ -190,12 +190,10 @@ Q1LIBM_FN bool sincos(double x, double &sin_out, double &cos_out)
     const double cu = f_add(kC[C_BIG], aca);
     const double cr = f_add(f_sub(aca, f_sub(cu, kC[C_BIG])), cd);
     const uint32_t ck = f_lo(cu);
-    /* both evaluations use the same table entry except in the fold range when |tf| and |af|
-     * round to different nodes */
+    /* (the two entries are the same one except in the fold range when |tf| and |af| round to
+     * different nodes; two unconditional loads are cheaper than the test and the register copies) */
     const TabEntry tc = lookup(ck);
-    TabEntry ts = tc;
-    if (sk != ck)
-        ts = lookup(sk);
+    const TabEntry ts = lookup(sk);
 
     const double sxx = f_mul(sr, sr);
     const double ss = f_add(sr, f_fma(f_mul(sr, sxx), f_fma(sxx, kC[C_SN5], kC[C_SN3]), sd));

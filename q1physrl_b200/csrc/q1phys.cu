@@ -913,6 +913,8 @@ struct q1_env {
     int sm_count = 148;
     bool pdl = true; /* launch the step kernel with programmatic stream serialization */
     int host_chunks = 2; /* pipeline depth of q1_step_host for large page-locked batches */
+    bool host_direct = true; /* q1_step_host: let the step kernel read / write page-locked host buffers
+                                itself (mapped memory over PCIe) instead of staging them through HBM */
     cudaStream_t host_stream = nullptr;
     cudaStream_t in_stream = nullptr, out_stream = nullptr; /* the chunked pipeline of q1_step_host */
     cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
@@ -1025,6 +1027,19 @@ int check_launch(const char *what)
     return Q1_OK;
 }
 
+/* The address under which the device reaches the page-locked host buffer `p` (the same address
+ * under unified addressing, possibly another one for cudaHostRegister'ed memory); NULL if the
+ * buffer is not mapped into the device's address space. */
+template <typename T> T *device_view(T *p)
+{
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void *>(static_cast<const void *>(p)), 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return static_cast<T *>(d);
+}
+
 int ensure_scratch(q1_env *env, size_t bytes)
 {
     if (!env->host_stream)
@@ -1121,6 +1136,8 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     env->pdl = getenv("Q1PHYS_NO_PDL") == nullptr;
     if (const char *hc = getenv("Q1PHYS_HOST_CHUNKS"))
         env->host_chunks = std::max(1, std::min(8, atoi(hc)));
+    if (const char *hd = getenv("Q1PHYS_HOST_DIRECT"))
+        env->host_direct = atoi(hd) != 0;
     /* the reciprocal sequences assume positive divisors in a sane exponent range */
     auto sane = [](double v) { return v > 1e-100 && v < 1e100; };
     env->P.ieee_div = (flags & Q1_F_IEEE_DIVISION) || !sane(cfg->time_limit) ||
@@ -1458,8 +1475,30 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
      * directions are independent copy engines), so a step costs about max(H2D, D2H), not the sum. */
     constexpr int kMaxChunks = 8;
     int chunks = 1;
-    if (n >= (size_t)1 << 16 && is_pinned(keys) && is_pinned(obs) && is_pinned(reward) &&
-        is_pinned(done) && (!env->P.allow_yaw || is_pinned(mouse)) && (!zero_start || is_pinned(zero_start)))
+    const bool all_pinned = is_pinned(keys) && is_pinned(obs) && is_pinned(reward) && is_pinned(done) &&
+                            (!env->P.allow_yaw || is_pinned(mouse)) && (!zero_start || is_pinned(zero_start));
+    if (all_pinned && env->host_direct && n >= (size_t)1 << 12) {
+        /* Page-locked buffers are mapped into the device's address space: the step kernel bulk-loads
+         * the actions from host memory and bulk-stores the results to host memory itself.  Both PCIe
+         * directions then run concurrently for the whole launch, tile by tile, with no staging copy,
+         * no chunk boundaries and one launch: a step costs max(H2D, D2H) of the wire. */
+        const uint8_t *m_keys = device_view(keys);
+        const void *m_mouse = env->P.allow_yaw ? device_view(mouse) : nullptr;
+        float *m_obs = device_view(obs), *m_rew = device_view(reward);
+        uint8_t *m_done = device_view(done), *m_zs = zero_start ? device_view(zero_start) : nullptr;
+        if (m_keys && m_obs && m_rew && m_done && (!env->P.allow_yaw || m_mouse) && (!zero_start || m_zs)) {
+            if (!env->host_stream)
+                Q1_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+            rc = step_range(env, m_keys, m_mouse, mouse_kind, m_obs, m_rew, m_done, m_zs, auto_reset, 0,
+                            (int64_t)n, env->host_stream);
+            if (rc != Q1_OK)
+                return rc;
+            Q1_CUDA(cudaStreamSynchronize(env->host_stream));
+            env->ticks += 1;
+            return Q1_OK;
+        }
+    }
+    if (n >= (size_t)1 << 16 && all_pinned)
         chunks = env->host_chunks;
     if (chunks <= 1) {
         Q1_CUDA(cudaMemcpyAsync(d_keys, keys, n * nk, cudaMemcpyHostToDevice, s));
