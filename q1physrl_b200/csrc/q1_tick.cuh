@@ -137,6 +137,25 @@ __device__ __forceinline__ double div_const(double a, double b, double y)
     return __fma_rn(r, y, q);
 }
 
+/* The same quotient in three operations, for divisors whose rounded reciprocal is good enough:
+ * if |y b - 1| <= 2^-54 then q = RN(a y) is already faithful (|q - a/b| < |a/b| 2^-54 + ulp/2
+ * < 1 ulp, the first term being below half an ulp because |a/b| < 2^(e+1) strictly), and one
+ * Markstein correction rounds correctly.  180 and 90 qualify (|y b - 1| = 0.34 * 2^-53), so do
+ * 10, 5 and f32(10.08); a handle whose action_range / yaw steps / time_limit do not is given the
+ * IEEE-division kernels instead (short_division_ok() in q1phys.cu).  q1_selftest_division checks
+ * this form against __ddiv_rn for every qualifying constant it draws. */
+__device__ __forceinline__ double div_const3(double a, double b, double y)
+{
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+/* device-side evaluation of the criterion (y b - 1 is exact in one fused multiply-add) */
+__device__ __forceinline__ bool short_division_ok_dev(double b, double y)
+{
+    return fabs(__fma_rn(y, b, -1.0)) <= 0x1p-54;
+}
+
 /* RN(1 / b) for a normal b well inside the exponent range: hardware seed (2^-23), one cubic and
  * one Markstein step.  q1_selftest_division checks this bit for bit against __drcp_rn / __ddiv_rn
  * on 10^10 random operands, one in 64 of them with a significand of all ones. */
@@ -269,9 +288,9 @@ __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
 /* sin and cos of a (radians) with the bits np.sin / np.cos return in the reference (phys:58-59,
  * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh.  Beyond its main range
  * (|a| >= 105414350, yaw past 6e9 degrees) libdevice's sincos answers instead. */
-__device__ __forceinline__ void sincos_ref(double a, double &s, double &c)
+__device__ __forceinline__ void sincos_ref(double a, double &s, double &c, uint32_t tab = 0)
 {
-    if (__builtin_expect(!q1libm::sincos(a, s, c), 0))
+    if (__builtin_expect(!q1libm::sincos(a, s, c, tab), 0))
         sincos(a, &s, &c);
 }
 
@@ -287,8 +306,8 @@ template <bool LEAN>
 __device__ __forceinline__ void observe(const Params &P, const Env &e, float o[6])
 {
     if (LEAN) {
-        o[0] = __double2float_rn(div_const(e.trem, P.time_limit, P.rcp_time_limit));
-        o[1] = __double2float_rn(div_const(e.yaw, 90.0, kTickConst[2]));
+        o[0] = __double2float_rn(div_const3(e.trem, P.time_limit, P.rcp_time_limit));
+        o[1] = __double2float_rn(div_const3(e.yaw, 90.0, kTickConst[2]));
     } else {
         o[0] = __double2float_rn(div64(e.trem, P.time_limit));
         o[1] = __double2float_rn(div64(e.yaw, 90.0));
@@ -438,7 +457,7 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
  * hover, reward = y velocity) is compiled in; otherwise those switches are read from Params. */
 template <bool STAMPS, bool LEAN, bool COMMON>
 __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, double mouse,
-                                     float &reward, bool &done)
+                                     float &reward, bool &done, uint32_t sincos_tab = 0)
 {
     const bool hover = COMMON ? false : (bool)P.hover;
     const bool allow_yaw = COMMON ? true : (bool)P.allow_yaw;
@@ -455,10 +474,10 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
     if (allow_yaw) {
         if (!discrete_yaw) {                                                             /* env:236 */
             double t = mul64(mouse, P.max_yaw_delta);
-            mouse_x = LEAN ? div_const(t, P.action_range, P.rcp_action_range) : div64(t, P.action_range);
+            mouse_x = LEAN ? div_const3(t, P.action_range, P.rcp_action_range) : div64(t, P.action_range);
         } else {                                                                         /* env:238 */
             double t = mul64(sub64(mouse, P.yaw_steps), P.max_yaw_delta);
-            mouse_x = LEAN ? div_const(t, P.yaw_steps, P.rcp_yaw_steps) : div64(t, P.yaw_steps);
+            mouse_x = LEAN ? div_const3(t, P.yaw_steps, P.rcp_yaw_steps) : div64(t, P.yaw_steps);
         }
     }
 
@@ -515,13 +534,13 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
     /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
     double sy, cy;
     if (LEAN) {                                                                          /* phys:58-59 */
-        const double a = div_const(mul64(e.yaw, kTickConst[0]), 180.0, kTickConst[1]);
+        const double a = div_const3(mul64(e.yaw, kTickConst[0]), 180.0, kTickConst[1]);
         if (Q1_POLY_SINCOS)
             sincos_rad(a, sy, cy);
         else
-            sincos_ref(a, sy, cy);
+            sincos_ref(a, sy, cy, sincos_tab);
     } else {
-        sincos_ref(div64(mul64(e.yaw, kPi), 180.0), sy, cy);
+        sincos_ref(div64(mul64(e.yaw, kPi), 180.0), sy, cy, sincos_tab);
     }
     bool og = e.bits & F_ON_GROUND, jr = e.bits & F_JUMP_RELEASED;
     move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,

@@ -34,10 +34,13 @@ using namespace q1;
 namespace {
 
 constexpr int kBlock = kTile;      /* threads per CTA: one env per thread, one state block per CTA tile */
+/* Resident CTAs per SM the persistent step kernel is sized for.  Measured at 2^20 envs (us per tick,
+ * same box): 8 CTAs x 64 registers 23.5, 7 x 72: 23.3, 6 x 80: 22.7, 5 x 96: 23.5, 4 x 128: 25.3.  With
+ * the libm-exact sin/cos the tick holds more live f64 values; at 64 registers the schedule serialises. */
 #ifndef Q1_STEP_CTAS
-#define Q1_STEP_CTAS 8
+#define Q1_STEP_CTAS 6
 #endif
-constexpr int kStepCtasPerSm = Q1_STEP_CTAS; /* resident CTAs per SM the persistent step kernel is sized for */
+constexpr int kStepCtasPerSm = Q1_STEP_CTAS;
 
 __device__ __forceinline__ unsigned char *state_block(const Params &P, int64_t i)
 {
@@ -303,7 +306,10 @@ enum : uint32_t {
     OUT_BYTES = OUT_ZS + kTile
 };
 static_assert(IN_BYTES % 128 == 0 && OUT_BYTES % 128 == 0, "every sub-buffer stays 16-byte aligned");
-constexpr int kInStages = 3;
+#ifndef Q1_IN_STAGES
+#define Q1_IN_STAGES 3
+#endif
+constexpr int kInStages = Q1_IN_STAGES;   /* input ring depth: loads run kInStages - 1 tiles ahead */
 constexpr int kOutStages = 2;
 
 /* Persistent, TMA-pipelined step kernel (counter mode, full tiles, 16-byte aligned buffers, f32 or
@@ -317,6 +323,16 @@ constexpr int kOutStages = 2;
  * loads), and every wait on an earlier bulk group sits one full tile after its issue, so no warp
  * ever blocks on the TMA engine.  Threads touch only shared memory (16-byte LDS/STS, 32-bit
  * addresses): no per-thread global address arithmetic, no load latency on the compute warps. */
+/* 1: k_step_tma moves its bytes but skips the tick (measures the ceiling of the memory pipeline
+ * alone; the results are meaningless).  Never set in the shipped build. */
+#ifndef Q1_PASSTHROUGH
+#define Q1_PASSTHROUGH 0
+#endif
+/* 1: k_step_tma keeps a copy of the libm sin/cos table (3.5 KB) in shared memory */
+#ifndef Q1_SMEM_TABLE
+#define Q1_SMEM_TABLE 0
+#endif
+
 template <bool TRACK, bool LEAN, bool COMMON>
 __global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
 k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
@@ -328,6 +344,14 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     __shared__ __align__(128) unsigned char in_mem[kInStages * IN_BYTES];
     __shared__ __align__(128) unsigned char out_mem[kOutStages * OUT_BYTES];
     __shared__ __align__(8) uint64_t full_bar[kInStages];
+#if Q1_SMEM_TABLE
+    __shared__ __align__(32) double sincos_tab[440];   /* CTA-local copy of the libm sin/cos table */
+    for (int k = threadIdx.x; k < 440; k += kBlock)
+        sincos_tab[k] = q1libm::kTab[k];                /* constant data: no dependency on earlier grids */
+    const uint32_t tab = smem_addr(sincos_tab);
+#else
+    const uint32_t tab = 0;
+#endif
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
     const bool issuer = (tid & 31u) == 0;
@@ -362,9 +386,9 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (warp == 3 && issuer) { /* the loading lane primes two stages; the third fills after tile 0 */
+    if (warp == 3 && issuer) { /* the loading lane primes all stages but one; the last fills after tile 0 */
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < kInStages - 1; s++) {
             const int64_t tile = tile_begin + blockIdx.x + (int64_t)s * gridDim.x;
             if (tile < tiles)
                 issue_loads(s, tile);
@@ -405,7 +429,12 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
         }
         float r;
         bool d;
-        tick<false, LEAN, COMMON>(P, e, keybits, m, r, d);
+        if (Q1_PASSTHROUGH) { /* traffic-only build: same bytes in and out, no arithmetic */
+            r = e.vx + (float)m;
+            d = keybits == 0xffu;
+        } else {
+            tick<false, LEAN, COMMON>(P, e, keybits, m, r, d, tab);
+        }
         const bool zs = e.bits & F_ZERO_START;
         bool finished = false;
         double ret = 0.0;
@@ -429,7 +458,11 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             P.ep_return[i] = ret;
         }
         float o[6];
-        observe<LEAN>(P, e, o);
+        if (Q1_PASSTHROUGH) {
+            o[0] = e.vx; o[1] = e.vy; o[2] = e.vz; o[3] = (float)e.z; o[4] = (float)e.yaw; o[5] = (float)e.trem;
+        } else {
+            observe<LEAN>(P, e, o);
+        }
         sts_f2(ob + OUT_OBS + tid * 24u, o[0], o[1]);
         sts_f2(ob + OUT_OBS + tid * 24u + 8u, o[2], o[3]);
         sts_f2(ob + OUT_OBS + tid * 24u + 16u, o[4], o[5]);
@@ -460,7 +493,7 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             } else {
                 /* refill the stage of the previous tile: all warps left it a barrier ago and its
                  * state store was drained before this barrier */
-                const int64_t next = t + 2 * (int64_t)gridDim.x;
+                const int64_t next = t + (kInStages - 1) * (int64_t)gridDim.x;
                 if (next < tiles)
                     issue_loads(s >= 1 ? s - 1 : kInStages - 1, next);
             }
@@ -813,6 +846,8 @@ k_selftest(uint64_t iters, uint64_t seed, unsigned long long *__restrict__ out)
         double c = (it & 8) ? random_double(rng, 20, false) : consts[it & 7];
         double yc = __drcp_rn(c);
         bad[2] += __double_as_longlong(div_const(a, c, yc)) != __double_as_longlong(__ddiv_rn(a, c));
+        if (short_division_ok_dev(c, yc))   /* the three-operation form, where its criterion holds */
+            bad[2] += __double_as_longlong(div_const3(a, c, yc)) != __double_as_longlong(__ddiv_rn(a, c));
         /* 3: the physics ranges: wish velocity / wish speed, new_speed / speed */
         double ws = 1.0 + (double)(splitmix64(rng) >> 11) * (2000.0 / 9007199254740992.0);
         double wx = ((double)(splitmix64(rng) >> 11) * (2.0 / 9007199254740992.0) - 1.0) * ws;
@@ -913,6 +948,7 @@ struct q1_env {
     int sm_count = 148;
     bool pdl = true; /* launch the step kernel with programmatic stream serialization */
     int host_chunks = 2; /* pipeline depth of q1_step_host for large page-locked batches */
+    bool balance_grid = false; /* step kernel: shrink the grid so that all CTAs walk equally many tiles */
     bool host_direct = true; /* q1_step_host: let the step kernel read / write page-locked host buffers
                                 itself (mapped memory over PCIe) instead of staging them through HBM */
     cudaStream_t host_stream = nullptr;
@@ -1136,12 +1172,19 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     env->pdl = getenv("Q1PHYS_NO_PDL") == nullptr;
     if (const char *hc = getenv("Q1PHYS_HOST_CHUNKS"))
         env->host_chunks = std::max(1, std::min(8, atoi(hc)));
+    if (const char *bg = getenv("Q1PHYS_BALANCE_GRID"))
+        env->balance_grid = atoi(bg) != 0;
     if (const char *hd = getenv("Q1PHYS_HOST_DIRECT"))
         env->host_direct = atoi(hd) != 0;
     /* the reciprocal sequences assume positive divisors in a sane exponent range */
     auto sane = [](double v) { return v > 1e-100 && v < 1e100; };
-    env->P.ieee_div = (flags & Q1_F_IEEE_DIVISION) || !sane(cfg->time_limit) ||
-                      (cfg->allow_yaw && cfg->discrete_yaw_steps == -1 && !sane(cfg->action_range));
+    /* ... and that q = RN(a * RN(1/b)) is a faithful quotient (div_const3 in q1_tick.cuh) */
+    auto short_division_ok = [](double b) { return std::fabs(std::fma(1.0 / b, b, -1.0)) <= 0x1p-54; };
+    auto divisor_ok = [&](double b) { return sane(b) && short_division_ok(b); };
+    env->P.ieee_div = (flags & Q1_F_IEEE_DIVISION) || !divisor_ok(cfg->time_limit) ||
+                      (cfg->allow_yaw && cfg->discrete_yaw_steps == -1 && !divisor_ok(cfg->action_range)) ||
+                      (cfg->allow_yaw && cfg->discrete_yaw_steps != -1 &&
+                       !divisor_ok((double)cfg->discrete_yaw_steps));
     Params &P = env->P;
     P.seed = seed;
     P.env_index_base = env_index_base;
@@ -1362,8 +1405,15 @@ static int step_range(q1_env *env, const uint8_t *keys, const void *mouse, int m
         const bool common = env->P.allow_yaw && !env->P.discrete_yaw && !env->P.hover &&
                             !env->P.speed_reward && mouse_kind == Q1_MOUSE_F32;
         rc = dispatch(env, [&](auto, auto tr, auto ln) {
-            unsigned grid = (unsigned)std::min<int64_t>(tile_end - tile_begin,
-                                                        (int64_t)env->sm_count * kStepCtasPerSm);
+            const int64_t ntiles = tile_end - tile_begin;
+            const int64_t resident = (int64_t)env->sm_count * kStepCtasPerSm;
+            int64_t g = std::min<int64_t>(ntiles, resident);
+            if (env->balance_grid && ntiles > resident) {
+                /* same number of rounds, but every CTA walks (almost) the same number of tiles */
+                const int64_t rounds = (ntiles + resident - 1) / resident;
+                g = (ntiles + rounds - 1) / rounds;
+            }
+            unsigned grid = (unsigned)g;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(kBlock);
