@@ -336,7 +336,9 @@ def run_cuda_arm(args, rank, world, local_rank):
                                  "step on torch's current stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "VectorPhysEnv.vector_step((keys, mouse)) with page-locked NumPy arrays"},
+                    "api": "VectorPhysEnv.vector_step((keys, mouse)) with page-locked NumPy arrays: q1_step_host "
+                           "launches the step kernel on the mapped host buffers (actions read and results "
+                           "written over PCIe inside the launch), then synchronises"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "kernel": "k_step_tma",

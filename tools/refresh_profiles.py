@@ -1,0 +1,77 @@
+"""Turn the artefacts of tools/evidence.sh (gpurun_out/) into the committed profiles/r1_* files:
+bench lines, the ncu launch list and its per-kernel summary, the raw metrics of the `ncu --set full`
+capture of k_step_tma and the SASS / stall summary of tools/ncu_summary.py."""
+import collections
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+for src, dst in (("bench_b200.json", f"{tag}_bench_b200.json"), ("bench_reference.json", f"{tag}_bench_reference.json"),
+                 ("launches.csv", f"{tag}_bench_launches.csv")):
+    shutil.copyfile(os.path.join(OUT, src), os.path.join(PROF, dst))
+
+# per-kernel summary of the launch list
+rows = [r for r in csv.reader(open(os.path.join(OUT, "launches.csv"))) if len(r) > 14 and r[0].isdigit()]
+per = collections.OrderedDict()
+for r in rows:
+    us = float(r[14]) / 1e3
+    name = r[4]
+    if "k_step_tma<0, 1, 1>" in name and us > 200:   # the e2e leg: same kernel on mapped host buffers (PCIe-bound)
+        name = "k_step_tma<0, 1, 1> on page-locked HOST buffers (e2e leg, PCIe-bound)"
+    per.setdefault(name, []).append(us)
+total = sum(sum(v) for v in per.values())
+with open(os.path.join(PROF, f"{tag}_bench_launches_summary.txt"), "w") as f:
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 python bench.py --steps 300 "
+            "--warmup 20 --no-cpu-baseline\n(per-launch times are cold-cache and serialised: compare shares; the "
+            "launches after the k_step_tma<0,1,1> ones belong to the e2e leg and to the closed-loop policy rollout / "
+            "config-4 rollout that run outside the timed region)\n\n")
+    for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        f.write(f"{name[:72]:72s} n={len(v):4d} mean={sum(v) / len(v):8.2f} us share={sum(v) / total:.3f}\n")
+
+# raw metrics of the full capture
+rep = os.path.join(OUT, "prof_step_tma.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+table = list(csv.reader(raw.splitlines()))
+hdr, units = table[0], table[1]
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+launches = [{w: f"{r[hdr.index(w)]} {units[hdr.index(w)]}" for w in want if w in hdr} for r in table[2:]]
+
+
+def num(launch, key):
+    v, unit = launch[key].split()[0], launch[key].split()[-1]
+    return float(v.replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(unit, 1)
+
+
+first = launches[0]
+doc = {
+    "kernel": "k_step_tma<TRACK=false,LEAN=true,COMMON=true>",
+    "source": "ncu --set full --clock-control none --import-source on -k regex:k_step_tma -s 30 -c 2, python bench.py "
+              "--steps 40 --warmup 10 --no-cpu-baseline (2^20 envs, nk=3)",
+    "dram_bytes_read": num(first, "dram__bytes_read.sum"),
+    "dram_bytes_write": num(first, "dram__bytes_write.sum"),
+    "duration_us": float(first["gpu__time_duration.sum"].split()[0]),
+    "algorithmic_bytes": 117 << 20,
+    "note": "single launch under the profiler: reads (49.3 MB) equal the algorithmic 47 B/env exactly -- no re-reads; "
+            "of the 73 MB written part is still dirty in the 126 MB L2 when the kernel ends and is written back during "
+            "later launches, so the in-kernel DRAM write count is below the algorithmic figure. In the back-to-back "
+            "bench loop (ring of 4 shards) every step moves the full 123 MB. The global loads are the 2 x 256-bit "
+            "lookups per env in the 3.5 KB libm sin/cos table (L1-resident).",
+    "raw": launches,
+}
+json.dump(doc, open(os.path.join(PROF, f"{tag}_step_tma_ncu.json"), "w"), indent=1)
+summary = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep],
+                         capture_output=True, text=True).stdout
+open(os.path.join(PROF, f"{tag}_step_tma_ncu_summary.txt"), "w").write(summary)
+print(summary)
