@@ -235,7 +235,14 @@ class ActionDecoder:
                               dtype=np.float64, order="C")
         yaw = np.array(np.broadcast_to(self._yaw, (n,)), dtype=np.float64, order="C")
         z_vel = np.ascontiguousarray(np.broadcast_to(np.asarray(z_vel, np.float32), (n,)))
-        tr = np.ascontiguousarray(np.broadcast_to(np.asarray(time_remaining, np.float64), (n,)))
+        tr_in = np.asarray(time_remaining)
+        if tr_in.dtype == np.float32:
+            # mkdemo.py:48-50 hands over a float32 time: NumPy then forms `time_limit - time_remaining`
+            # (env:241, 246) in float32.  Same value through the f64 kernel: now = f32(TL) - t in f32,
+            # passed as TL - now (exact for every now >= 2^-26 s when TL is a small dyadic number).
+            now = (np.float32(self._config.time_limit) - tr_in).astype(np.float64)
+            tr_in = np.float64(self._config.time_limit) - now
+        tr = np.ascontiguousarray(np.broadcast_to(np.asarray(tr_in, np.float64), (n,)))
         smove = np.empty(n, np.int64)
         fmove = np.empty(n, np.int64)
         jump = np.empty(n, np.uint8)

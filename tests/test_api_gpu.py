@@ -214,3 +214,43 @@ def test_fused_tcgen05_policy_kernel():
     m = e.metrics()
     print("fused policy:", m["zero_start_total_reward_mean"], m["zero_start_episodes"])
     assert m["zero_start_episodes"] == 8192 and 5600 < m["zero_start_total_reward_mean"] < 5800
+
+
+@pytest.mark.parametrize("tag", ["keys", "autojump"])
+def test_mkdemo_adapters_golden(tag):
+    """q1physrl_b200.mkdemo._make_observation / _apply_action against what the reference's own two
+    functions (mkdemo.py:39-55) returned / sent for a scripted fake client: observation values, and
+    every move command (yaw in radians, forward, side, buttons) over 800 frames, bit for bit --
+    including the float32 time width the reference's call imposes on the key rate limit."""
+    from q1physrl_b200 import env as benv, mkdemo
+    g = harness.load_golden("mkdemo_adapters")
+    cfg = benv.Config(**dict(g["config"], auto_jump=(tag == "autojump")))
+
+    class FakeClient:
+        moves = []
+
+        def move(self, **kw):
+            self.moves.append(kw)
+
+    client = FakeClient()
+    client.moves = []
+    dec = benv.ActionDecoder(cfg)
+    dec.vector_reset(np.array([benv.INITIAL_YAW_ZERO]))
+    T = g[f"{tag}_keys"].shape[0]
+    for t in range(T):
+        client.angles = tuple(g[f"{tag}_angles"][t])
+        client.velocity = tuple(g[f"{tag}_velocity"][t])
+        client.player_origin = tuple(g[f"{tag}_origin"][t])
+        tr = float(g[f"{tag}_time_remaining"][t])
+        obs = mkdemo._make_observation(client, tr, cfg)
+        assert obs.dtype == np.float64 and np.array_equal(obs, g[f"{tag}_obs"][t])
+        action = tuple([np.array([k]) for k in g[f"{tag}_keys"][t]] + [np.array([g[f"{tag}_mouse"][t]])])
+        mkdemo._apply_action(client, dec, action, tr)
+    m = client.moves
+    assert len(m) == T
+    assert np.array_equal(np.array([float(x["yaw"]) for x in m]), g[f"{tag}_move_yaw"])
+    assert np.array_equal(np.array([int(x["forward"]) for x in m]), g[f"{tag}_move_forward"])
+    assert np.array_equal(np.array([int(x["side"]) for x in m]), g[f"{tag}_move_side"])
+    assert np.array_equal(np.array([int(x["buttons"]) for x in m]), g[f"{tag}_move_buttons"])
+    assert all(x["pitch"] == 0 and x["roll"] == 0 and x["up"] == 0 and x["impulse"] == 0 for x in m)
+    assert np.array_equal(dec._last_key_press_time, g[f"{tag}_final_last_press"])

@@ -60,6 +60,33 @@ def test_oracle_decoder_matches_reference(name):
     assert np.array_equal(last_press, g["final_last_press"])
 
 
+@pytest.mark.parametrize("tag", ["keys", "autojump"])
+def test_oracle_decoder_with_float32_time_matches_mkdemo_reference(tag):
+    """mkdemo.py:47-55 calls ActionDecoder.map with a float32 time_remaining, which makes NumPy form
+    `time_limit - time_remaining` (env:241, 246) in float32.  The fixture holds what the reference's
+    own `_apply_action` sent to a scripted fake client; the oracle's f64 decode reproduces it when it
+    is handed TL - now with now = f32(TL) - f32(t) -- the transformation env.ActionDecoder.map
+    applies for float32 input."""
+    g = harness.load_golden("mkdemo_adapters")
+    cfg = dict(g["config"], auto_jump=(tag == "autojump"))
+    nk = g[f"{tag}_keys"].shape[1]
+    last_keys = np.zeros((1, nk), np.uint8)
+    last_press = np.full((1, nk), -cfg["key_press_delay"], np.float64)
+    yaw = np.array([90.0])
+    tl = cfg["time_limit"]
+    for t in range(g[f"{tag}_keys"].shape[0]):
+        now = (np.float32(tl) - np.float32(g[f"{tag}_time_remaining"][t])).astype(np.float64)
+        assert np.float64(tl) - (np.float64(tl) - now) == now
+        y, sm, fm, jp = qo.decode(cfg, last_keys, last_press, yaw, g[f"{tag}_keys"][t][None],
+                                  np.array([np.float64(g[f"{tag}_mouse"][t])]),
+                                  np.float32(g[f"{tag}_velocity"][t][2])[None], np.array([tl - now]))
+        assert y[0] * (np.pi / 180) == g[f"{tag}_move_yaw"][t]
+        assert sm[0] == g[f"{tag}_move_side"][t] and fm[0] == g[f"{tag}_move_forward"][t]
+        assert (2 if jp[0] else 0) == g[f"{tag}_move_buttons"][t]
+        yaw = y
+    assert np.array_equal(last_press, g[f"{tag}_final_last_press"])
+
+
 def test_philox_known_answer():
     """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
     assert qo.philox4x32(0, 0, 0, 0, 0, 0) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
