@@ -249,6 +249,29 @@ def run_cuda_arm(args, rank, world, local_rank):
     elapsed_ms = float(t.item())
     value = world * n * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- what a plain device-to-device copy achieves under the same launch pattern (same traffic per
+    # launch, ring of buffers so that nothing stays in L2, back-to-back launches): the practical
+    # ceiling at this launch size, reported beside the roofline (the peak itself is reached only by
+    # launches that move gigabytes)
+    copy_gbs = None
+    if rank == 0:
+        half = (2 * envs[0].info.state_bytes_per_env + nk + 34) * n // 2
+        csrc = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(ring)]
+        cdst = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(ring)]
+        for i in range(100):
+            cdst[i % ring].copy_(csrc[i % ring])
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        csteps = 2000
+        c0.record(stream)
+        for i in range(csteps):
+            cdst[i % ring].copy_(csrc[i % ring])
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        copy_gbs = 2 * half * csteps / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del csrc, cdst
+    barrier()
+
     # ---- e2e: the public API with host arrays (page-locked), copies inside the timed region
     e = envs[0]
     h_keys = e.pinned_empty((n, nk), np.uint8)
@@ -342,7 +365,11 @@ def run_cuda_arm(args, rank, world, local_rank):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "kernel": "k_step_tma",
-                         "bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src},
+                         "bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src,
+                         "same_size_copy_gbs": copy_gbs,
+                         "same_size_copy_note": "torch D2D copy_ moving the same bytes per launch, same ring, "
+                                                "timed live in this run: what any kernel launched at this size "
+                                                "can reach"},
             "clocks": clocks.summary(),
             "config4_rollout": {"value": rollout_value, "unit": UNIT, "envs_per_gpu": n4, "ticks": ticks4,
                                 "policy": "scripted strafe_jump generated on the device",
