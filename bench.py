@@ -184,14 +184,18 @@ class ClockSampler:
 def run_cuda_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from q1physrl_b200 import _lib, env as benv
+    from q1physrl_b200 import _lib, env as benv, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the movement step has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        # one process per GPU: run it (and first-touch its page-locked buffers) on the CPUs next to
+        # that GPU, so that the e2e leg's PCIe traffic does not cross the socket interconnect
+        numa = sharding.bind_to_device_cpus(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.envs
@@ -298,7 +302,7 @@ def run_cuda_arm(args, rank, world, local_rank):
     # ---- BASELINE config 5 + the one collective of this path: zero_start_total_reward_mean of the
     # reference's shipped policy (data/checkpoints/wr, weights in tests/golden/wr_policy.npz), rolled
     # out closed-loop on the device over 32768 envs per GPU (262144 over 8), metric all-reduced.
-    from q1physrl_b200 import policy as bpolicy, sharding
+    from q1physrl_b200 import policy as bpolicy
     policy_path = os.path.join(ROOT, "tests", "golden", "wr_policy.npz")
     n5, ticks5 = 1 << 15, 1500
     if os.path.exists(policy_path):
@@ -358,7 +362,7 @@ def run_cuda_arm(args, rank, world, local_rank):
                        "launch": "one q1_step call (k_step_tma launch, programmatic dependent launch) per "
                                  "step on torch's current stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "cpu_affinity": numa,
                     "api": "VectorPhysEnv.vector_step((keys, mouse)) with page-locked NumPy arrays: q1_step_host "
                            "launches the step kernel on the mapped host buffers (actions read and results "
                            "written over PCIe inside the launch), then synchronises"},

@@ -33,6 +33,33 @@ def make_sharded_env(config, rank: int, world_size: int, device: int = 0, seed: 
     return benv.VectorPhysEnv(local, device=device, seed=seed, env_index_base=start, **kwargs)
 
 
+def bind_to_device_cpus(device: int = 0) -> Optional[str]:
+    """Pin the calling process to the CPUs NVML reports as local to CUDA device `device` (same NUMA
+    node / PCIe root), so that page-locked buffers allocated afterwards are first-touched next to
+    the GPU that will read and write them.  One process per GPU calls this once at start-up.  Returns
+    a description of the affinity set, or None when NVML or the topology information is missing (the
+    process is then left as it is)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        pci = f"{torch.cuda.get_device_properties(device).pci_domain_id:08x}:{bus:02x}:" \
+              f"{torch.cuda.get_device_properties(device).pci_device_id:02x}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(pci.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs local to GPU {pci}"
+    except Exception:
+        return None
+
+
 _SUM_KEYS = ("zero_start_total_reward_sum", "zero_start_episodes", "episode_reward_sum", "episodes")
 
 
