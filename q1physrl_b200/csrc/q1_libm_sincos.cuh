@@ -114,22 +114,16 @@ constexpr uint32_t kHiReduce = 0x419921FBu;  /* |x| < 105414350: reduce_sincos *
 
 struct TabEntry { double sn, ssn, cs, ccs; };
 
-/* table entry k (k <= 109 for every argument the paths below produce).  `tab` = 0: the table in
- * global memory, read through L1; otherwise the shared-memory address of a CTA-local copy. */
-Q1LIBM_FN TabEntry lookup(uint32_t tab, uint32_t k)
+/* table entry k (k <= 109 for every argument the paths below produce).  The table (3.5 KB) stays in
+ * global memory and is read through L1; a copy in shared memory was measured 2 % slower. */
+Q1LIBM_FN TabEntry lookup(uint32_t k)
 {
     TabEntry e;
 #if defined(__CUDACC__)
-    if (tab) {
-        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.sn), "=d"(e.ssn) : "r"(tab + 32u * k));
-        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.cs), "=d"(e.ccs) : "r"(tab + 32u * k + 16u));
-    } else {
-        /* one 32-byte entry = one sector = one 256-bit load (sm_100: LDG.E.256) */
-        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-            : "=d"(e.sn), "=d"(e.ssn), "=d"(e.cs), "=d"(e.ccs) : "l"(kTab + 4 * k));
-    }
+    /* one 32-byte entry = one sector = one 256-bit load (sm_100: LDG.E.256) */
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+        : "=d"(e.sn), "=d"(e.ssn), "=d"(e.cs), "=d"(e.ccs) : "l"(kTab + 4 * k));
 #else
-    (void)tab;
     e.sn = kTab[4 * k]; e.ssn = kTab[4 * k + 1]; e.cs = kTab[4 * k + 2]; e.ccs = kTab[4 * k + 3];
 #endif
     return e;
@@ -146,7 +140,7 @@ Q1LIBM_FN TabEntry lookup(uint32_t tab, uint32_t k)
  *                                                         cos when (n + 1) & 2
  * The direct range is the reduction with xn forced to 0 (then y = t2 = b = x, db = 0, n = 0 come
  * out of the same operations exactly). */
-Q1LIBM_FN bool sincos(double x, double &sin_out, double &cos_out, uint32_t tab = 0)
+Q1LIBM_FN bool sincos(double x, double &sin_out, double &cos_out)
 {
     const uint32_t hx = f_hi(x);
     const uint32_t k = hx & 0x7fffffffu;
@@ -199,8 +193,8 @@ Q1LIBM_FN bool sincos(double x, double &sin_out, double &cos_out, uint32_t tab =
     const uint32_t ck = f_lo(cu);
     /* (the two entries are the same one except in the fold range when |tf| and |af| round to
      * different nodes; two unconditional loads are cheaper than the test and the register copies) */
-    const TabEntry tc = lookup(tab, ck);
-    const TabEntry ts = lookup(tab, sk);
+    const TabEntry tc = lookup(ck);
+    const TabEntry ts = lookup(sk);
 
     const double sxx = f_mul(sr, sr);
     const double ss = f_add(sr, f_fma(f_mul(sr, sxx), f_fma(sxx, kC[C_SN5], kC[C_SN3]), sd));

@@ -288,9 +288,9 @@ __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
 /* sin and cos of a (radians) with the bits np.sin / np.cos return in the reference (phys:58-59,
  * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh.  Beyond its main range
  * (|a| >= 105414350, yaw past 6e9 degrees) libdevice's sincos answers instead. */
-__device__ __forceinline__ void sincos_ref(double a, double &s, double &c, uint32_t tab = 0)
+__device__ __forceinline__ void sincos_ref(double a, double &s, double &c)
 {
-    if (__builtin_expect(!q1libm::sincos(a, s, c, tab), 0))
+    if (__builtin_expect(!q1libm::sincos(a, s, c), 0))
         sincos(a, &s, &c);
 }
 
@@ -457,7 +457,7 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
  * hover, reward = y velocity) is compiled in; otherwise those switches are read from Params. */
 template <bool STAMPS, bool LEAN, bool COMMON>
 __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, double mouse,
-                                     float &reward, bool &done, uint32_t sincos_tab = 0)
+                                     float &reward, bool &done)
 {
     const bool hover = COMMON ? false : (bool)P.hover;
     const bool allow_yaw = COMMON ? true : (bool)P.allow_yaw;
@@ -538,9 +538,9 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
         if (Q1_POLY_SINCOS)
             sincos_rad(a, sy, cy);
         else
-            sincos_ref(a, sy, cy, sincos_tab);
+            sincos_ref(a, sy, cy);
     } else {
-        sincos_ref(div64(mul64(e.yaw, kPi), 180.0), sy, cy, sincos_tab);
+        sincos_ref(div64(mul64(e.yaw, kPi), 180.0), sy, cy);
     }
     bool og = e.bits & F_ON_GROUND, jr = e.bits & F_JUMP_RELEASED;
     move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,

@@ -328,10 +328,6 @@ constexpr int kOutStages = 2;
 #ifndef Q1_PASSTHROUGH
 #define Q1_PASSTHROUGH 0
 #endif
-/* 1: k_step_tma keeps a copy of the libm sin/cos table (3.5 KB) in shared memory */
-#ifndef Q1_SMEM_TABLE
-#define Q1_SMEM_TABLE 0
-#endif
 
 template <bool TRACK, bool LEAN, bool COMMON>
 __global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
@@ -344,14 +340,6 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
     __shared__ __align__(128) unsigned char in_mem[kInStages * IN_BYTES];
     __shared__ __align__(128) unsigned char out_mem[kOutStages * OUT_BYTES];
     __shared__ __align__(8) uint64_t full_bar[kInStages];
-#if Q1_SMEM_TABLE
-    __shared__ __align__(32) double sincos_tab[440];   /* CTA-local copy of the libm sin/cos table */
-    for (int k = threadIdx.x; k < 440; k += kBlock)
-        sincos_tab[k] = q1libm::kTab[k];                /* constant data: no dependency on earlier grids */
-    const uint32_t tab = smem_addr(sincos_tab);
-#else
-    const uint32_t tab = 0;
-#endif
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
     const bool issuer = (tid & 31u) == 0;
@@ -433,7 +421,7 @@ k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
             r = e.vx + (float)m;
             d = keybits == 0xffu;
         } else {
-            tick<false, LEAN, COMMON>(P, e, keybits, m, r, d, tab);
+            tick<false, LEAN, COMMON>(P, e, keybits, m, r, d);
         }
         const bool zs = e.bits & F_ZERO_START;
         bool finished = false;
