@@ -311,14 +311,14 @@ def run_cuda_arm(args, rank, world, local_rank):
         tracked = benv.VectorPhysEnv(cfg5, device=local_rank, seed=args.seed,
                                      env_index_base=rank * n5, track_returns=True)
         torch.cuda.synchronize(dev)
-        t5 = time.perf_counter()
-        bpolicy.rollout(tracked, pol, ticks5)
+        timing5 = {}
+        bpolicy.rollout(tracked, pol, ticks5, timing=timing5)
         torch.cuda.synchronize(dev)
-        t5 = time.perf_counter() - t5
+        rate5 = world * n5 * timing5["ticks"] / timing5["seconds"] if timing5.get("seconds") else float("nan")
         policy_desc = (f"reference checkpoint data/checkpoints/wr (stochastic Q1PhysActionDist), params.json "
                        f"env_config, {n5} envs/GPU x {ticks5} ticks closed loop on the device (fused tcgen05 "
-                       f"policy kernel + step kernel in a CUDA graph), "
-                       f"{world * n5 * ticks5 / t5:.3e} env-steps/s incl. the policy")
+                       f"policy kernel + step kernel, 8 ticks per CUDA graph), "
+                       f"{rate5:.3e} env-steps/s incl. the policy (replays timed with CUDA events)")
     else:
         tracked = benv.VectorPhysEnv(workload_config(n5), device=local_rank, seed=args.seed,
                                      env_index_base=rank * n5, track_returns=True)

@@ -139,14 +139,15 @@ class FusedMLPPolicy(MLPPolicy):
         return out
 
 
-def rollout(env, policy, ticks, deterministic=False, graph=True):
+def rollout(env, policy, ticks, deterministic=False, graph=True, ticks_per_graph=8, timing=None):
     """Closed loop on the device: policy -> `step_tensors` (fused auto-reset) for `ticks` ticks.
     Returns the last (obs, reward, done, zero_start) tensors; with `track_returns` the episode
     statistics accumulate in `env.metrics()`.
 
-    graph=True captures one tick (three GEMMs, sampling, the step kernel) in a CUDA graph and
-    replays it: the loop is launch-bound otherwise.  The sampling noise advances through a device
-    counter, so replays draw fresh actions."""
+    graph=True captures `ticks_per_graph` ticks (policy kernel, noise counter, step kernel each) in
+    one CUDA graph and replays it: the loop is launch-bound otherwise.  The sampling noise advances
+    through a device counter, so replays draw fresh actions.  `timing`: a dict that receives
+    `ticks` and `seconds` of the replayed part, timed with CUDA events (capture excluded)."""
     torch = policy._torch
     ticks = int(ticks)
     dev = policy.device
@@ -174,12 +175,22 @@ def rollout(env, policy, ticks, deterministic=False, graph=True):
             for _ in range(3):          # warm up allocators / cuBLAS workspaces outside the capture
                 tick()
         torch.cuda.current_stream(dev).wait_stream(side)
+        per = max(1, min(int(ticks_per_graph), ticks - 3))
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            tick()
-        for _ in range(ticks - 4):
+            for _ in range(per):
+                tick()
+        replays = (ticks - 3) // per      # the capture itself executes nothing
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
             g.replay()
+        e1.record()
+        for _ in range(ticks - 3 - replays * per):
+            tick()
         torch.cuda.current_stream(dev).synchronize()
+        if timing is not None:
+            timing.update(ticks=replays * per, seconds=e0.elapsed_time(e1) * 1e-3)
     finally:
         policy.step_count = int(policy._step_dev.item())
         policy._step_dev = None
