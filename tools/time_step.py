@@ -18,7 +18,8 @@ steps, warmup = max(500, 8000 * (1 << 20) // n), 200
 dev = torch.device("cuda", 0)
 cfg = bench.workload_config(n)
 lib = _lib.load()
-envs = [benv.VectorPhysEnv(cfg, device=0, seed=r, env_index_base=r * n) for r in range(ring)]
+stamps = bool(int(os.environ.get("Q1_TIME_STAMPS", "0")))   # 1: f64 key stamps -> the plain k_step kernel
+envs = [benv.VectorPhysEnv(cfg, device=0, seed=r, env_index_base=r * n, f64_key_stamps=stamps) for r in range(ring)]
 nk = envs[0].info.num_keys
 g = torch.Generator(device=dev).manual_seed(0)
 keys = [torch.randint(0, 2, (n, nk), generator=g, device=dev, dtype=torch.uint8) for _ in range(ring)]
