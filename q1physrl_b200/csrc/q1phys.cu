@@ -508,6 +508,10 @@ k_step(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
        float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ zero_start,
        int auto_reset, int64_t first, int64_t end)
 {
+    /* same protocol as k_step_tma: let the next launch stage itself, touch global memory only after
+     * every earlier launch has completed (no-ops when launched without the attribute) */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t i = first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = i < end;
     bool finished = false, zs = false;
@@ -1387,6 +1391,10 @@ static int step_range(q1_env *env, const uint8_t *keys, const void *mouse, int m
         aligned16(reward) && aligned16(done) &&
         (!zero_start || aligned16(zero_start)) && (!env->P.allow_yaw || aligned16(mouse)))
         tile_end = end / kBlock;
+    /* a ragged tail costs a second launch (~5 us after the first); below 2^18 envs one launch of the
+     * plain kernel over everything is the faster way to serve it */
+    if (tile_end > tile_begin && end % kBlock != 0 && tile_end - tile_begin < 2048)
+        tile_end = tile_begin;
     int rc = Q1_OK;
     if (tile_end > tile_begin) {
         /* the compiled-in configuration: continuous f32 mouse action, no hover, y-velocity reward */
@@ -1426,10 +1434,22 @@ static int step_range(q1_env *env, const uint8_t *keys, const void *mouse, int m
     const int64_t first = tile_end > tile_begin ? tile_end * kBlock : begin;
     if (rc == Q1_OK && first < end)
         rc = dispatch(env, [&](auto st, auto tr, auto ln) {
-            k_step<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
-                <<<grid_for(end - first), kBlock, 0, s>>>(env->P, keys, mouse, mouse_kind, obs,
-                                                         reward, done, zero_start, auto_reset, first,
-                                                         end);
+            /* launched as a programmatic dependent as well: after a TMA launch only its execution,
+             * not its launch latency, is added to the tick (it waits for that launch to complete) */
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid_for(end - first));
+            cfg.blockDim = dim3(kBlock);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = env->pdl ? 1 : 0;
+            cudaError_t err = cudaLaunchKernelEx(
+                &cfg, k_step<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>, env->P, keys,
+                mouse, mouse_kind, obs, reward, done, zero_start, auto_reset, first, (int64_t)end);
+            if (err != cudaSuccess)
+                return fail(Q1_ECUDA, std::string("k_step launch: ") + cudaGetErrorString(err));
             return check_launch("k_step");
         });
     return rc;
