@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs", type=int, default=NUM_ENVS, help="envs per GPU")
     ap.add_argument("--ring", type=int, default=4, help="env shards ticked round-robin (L2 eviction)")
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

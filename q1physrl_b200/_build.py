@@ -54,5 +54,30 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+FASTFIX_SRC = os.path.join(_HERE, "csrc", "fastfix.c")
+
+
+def fastfix_path():
+    import sysconfig
+    return os.path.join(_HERE, "_fastfix" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_fastfix(force=False):
+    """Compile the CPython extension `q1physrl_b200._fastfix` (host-side normalisation of RLLib's
+    nested action format, csrc/fastfix.c) in-tree with the C compiler; returns its path, or None when
+    no compiler / Python headers are available (env.py then uses its NumPy route)."""
+    import sysconfig
+    out = fastfix_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(FASTFIX_SRC):
+        return out
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    include = sysconfig.get_paths().get("include")
+    if not cc or not include or not os.path.exists(os.path.join(include, "Python.h")):
+        return None
+    subprocess.run([cc, "-O2", "-shared", "-fPIC", "-I", include, FASTFIX_SRC, "-o", out], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_fastfix(force=True))

@@ -1,0 +1,150 @@
+/*
+ * fastfix.c -- CPython extension `q1physrl_b200._fastfix`: the reference's ActionDecoder._fix_actions
+ * (q1physrl_env/env.py:221-223) without the interpreter in the inner loop.
+ *
+ * RLLib hands VectorPhysEnv.vector_step a list of N per-env tuples whose nk+1 elements are Python /
+ * NumPy scalars or 1-element arrays; the reference normalises them with a Python double loop and
+ * np.ravel per element, which is 94 % of its vector_step wall time.  This
+ * walks the same nested sequence in C and writes the (N, width) float64 array the decoder consumes:
+ * element value = the first item of the flattened element, converted to double -- what
+ * np.array([[np.ravel(x)[0] for x in a] for a in actions], dtype=float64) yields.
+ *
+ *   fix_actions(actions, width, out) -> None      out: writable C-contiguous float64 buffer (N*width)
+ *
+ * Raises (TypeError / ValueError) for anything it does not recognise; the caller then takes the
+ * reference's own element-wise route, which produces the reference's own error behaviour.
+ * Plain CPython API + the buffer protocol; no NumPy headers needed.
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+#include <string.h>
+
+/* first element of a buffer-protocol object (NumPy arrays and NumPy scalars), as double */
+static int first_of_buffer(PyObject *obj, double *out)
+{
+    Py_buffer view;
+    if (PyObject_GetBuffer(obj, &view, PyBUF_FORMAT | PyBUF_ND | PyBUF_STRIDES) != 0) {
+        PyErr_Clear();
+        return -1;
+    }
+    int rc = -1;
+    if (view.len >= view.itemsize && view.itemsize > 0 && view.buf) {
+        const char *f = view.format ? view.format : "B";
+        while (*f == '@' || *f == '=' || *f == '<' || *f == '|')   /* native / little-endian only */
+            f++;
+        const void *p = view.buf;   /* row-major first element is at the base address */
+        rc = 0;
+        if (f[0] && f[1] == '\0') {
+            switch (f[0]) {
+            case 'd': { double v; memcpy(&v, p, 8); *out = v; break; }
+            case 'f': { float v; memcpy(&v, p, 4); *out = (double)v; break; }
+            case 'e': rc = -1; break;                                  /* float16: let NumPy do it */
+            case '?': *out = *(const unsigned char *)p ? 1.0 : 0.0; break;
+            case 'b': *out = (double)*(const signed char *)p; break;
+            case 'B': *out = (double)*(const unsigned char *)p; break;
+            case 'h': { int16_t v; memcpy(&v, p, 2); *out = (double)v; break; }
+            case 'H': { uint16_t v; memcpy(&v, p, 2); *out = (double)v; break; }
+            case 'i': { int32_t v; memcpy(&v, p, 4); *out = (double)v; break; }
+            case 'I': { uint32_t v; memcpy(&v, p, 4); *out = (double)v; break; }
+            case 'l': if (view.itemsize == 8) { int64_t v; memcpy(&v, p, 8); *out = (double)v; }
+                      else { int32_t v; memcpy(&v, p, 4); *out = (double)v; } break;
+            case 'L': if (view.itemsize == 8) { uint64_t v; memcpy(&v, p, 8); *out = (double)v; }
+                      else { uint32_t v; memcpy(&v, p, 4); *out = (double)v; } break;
+            case 'q': { int64_t v; memcpy(&v, p, 8); *out = (double)v; break; }
+            case 'Q': { uint64_t v; memcpy(&v, p, 8); *out = (double)v; break; }
+            default: rc = -1;
+            }
+        } else {
+            rc = -1;
+        }
+    }
+    PyBuffer_Release(&view);
+    return rc;
+}
+
+static int element_value(PyObject *x, double *out)
+{
+    if (PyFloat_CheckExact(x)) {
+        *out = PyFloat_AS_DOUBLE(x);
+        return 0;
+    }
+    if (PyLong_CheckExact(x) || PyBool_Check(x)) {
+        double v = PyLong_AsDouble(x);
+        if (v == -1.0 && PyErr_Occurred())
+            return -1;
+        *out = v;
+        return 0;
+    }
+    if (PyObject_CheckBuffer(x) && first_of_buffer(x, out) == 0)
+        return 0;
+    if (PyList_Check(x) || PyTuple_Check(x)) {       /* nested sequence: np.ravel(x)[0] is its first leaf */
+        if (PySequence_Fast_GET_SIZE(x) < 1) {
+            PyErr_SetString(PyExc_ValueError, "empty action element");
+            return -1;
+        }
+        return element_value(PySequence_Fast_GET_ITEM(x, 0), out);
+    }
+    PyObject *f = PyNumber_Float(x);                  /* anything else that knows how to be a float */
+    if (!f)
+        return -1;
+    *out = PyFloat_AS_DOUBLE(f);
+    Py_DECREF(f);
+    return 0;
+}
+
+static PyObject *fix_actions(PyObject *self, PyObject *args)
+{
+    PyObject *actions, *out_obj;
+    Py_ssize_t width;
+    if (!PyArg_ParseTuple(args, "OnO", &actions, &width, &out_obj))
+        return NULL;
+    PyObject *outer = PySequence_Fast(actions, "actions must be a sequence of per-env action tuples");
+    if (!outer)
+        return NULL;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(outer);
+    Py_buffer out;
+    if (PyObject_GetBuffer(out_obj, &out, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) != 0) {
+        Py_DECREF(outer);
+        return NULL;
+    }
+    PyObject *result = NULL;
+    if (width < 1 || out.len != (Py_ssize_t)(n * width * sizeof(double))) {
+        PyErr_SetString(PyExc_ValueError, "out must hold len(actions) * width float64 values");
+        goto done;
+    }
+    double *dst = (double *)out.buf;
+    for (Py_ssize_t i = 0; i < n; i++) {
+        PyObject *row = PySequence_Fast_GET_ITEM(outer, i);
+        if (!(PyTuple_Check(row) || PyList_Check(row))) {
+            PyErr_SetString(PyExc_TypeError, "each action must be a tuple or a list");
+            goto done;
+        }
+        if (PySequence_Fast_GET_SIZE(row) != width) {
+            PyErr_SetString(PyExc_ValueError, "action with an unexpected number of elements");
+            goto done;
+        }
+        for (Py_ssize_t j = 0; j < width; j++)
+            if (element_value(PySequence_Fast_GET_ITEM(row, j), dst + i * width + j) != 0) {
+                if (!PyErr_Occurred())
+                    PyErr_SetString(PyExc_TypeError, "unsupported action element");
+                goto done;
+            }
+    }
+    result = Py_None;
+    Py_INCREF(result);
+done:
+    PyBuffer_Release(&out);
+    Py_DECREF(outer);
+    return result;
+}
+
+static PyMethodDef methods[] = {
+    {"fix_actions", fix_actions, METH_VARARGS,
+     "fix_actions(actions, width, out): normalise RLLib's nested action format into the (N, width) "
+     "float64 buffer `out` (reference env.py:221-223)."},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_fastfix", NULL, -1, methods, NULL, NULL, NULL, NULL};
+
+PyMODINIT_FUNC PyInit__fastfix(void) { return PyModule_Create(&module); }

@@ -948,6 +948,8 @@ struct q1_env {
     cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *bounce = nullptr;      /* page-locked, device-mapped staging of q1_step_host for small batches */
+    size_t bounce_bytes = 0;
 };
 
 namespace {
@@ -1244,6 +1246,8 @@ int q1_destroy(q1_env *env)
     DeviceGuard guard(env->device);
     if (env->scratch)
         cudaFree(env->scratch);
+    if (env->bounce)
+        cudaFreeHost(env->bounce);
     if (env->host_stream)
         cudaStreamDestroy(env->host_stream);
     if (env->in_stream) {
@@ -1517,22 +1521,11 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
     size_t o_keys = 0, o_mouse = align_up(n * nk), o_obs = o_mouse + align_up(8 * n);
     size_t o_rew = o_obs + align_up(24 * n), o_done = o_rew + align_up(4 * n);
     size_t o_zs = o_done + align_up(n), total = o_zs + align_up(n);
-    int rc = ensure_scratch(env, total);
-    if (rc != Q1_OK)
-        return rc;
-    char *d = static_cast<char *>(env->scratch);
-    uint8_t *d_keys = reinterpret_cast<uint8_t *>(d + o_keys);
-    char *d_mouse = d + o_mouse;
-    float *d_obs = reinterpret_cast<float *>(d + o_obs), *d_rew = reinterpret_cast<float *>(d + o_rew);
-    uint8_t *d_done = reinterpret_cast<uint8_t *>(d + o_done);
-    uint8_t *d_zs = zero_start ? reinterpret_cast<uint8_t *>(d + o_zs) : nullptr;
+    if (!env->host_stream)
+        Q1_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
     cudaStream_t s = env->host_stream;
+    int rc = Q1_OK;
 
-    /* Large batches in page-locked memory run as a pipeline over env chunks: the action upload of
-     * chunk c+1, the tick of chunk c and the result download of chunk c-1 overlap (the two PCIe
-     * directions are independent copy engines), so a step costs about max(H2D, D2H), not the sum. */
-    constexpr int kMaxChunks = 8;
-    int chunks = 1;
     const bool all_pinned = is_pinned(keys) && is_pinned(obs) && is_pinned(reward) && is_pinned(done) &&
                             (!env->P.allow_yaw || is_pinned(mouse)) && (!zero_start || is_pinned(zero_start));
     if (all_pinned && env->host_direct && n >= (size_t)1 << 12) {
@@ -1545,17 +1538,67 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
         float *m_obs = device_view(obs), *m_rew = device_view(reward);
         uint8_t *m_done = device_view(done), *m_zs = zero_start ? device_view(zero_start) : nullptr;
         if (m_keys && m_obs && m_rew && m_done && (!env->P.allow_yaw || m_mouse) && (!zero_start || m_zs)) {
-            if (!env->host_stream)
-                Q1_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
             rc = step_range(env, m_keys, m_mouse, mouse_kind, m_obs, m_rew, m_done, m_zs, auto_reset, 0,
-                            (int64_t)n, env->host_stream);
+                            (int64_t)n, s);
             if (rc != Q1_OK)
                 return rc;
-            Q1_CUDA(cudaStreamSynchronize(env->host_stream));
+            Q1_CUDA(cudaStreamSynchronize(s));
             env->ticks += 1;
             return Q1_OK;
         }
     }
+    if (!all_pinned && env->host_direct && n <= (size_t)1 << 16) {
+        /* Small batches in ordinary (pageable) memory -- RLLib's 100 envs per worker, the gym-style
+         * single env: seven staged cudaMemcpy calls cost far more than the tick.  Bounce through one
+         * page-locked, device-mapped buffer owned by the handle instead: two host memcpys in, ONE
+         * launch that reads and writes that buffer across PCIe, one synchronisation, four memcpys out. */
+        if (env->bounce_bytes < total) {
+            if (env->bounce)
+                cudaFreeHost(env->bounce);
+            env->bounce = nullptr;
+            env->bounce_bytes = 0;
+            Q1_CUDA(cudaHostAlloc(&env->bounce, total, cudaHostAllocMapped));
+            env->bounce_bytes = total;
+        }
+        char *h = static_cast<char *>(env->bounce);
+        char *m = device_view(h);
+        if (m) {
+            std::memcpy(h + o_keys, keys, n * nk);
+            if (env->P.allow_yaw)
+                std::memcpy(h + o_mouse, mouse, mouse_size * n);
+            rc = step_range(env, reinterpret_cast<const uint8_t *>(m + o_keys), m + o_mouse, mouse_kind,
+                            reinterpret_cast<float *>(m + o_obs), reinterpret_cast<float *>(m + o_rew),
+                            reinterpret_cast<uint8_t *>(m + o_done),
+                            zero_start ? reinterpret_cast<uint8_t *>(m + o_zs) : nullptr, auto_reset, 0,
+                            (int64_t)n, s);
+            if (rc != Q1_OK)
+                return rc;
+            Q1_CUDA(cudaStreamSynchronize(s));
+            std::memcpy(obs, h + o_obs, 24 * n);
+            std::memcpy(reward, h + o_rew, 4 * n);
+            std::memcpy(done, h + o_done, n);
+            if (zero_start)
+                std::memcpy(zero_start, h + o_zs, n);
+            env->ticks += 1;
+            return Q1_OK;
+        }
+    }
+
+    rc = ensure_scratch(env, total);
+    if (rc != Q1_OK)
+        return rc;
+    char *d = static_cast<char *>(env->scratch);
+    uint8_t *d_keys = reinterpret_cast<uint8_t *>(d + o_keys);
+    char *d_mouse = d + o_mouse;
+    float *d_obs = reinterpret_cast<float *>(d + o_obs), *d_rew = reinterpret_cast<float *>(d + o_rew);
+    uint8_t *d_done = reinterpret_cast<uint8_t *>(d + o_done);
+    uint8_t *d_zs = zero_start ? reinterpret_cast<uint8_t *>(d + o_zs) : nullptr;
+
+    /* Large batches in page-locked memory with Q1PHYS_HOST_DIRECT=0 run as a pipeline over env
+     * chunks: the action upload of chunk c+1, the tick of chunk c and the result download of chunk
+     * c-1 overlap (the two PCIe directions are independent copy engines). */
+    constexpr int kMaxChunks = 8;
+    int chunks = 1;
     if (n >= (size_t)1 << 16 && all_pinned)
         chunks = env->host_chunks;
     if (chunks <= 1) {

@@ -121,6 +121,46 @@ def test_action_normalisation():
     assert k4.tolist() == [[1, 0, 1]] and m4 is None
 
 
+def test_fast_action_normalisation_equals_the_reference_expression():
+    """csrc/fastfix.c against the reference's own element-wise expression (env.py:221-223) on mixed
+    element kinds: Python ints / floats / bools, NumPy scalars of every width, 1-element arrays,
+    nested 1-element lists -- and against the unmodified reference method where it is mounted."""
+    from q1physrl_b200 import _build, env as benv
+    assert _build.build_fastfix() is not None and benv._fastfix is not None
+    rng = np.random.default_rng(4)
+    kinds = [int, float, bool, np.int8, np.uint8, np.int32, np.int64, np.uint64, np.float32, np.float64,
+             np.bool_, lambda v: np.array([v], np.float32), lambda v: np.array([v], np.int64),
+             lambda v: np.array([[v]], np.float64), lambda v: [v], lambda v: (float(v),)]
+    n, width = 257, 5
+    actions = []
+    for i in range(n):
+        row = []
+        for j in range(width):
+            if j < 4:
+                row.append(kinds[rng.integers(len(kinds))](int(rng.integers(0, 2))))
+            else:                                              # the mouse entry: float-capable kinds
+                fk = [k for k in kinds if k not in (int, bool, np.int8, np.uint8, np.int32, np.int64,
+                                                    np.uint64, np.bool_)]
+                fk = [k for k in fk if k is not kinds[12]]     # (the int64 1-array)
+                row.append(fk[rng.integers(len(fk))](float(np.float32(rng.uniform(-10, 10)))))
+        actions.append(tuple(row) if i % 2 else row)
+    want = np.array([[np.ravel(x)[0] for x in a] for a in actions], dtype=np.float64)
+    out = np.empty((n, width), np.float64)
+    benv._fastfix.fix_actions(actions, width, out)
+    assert np.array_equal(out, want)
+    assert np.array_equal(benv._fix_actions(actions, width), want)
+    for bad in ([(1, 2)], [(1, 2, 3, 4, "x")], [(1, 2, 3, 4, None)], [(1, 2, 3, 4, [])]):
+        with pytest.raises((TypeError, ValueError)):
+            benv._fastfix.fix_actions(bad, width, np.empty((1, width)))
+    with pytest.raises((TypeError, ValueError)):
+        benv._fastfix.fix_actions(actions, width, np.empty((n, width - 1)))
+    from oracle import refshim
+    if refshim.available():
+        ref_env, _ = refshim.load()
+        dec = ref_env.ActionDecoder(ref_env.Config.get_default())
+        assert np.array_equal(np.asarray(dec._fix_actions(actions), np.float64), want)
+
+
 def test_action_and_observation_spaces():
     from q1physrl_b200 import env as benv
     cfg = benv.Config.get_default()

@@ -74,6 +74,9 @@ CONFIGS = {
     "hover_nojump": dict(harness.PARAMS_100M, hover=True, allow_jump=False, key_press_delay=0.0),
     "integer_delay": dict(harness.PARAMS_100M, key_press_delay=0.25, time_delta=0.0125, time_limit=4.0),
     "noyaw": dict(harness.PARAMS_100M, allow_yaw=False, zero_start_prob=0.5),
+    # divisors whose rounded reciprocal is NOT good enough for the three-operation division
+    # (|RN(1/7.3) * 7.3 - 1| = 0.72 * 2^-53 > 2^-54): q1_create must fall back to IEEE division
+    "odd_divisors": dict(harness.PARAMS_100M, action_range=7.3, time_limit=7.3),
 }
 
 
