@@ -161,8 +161,9 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
  * With buffers from q1_host_alloc (or any page-locked, device-mapped memory) the step kernel itself
  * bulk-loads the actions from and bulk-stores the results to host memory, so both PCIe directions
  * run for the whole launch and a step costs max(H2D, D2H) of the wire (Q1PHYS_HOST_DIRECT=0 selects
- * the older chunked copy / tick / copy pipeline instead); pageable memory works too, through staging
- * copies at the driver's speed. */
+ * the older chunked copy / tick / copy pipeline instead).  Pageable memory works too: up to 65 536 envs
+ * bounce through one page-locked, device-mapped buffer owned by the handle (two memcpy in, one launch,
+ * four memcpy out); larger batches through staging copies at the driver's speed. */
 int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind, float *obs,
                  float *reward, uint8_t *done, uint8_t *zero_start, int auto_reset);
 

@@ -421,9 +421,10 @@ class VectorPhysEnv(VectorEnv):
 
     # ------------------------------------------------------------------ buffers
     def pinned_empty(self, shape, dtype):
-        """A page-locked NumPy array (freed with the env).  Actions handed to `vector_step` from
-        such arrays, together with `reuse_output_buffers`, let `q1_step_host` run its chunked
-        upload / tick / download pipeline by DMA."""
+        """A page-locked, device-mapped NumPy array (freed with the env).  With actions handed to
+        `vector_step` from such arrays and `reuse_output_buffers`, `q1_step_host` launches the step
+        kernel directly on the host buffers: no staging copies, both PCIe directions busy for the
+        whole launch."""
         return self._pinned.empty(shape, dtype)
 
     def _outputs(self):
