@@ -1528,7 +1528,7 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
 
     const bool all_pinned = is_pinned(keys) && is_pinned(obs) && is_pinned(reward) && is_pinned(done) &&
                             (!env->P.allow_yaw || is_pinned(mouse)) && (!zero_start || is_pinned(zero_start));
-    if (all_pinned && env->host_direct && n >= (size_t)1 << 12) {
+    if (all_pinned && env->host_direct) {
         /* Page-locked buffers are mapped into the device's address space: the step kernel bulk-loads
          * the actions from host memory and bulk-stores the results to host memory itself.  Both PCIe
          * directions then run concurrently for the whole launch, tile by tile, with no staging copy,
