@@ -367,14 +367,15 @@ def test_full_size_properties():
         assert np.array_equal(sa[f], sb[f]), f
 
 
+@pytest.mark.parametrize("n", [65536 * 3 + 300, 300], ids=["large", "small"])
 @pytest.mark.parametrize("mode", ["direct", "pipeline"])
-def test_host_pipeline_matches_single_shot(mode, monkeypatch):
+def test_host_pipeline_matches_single_shot(mode, n, monkeypatch):
     """q1_step_host with page-locked buffers either lets the step kernel read / write the mapped
     host buffers itself ("direct") or runs a chunked upload / tick / download pipeline; results must
-    equal the single-shot staging path (pageable arrays), ragged tail included."""
+    equal what pageable arrays give (HBM staging for the large batch, the page-locked bounce buffer
+    for the small one), ragged tail included."""
     from q1physrl_b200 import env as benv
     monkeypatch.setenv("Q1PHYS_HOST_DIRECT", "1" if mode == "direct" else "0")
-    n = 65536 * 3 + 300
     cfg = dict(harness.PARAMS_100M, num_envs=n, time_limit=1.0, zero_start_prob=0.5)
     a = benv.VectorPhysEnv(cfg, seed=5, reuse_output_buffers=True)
     b = benv.VectorPhysEnv(cfg, seed=5, reuse_output_buffers=False)
