@@ -50,3 +50,18 @@ def test_table_matches_high_precision_values():
             assert tab[k, off] == float(v)
             err = abs(mpmath.mpf(tab[k, off]) + mpmath.mpf(tab[k, off + 1]) - v)
             assert err <= mpmath.mpf(2) ** -100
+
+
+def test_numpy_sin_cos_are_the_c_library_ones():
+    """The premise of q1_libm_sincos.cuh: np.sin / np.cos on float64 (phys.py:58-59) return what the C
+    library's scalar sin / cos return on this platform (no SIMD float64 trigonometric loop in this
+    NumPy build).  If a NumPy upgrade changes that, the reference itself changes and this flags it."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from oracle import q1_oracle as qo
+    rng = np.random.default_rng(9)
+    x = np.concatenate([(rng.uniform(-8000, 8000, 400000) * np.pi) / 180.0, rng.uniform(-3, 3, 300000),
+                        rng.uniform(-1e5, 1e5, 300000)])
+    s, c = qo.sincos(x)
+    assert np.array_equal(np.sin(x).view(np.int64), s.view(np.int64))
+    assert np.array_equal(np.cos(x).view(np.int64), c.view(np.int64))
