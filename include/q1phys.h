@@ -267,6 +267,15 @@ int q1_policy_act(q1_policy *policy, int64_t n, const float *obs, double action_
  * Every count must be 0. */
 int q1_selftest_division(int device, uint64_t samples, uint64_t seed, uint64_t mismatches[8]);
 
+/* Exact checkpoint / resume (the reference env has none; RLLib's trainer.save() loses env state,
+ * train.py:119-133): the raw device image of the handle -- state blocks, key stamps, reset epochs,
+ * episode returns, metric accumulators -- plus its tick count and RNG key.  A handle created with
+ * the same config and flags that loads the image continues bit for bit like the one that saved it,
+ * resets included.  `bytes` from q1_snapshot_bytes. */
+int q1_snapshot_bytes(const q1_env *env, uint64_t *bytes);
+int q1_snapshot_save_host(q1_env *env, void *buffer, uint64_t bytes);
+int q1_snapshot_load_host(q1_env *env, const void *buffer, uint64_t bytes);
+
 /* sin and cos of n HOST doubles (radians) as the kernels compute them: glibc 2.39's __sin / __cos
  * (sysdeps/ieee754/dbl-64/s_sin.c, FMA build) restated on the device, i.e. the bits np.sin /
  * np.cos return in the reference (phys.py:58-59, env.py:475-476).  For parity tests. */

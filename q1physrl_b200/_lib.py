@@ -120,6 +120,9 @@ SIGNATURES = {
     "q1_policy_act": (c_int, [c_void_p, c_i64, c_void_p, c_double, c_double, c_int, c_u64, c_u64, c_void_p,
                               c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 8)]),
+    "q1_snapshot_bytes": (c_int, [c_void_p, ctypes.POINTER(c_u64)]),
+    "q1_snapshot_save_host": (c_int, [c_void_p, c_void_p, c_u64]),
+    "q1_snapshot_load_host": (c_int, [c_void_p, c_void_p, c_u64]),
     "q1_sincos_host": (c_int, [c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     "q1_decode_host": (c_int, [ctypes.POINTER(Q1Config), c_int, c_i64] + [c_void_p] * 10),
 }

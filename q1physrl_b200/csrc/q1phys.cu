@@ -1715,6 +1715,65 @@ int q1_observe_host(q1_env *env, float *obs_host)
 
 /* -- state copy-out / copy-in in the reference layout ----------------------------------------- */
 
+/* -- exact checkpoint / resume: the raw device image of a handle ------------------------------ */
+
+namespace {
+struct SnapshotHeader {
+    uint64_t magic, pool_bytes, ticks, seed, env_index_base;
+    int64_t n;
+    int32_t num_keys, stamps, track, abi;
+};
+constexpr uint64_t kSnapshotMagic = 0x51315048595353ull; /* "Q1PHYSS" */
+} // namespace
+
+int q1_snapshot_bytes(const q1_env *env, uint64_t *bytes)
+{
+    if (!env || !bytes)
+        return fail(Q1_EINVAL, "env / bytes is NULL");
+    *bytes = sizeof(SnapshotHeader) + env->pool_bytes;
+    return Q1_OK;
+}
+
+int q1_snapshot_save_host(q1_env *env, void *buffer, uint64_t bytes)
+{
+    if (!env || !buffer)
+        return fail(Q1_EINVAL, "env / buffer is NULL");
+    if (bytes < sizeof(SnapshotHeader) + env->pool_bytes)
+        return fail(Q1_EINVAL, "snapshot buffer too small (see q1_snapshot_bytes)");
+    DeviceGuard guard(env->device);
+    Q1_CUDA(cudaDeviceSynchronize());
+    SnapshotHeader h = {kSnapshotMagic, env->pool_bytes, env->ticks, env->P.seed, env->P.env_index_base,
+                        env->P.n, env->P.num_keys, env->stamps ? 1 : 0, env->track ? 1 : 0, Q1_ABI_VERSION};
+    std::memcpy(buffer, &h, sizeof h);
+    Q1_CUDA(cudaMemcpy(static_cast<char *>(buffer) + sizeof h, env->pool, env->pool_bytes,
+                       cudaMemcpyDeviceToHost));
+    return Q1_OK;
+}
+
+int q1_snapshot_load_host(q1_env *env, const void *buffer, uint64_t bytes)
+{
+    if (!env || !buffer)
+        return fail(Q1_EINVAL, "env / buffer is NULL");
+    SnapshotHeader h;
+    if (bytes < sizeof h)
+        return fail(Q1_EINVAL, "snapshot truncated");
+    std::memcpy(&h, buffer, sizeof h);
+    if (h.magic != kSnapshotMagic || h.abi != Q1_ABI_VERSION)
+        return fail(Q1_EINVAL, "not a libq1phys snapshot of this ABI version");
+    if (h.n != env->P.n || h.num_keys != env->P.num_keys || h.stamps != (env->stamps ? 1 : 0) ||
+        h.track != (env->track ? 1 : 0) || h.pool_bytes != env->pool_bytes ||
+        bytes < sizeof h + h.pool_bytes)
+        return fail(Q1_EINVAL, "snapshot was taken from a handle with another size / key count / flags");
+    DeviceGuard guard(env->device);
+    Q1_CUDA(cudaDeviceSynchronize());
+    Q1_CUDA(cudaMemcpy(env->pool, static_cast<const char *>(buffer) + sizeof h, env->pool_bytes,
+                       cudaMemcpyHostToDevice));
+    env->ticks = h.ticks;
+    env->P.seed = h.seed;                      /* the reset stream continues where the snapshot left it */
+    env->P.env_index_base = h.env_index_base;
+    return Q1_OK;
+}
+
 int q1_get_state_host(q1_env *env, const q1_state_view *v)
 {
     if (!env || !v)

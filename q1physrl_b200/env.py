@@ -591,6 +591,23 @@ class VectorPhysEnv(VectorEnv):
             "episode_reward_max": m.return_max,
         }
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def snapshot(self) -> np.ndarray:
+        """The exact image of this env (state, key timers, reset epochs, episode returns, metric
+        accumulators, tick count, RNG key) as a uint8 array.  `restore` it into an env created with
+        the same config and flags and that env continues bit for bit like this one, resets included
+        -- the save/restore the reference env lacks (RLLib's trainer.save() drops env state)."""
+        nbytes = ctypes.c_uint64(0)
+        _lib.check(self._lib.q1_snapshot_bytes(self._handle, ctypes.byref(nbytes)))
+        buf = np.empty(nbytes.value, np.uint8)
+        _lib.check(self._lib.q1_snapshot_save_host(self._handle, _ptr(buf), nbytes.value))
+        return buf
+
+    def restore(self, snapshot: np.ndarray):
+        """Load an image produced by `snapshot()`."""
+        buf = np.ascontiguousarray(snapshot, np.uint8)
+        _lib.check(self._lib.q1_snapshot_load_host(self._handle, _ptr(buf), buf.size))
+
     # ------------------------------------------------------------------ state access
     def get_state(self, fields=_STATE_FIELDS) -> dict:
         """Snapshot of the full per-env state as NumPy arrays in the reference's layout."""

@@ -397,6 +397,44 @@ def test_host_pipeline_matches_single_shot(mode, n, monkeypatch):
     assert a.info.ticks == b.info.ticks == 80
 
 
+@pytest.mark.parametrize("stamps", [False, True], ids=["counters", "f64stamps"])
+def test_snapshot_restore_resumes_bit_for_bit(stamps):
+    """Checkpoint / resume: an env restored from `snapshot()` continues exactly like the env that took
+    it -- outputs of every later tick, resets (same draws), episode metrics and final state."""
+    from q1physrl_b200 import _lib, env as benv
+    n = 3000
+    cfg = dict(harness.PARAMS_100M, num_envs=n, time_limit=2.0, zero_start_prob=0.3)
+    a = benv.VectorPhysEnv(cfg, seed=21, env_index_base=777, track_returns=True, f64_key_stamps=stamps,
+                           reuse_output_buffers=False)
+    rng = np.random.default_rng(8)
+    for t in range(300):
+        a.vector_step(harness.random_actions(cfg, rng, n, 4), auto_reset=True)
+    image = a.snapshot()
+    actions = [harness.random_actions(cfg, rng, n, 4) for _ in range(450)]
+    want = [a.vector_step(act, auto_reset=True)[:3] for act in actions]
+    b = benv.VectorPhysEnv(cfg, seed=999, env_index_base=0, track_returns=True, f64_key_stamps=stamps,
+                           reuse_output_buffers=False)
+    b.restore(image)
+    assert b.info.ticks == 300
+    for t, act in enumerate(actions):
+        got = b.vector_step(act, auto_reset=True)[:3]
+        for x, y in zip(got, want[t]):
+            assert np.array_equal(x, y), t
+    sa, sb = a.get_state(), b.get_state()
+    for f in sa:
+        assert np.array_equal(sa[f], sb[f]), f
+    ma, mb = a.metrics(), b.metrics()
+    assert ma["episodes"] == mb["episodes"] > n and ma["zero_start_episodes"] == mb["zero_start_episodes"]
+    assert ma["episode_reward_max"] == mb["episode_reward_max"]
+    for k in ("episode_reward_sum", "zero_start_total_reward_sum"):   # f64 atomics: order-dependent last bits
+        assert abs(ma[k] - mb[k]) <= 1e-12 * abs(ma[k])
+    other = benv.VectorPhysEnv(dict(cfg, num_envs=n + 1), seed=1, track_returns=True, f64_key_stamps=stamps)
+    with pytest.raises(_lib.Q1Error):
+        other.restore(image)
+    with pytest.raises(_lib.Q1Error):
+        b.restore(image[:100])
+
+
 def test_phys_apply_float32_time_delta_golden():
     from q1physrl_b200 import phys
     g = harness.load_golden("phys_apply_dt32_n4096")
