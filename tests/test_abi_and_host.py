@@ -161,6 +161,17 @@ def test_fast_action_normalisation_equals_the_reference_expression():
         assert np.array_equal(np.asarray(dec._fix_actions(actions), np.float64), want)
 
 
+def test_cpu_binding_is_a_no_op_without_a_gpu():
+    """sharding.bind_to_device_cpus never raises: without NVML / a CUDA device it leaves the process
+    alone and says so."""
+    import os
+    from q1physrl_b200 import sharding
+    before = os.sched_getaffinity(0)
+    out = sharding.bind_to_device_cpus(0)
+    assert out is None or isinstance(out, str)
+    assert os.sched_getaffinity(0) <= before
+
+
 def test_action_and_observation_spaces():
     from q1physrl_b200 import env as benv
     cfg = benv.Config.get_default()
