@@ -54,8 +54,10 @@ def test_table_matches_high_precision_values():
 
 def test_numpy_sin_cos_are_the_c_library_ones():
     """The premise of q1_libm_sincos.cuh: np.sin / np.cos on float64 (phys.py:58-59) return what the C
-    library's scalar sin / cos return on this platform (no SIMD float64 trigonometric loop in this
-    NumPy build).  If a NumPy upgrade changes that, the reference itself changes and this flags it."""
+    library's scalar sin / cos return on this platform (this NumPy build has no SIMD float64 sin / cos
+    loop of its own -- checked on an AVX512 (Sapphire Rapids class) host, where such loops would be
+    dispatched if they existed).  If a NumPy upgrade changes that, the reference itself changes and
+    this flags it."""
     import sys
     sys.path.insert(0, os.path.join(HERE, ".."))
     from oracle import q1_oracle as qo
