@@ -11,6 +11,8 @@
  *   |x| < 2.426265          t = hp0 - |x|:  sin = do_cos(t, hp1),  cos = do_sin(t + hp1, tail)
  *   |x| < 105414350         x = n pi/2 + (a + da) by a four-constant Cody-Waite reduction
  *                           (reduce_sincos); quadrant n picks do_sin(a, da) / do_cos(a, da) and signs
+ *   larger finite |x|       the same with (n, a, da) from __branred (branred.c): x 2^-600 split in two
+ *                           26-bit pieces, each multiplied by 144 bits of 2/pi taken from a table
  *   do_sin / do_cos         x = xk + r with xk = k/128 from the 440-double table {sin, cos}(xk)
  *                           in two words each; short polynomials in r; angle-addition correction
  *   do_sin, |x| < 0.126     a degree-11 Taylor form instead of the table
@@ -21,7 +23,6 @@
  * instruction stream; tests/test_libm_sincos.py compares this header, compiled for the host, with
  * the installed libm on 2*10^8 arguments (uniform, log-uniform, around every branch threshold and
  * around multiples of pi/2), and tests/test_cuda_parity.py does the same for the device build.
- * Arguments of 105414350 or more (yaw beyond 6*10^9 degrees) take the platform's own sincos.
  *
  * The file compiles as CUDA (device, *_rn intrinsics: nothing the compiler may re-fuse) and as
  * plain C++ (host, for the CPU test: build with -ffp-contract=off).
@@ -50,6 +51,7 @@ Q1LIBM_FN double f_flip(double a, uint32_t sign_bit) /* a with its sign XORed by
     return __hiloint2double((int)(f_hi(a) ^ sign_bit), (int)f_lo(a));
 }
 Q1LIBM_FN double f_abs(double a) { return fabs(a); }
+Q1LIBM_FN double f_from_hi(uint32_t hi) { return __hiloint2double((int)hi, 0); }
 #else
 #define Q1LIBM_FN static inline
 #define Q1LIBM_TABLE static const double
@@ -66,11 +68,21 @@ Q1LIBM_FN double f_flip(double a, uint32_t sign_bit)
     double r; std::memcpy(&r, &u, 8); return r;
 }
 Q1LIBM_FN double f_abs(double a) { return std::fabs(a); }
+Q1LIBM_FN double f_from_hi(uint32_t hi)
+{
+    uint64_t u = (uint64_t)hi << 32;
+    double r; std::memcpy(&r, &u, 8); return r;
+}
 #endif
 
 /* glibc __sincostab: {sn, ssn, cs, ccs} for xk = k/128, k = 0..109 */
 Q1LIBM_TABLE kTab[440] = {
 #include "q1_libm_sincos_tab.inc"
+};
+
+/* glibc branred.h toverp[75]: the digits of 2/pi in base 2^24 */
+Q1LIBM_TABLE kToverp[75] = {
+#include "q1_libm_branred_tab.inc"
 };
 
 /* s_sin.c / usncs.h / trigo.h constants (values as stored in the library).  On the device they
@@ -129,8 +141,85 @@ Q1LIBM_FN TabEntry lookup(uint32_t k)
     return e;
 }
 
-/* sin(x) and cos(x) as __sin / __cos return them, for |x| < 105414350 (high word below
- * 0x419921FB).  Returns false (outputs untouched) for larger, infinite or NaN arguments.
+/* One half of __branred (branred.c): x1 (a 26-bit piece of x 2^-600) times 2/pi, integer part
+ * dropped, fraction as b + bb, integer part mod 4 kept in `sum`.  Plain multiplies and adds -- this
+ * file of glibc is built without FMA contraction even for the FMA variants of sin / cos. */
+Q1LIBM_FN void branred_half(double x1, double &b, double &bb, double &sum)
+{
+    const double big = 0x1.8p52, big1 = 0x1.8p54, tm24 = 0x1p-24;
+    int k = (int)((f_hi(x1) >> 20) & 2047u);
+    k = (k - 450) / 24;
+    if (k < 0)
+        k = 0;
+    /* gor = 2^576 with its exponent lowered by 24 k */
+    double gor = f_from_hi(0x63f00000u - ((uint32_t)(k * 24) << 20));
+    double r[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        r[i] = f_mul(f_mul(x1, kToverp[k + i]), gor);
+        gor = f_mul(gor, tm24);
+    }
+    sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double s = f_sub(f_add(r[i], big), big);       /* round to nearest integer */
+        sum = f_add(sum, s);
+        r[i] = f_sub(r[i], s);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        t = f_add(t, r[5 - i]);
+    bb = f_add(f_add(f_add(f_add(f_add(f_sub(r[0], t), r[1]), r[2]), r[3]), r[4]), r[5]);
+    double s = f_sub(f_add(t, big), big);
+    sum = f_add(sum, s);
+    t = f_sub(t, s);
+    b = f_add(t, bb);
+    bb = f_add(f_sub(t, b), bb);
+    s = f_sub(f_add(sum, big1), big1);
+    sum = f_sub(sum, s);
+}
+
+/* __branred (branred.c): x = n pi/2 + (a + aa) for |x| >= 105414350, n mod 4 returned */
+Q1LIBM_FN uint32_t branred(double x, double &a, double &aa)
+{
+    const double split = 134217729.0;                         /* 2^27 + 1 */
+    const double mp1 = 0x1.921fb58000000p+0, mp2 = -0x1.dde9740000000p-27;
+    x = f_mul(x, 0x1p-600);
+    double t = f_mul(x, split);                               /* split x into two numbers */
+    const double x1 = f_sub(t, f_sub(t, x));
+    const double x2 = f_sub(x, x1);
+    double b1, bb1, sum1, b2, bb2, sum2;
+    branred_half(x1, b1, bb1, sum1);
+    branred_half(x2, b2, bb2, sum2);
+    double sum = f_add(sum1, sum2);
+    double b = f_add(b1, b2);
+    double bb = f_abs(b1) > f_abs(b2) ? f_add(f_sub(b1, b), b2) : f_add(f_sub(b2, b), b1);
+    if (b > 0.5) {
+        b = f_sub(b, 1.0);
+        sum = f_add(sum, 1.0);
+    } else if (b < -0.5) {
+        b = f_add(b, 1.0);
+        sum = f_sub(sum, 1.0);
+    }
+    double s = f_add(b, f_add(f_add(bb, bb1), bb2));
+    t = f_add(f_add(f_sub(b, s), bb), f_add(bb1, bb2));
+    b = f_mul(s, split);
+    const double t1 = f_sub(b, f_sub(b, s));
+    const double t2 = f_sub(s, t1);
+    b = f_mul(s, kC[C_HP0]);
+    bb = f_add(f_add(f_add(f_sub(f_mul(t1, mp1), b), f_mul(t1, mp2)), f_mul(t2, mp1)),
+               f_add(f_add(f_mul(t2, mp2), f_mul(s, kC[C_HP1])), f_mul(t, kC[C_HP0])));
+    s = f_add(b, bb);
+    t = f_add(f_sub(b, s), bb);
+    a = s;
+    aa = t;
+    return (uint32_t)((int)sum) & 3u;
+}
+
+/* sin(x) and cos(x) as __sin / __cos return them, for every finite x (HUGE = false: only for
+ * |x| < 105414350; the per-tick kernels use that -- carrying the __branred code, even out of line,
+ * costs them 0.7 - 1.7 % -- and hand larger arguments, yaw past 6e9 degrees, to libdevice).  Returns false (outputs untouched) for larger, infinite or NaN arguments.
  *
  * In every range one do_sin and one do_cos evaluation serve both results; the ranges differ only
  * in the arguments handed to them and in which result goes where:
@@ -140,26 +229,33 @@ Q1LIBM_FN TabEntry lookup(uint32_t k)
  *                                                         cos when (n + 1) & 2
  * The direct range is the reduction with xn forced to 0 (then y = t2 = b = x, db = 0, n = 0 come
  * out of the same operations exactly). */
+template <bool HUGE = true>
 Q1LIBM_FN bool sincos(double x, double &sin_out, double &cos_out)
 {
     const uint32_t hx = f_hi(x);
     const uint32_t k = hx & 0x7fffffffu;
-    if (!(k < kHiReduce))
-        return false;
     const double ax = f_abs(x);
     const bool direct = k < kHiTable, fold = !direct & (k < kHiFold);
-
-    /* reduce_sincos */
-    double tq = f_fma(x, kC[C_HPINV], kC[C_TOINT]);
-    tq = direct ? kC[C_TOINT] : tq;
-    const double xn = f_sub(tq, kC[C_TOINT]);
-    const uint32_t n = f_lo(tq) & 3u;
-    const double y = f_fma(-xn, kC[C_MP2], f_fma(-xn, kC[C_MP1], x));
-    const double t2 = f_fma(-xn, kC[C_PP3], y);
-    const double db1 = f_fma(-kC[C_PP3], xn, f_sub(y, t2));
-    const double b = f_fma(-xn, kC[C_PP4], t2);
-    const double db2 = f_fma(-xn, kC[C_PP4], f_sub(t2, b));
-    const double db = f_add(db1, db2);
+    double b, db;
+    uint32_t n;
+    if (!(k < kHiReduce)) {
+        /* |x| >= 105414350: __branred, then the same do_sin / do_cos choice as the reduced range */
+        if (!HUGE || k >= 0x7ff00000u)
+            return false;
+        n = branred(x, b, db);
+    } else {
+        /* reduce_sincos */
+        double tq = f_fma(x, kC[C_HPINV], kC[C_TOINT]);
+        tq = direct ? kC[C_TOINT] : tq;
+        const double xn = f_sub(tq, kC[C_TOINT]);
+        n = f_lo(tq) & 3u;
+        const double y = f_fma(-xn, kC[C_MP2], f_fma(-xn, kC[C_MP1], x));
+        const double t2 = f_fma(-xn, kC[C_PP3], y);
+        const double db1 = f_fma(-kC[C_PP3], xn, f_sub(y, t2));
+        b = f_fma(-xn, kC[C_PP4], t2);
+        const double db2 = f_fma(-xn, kC[C_PP4], f_sub(t2, b));
+        db = f_add(db1, db2);
+    }
 
     /* fold around pi/2 */
     const double tf = f_sub(kC[C_HP0], ax);

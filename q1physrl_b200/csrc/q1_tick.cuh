@@ -286,11 +286,14 @@ __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
 }
 
 /* sin and cos of a (radians) with the bits np.sin / np.cos return in the reference (phys:58-59,
- * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh.  Beyond its main range
- * (|a| >= 105414350, yaw past 6e9 degrees) libdevice's sincos answers instead. */
+ * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh.  HUGE = true (phys.apply, the
+ * sweep, resets, q1_sincos_host): every finite argument; HUGE = false (the per-tick kernels): up to
+ * |a| < 105414350, i.e. yaw below 6e9 degrees -- beyond that, and for infinities / NaN, libdevice's
+ * sincos answers (accurate, NaN like libm, not necessarily the same last bit). */
+template <bool HUGE = true>
 __device__ __forceinline__ void sincos_ref(double a, double &s, double &c)
 {
-    if (__builtin_expect(!q1libm::sincos(a, s, c), 0))
+    if (__builtin_expect(!q1libm::sincos<HUGE>(a, s, c), 0))
         sincos(a, &s, &c);
 }
 
@@ -538,9 +541,9 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
         if (Q1_POLY_SINCOS)
             sincos_rad(a, sy, cy);
         else
-            sincos_ref(a, sy, cy);
+            sincos_ref<false>(a, sy, cy);
     } else {
-        sincos_ref(div64(mul64(e.yaw, kPi), 180.0), sy, cy);
+        sincos_ref<false>(div64(mul64(e.yaw, kPi), 180.0), sy, cy);
     }
     bool og = e.bits & F_ON_GROUND, jr = e.bits & F_JUMP_RELEASED;
     move_body<LEAN>(e.vx, e.vy, e.vz, e.z, og, jr, cy, sy, sy, -cy, fmove, smove, jump, P.dt,
@@ -587,7 +590,7 @@ __device__ __forceinline__ void reset_env(const Params &P, Env &e, uint64_t gidx
         angle = kPi / 2;
     }
     double sa, ca;
-    sincos_ref(angle, sa, ca);
+    sincos_ref<false>(angle, sa, ca);   /* angle in (1, 2 pi] */
     e.vx = __double2float_rn(mul64(speed, ca));
     e.vy = __double2float_rn(mul64(speed, sa));
     e.bits = F_JUMP_RELEASED | (zs ? F_ZERO_START : 0u); /* timers 0: every key may be pressed */

@@ -51,7 +51,7 @@ static void worker(uint64_t seed, uint64_t count, Tally *out)
         case 0: x = (unit(s) * 2 - 1) * 3.0; break;                       // the direct / fold ranges
         case 1: x = (unit(s) * 2 - 1) * 130.0; break;                     // an episode's yaw range
         case 2: x = (unit(s) * 2 - 1) * 1.0e5; break;
-        case 3: x = ldexp(unit(s) + 0.5, (int)(splitmix(s) % 60) - 32) * ((splitmix(s) & 1) ? 1 : -1); break;
+        case 3: x = ldexp(unit(s) + 0.5, (int)(splitmix(s) % 1080) - 56) * ((splitmix(s) & 1) ? 1 : -1); break;
         case 4: {                                                          // near a threshold, +-2^20 ulps
             double th = thresholds[splitmix(s) % (sizeof thresholds / sizeof *thresholds)];
             x = from_bits(to_bits(th) + (int64_t)(splitmix(s) % 2097152) - 1048576);
@@ -93,7 +93,8 @@ int main(int argc, char **argv)
     // every integer number of degrees an episode can start from, and the exact special values
     Tally sp;
     for (int d = -72000; d <= 72000; d++) check(((double)d * 3.14159265358979323846) / 180.0, sp);
-    const double specials[] = {0.0, -0.0, 0x1p-1022, 0x1p-1074, 0x1p-27, 0x1p-26, 0.126, 0.855469, 1.5707963267948966};
+    const double specials[] = {0.0, -0.0, 0x1p-1022, 0x1p-1074, 0x1p-27, 0x1p-26, 0.126, 0.855469, 1.5707963267948966,
+                               105414336.0, 105414350.0, 1e9, 1e22, 0x1p1023, 1.7976931348623157e308};
     for (double v : specials) { check(v, sp); check(-v, sp); }
     total.n += sp.n; total.bad += sp.bad;
     if (sp.bad && total.bad == sp.bad) total.first_bad = sp.first_bad;
