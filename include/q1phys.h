@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define Q1_ABI_VERSION 1
+#define Q1_ABI_VERSION 2
 
 enum {
     Q1_OK = 0,
@@ -176,6 +176,73 @@ int q1_host_free(void *ptr);
  * the per-env sum of rewards over the call, obs (n,6) the final observation; either may be NULL. */
 int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *obs,
                float *reward_sum, void *stream);
+
+/* -- trajectory recorder: q1physrl/analyse.py:197-240 `eval_sim`, N envs at once, on the device ----- */
+
+/* Where a recorded rollout takes its actions from. */
+enum {
+    Q1_ACTIONS_ARRAYS = 0,   /* caller arrays laid out [tick][env] (a scripted or pre-computed stream) */
+    Q1_ACTIONS_BUILTIN = 1   /* a built-in device-side policy (Q1_POLICY_*) */
+};
+typedef struct q1_action_source {
+    int32_t kind;             /* Q1_ACTIONS_* */
+    int32_t builtin_policy;   /* Q1_POLICY_*, kind BUILTIN */
+    uint64_t policy_seed;     /* kind BUILTIN */
+    const uint8_t *keys;      /* kind ARRAYS: (ticks, n, num_keys) u8, bit 0 = the key action */
+    const void *mouse;        /* kind ARRAYS: (ticks, n) of mouse_kind; may be NULL without allow_yaw */
+    int32_t mouse_kind;       /* Q1_MOUSE_* */
+    int32_t reserved;
+} q1_action_source;
+
+/* Per-tick record, every array [ticks][n] (tick-major, C order); any pointer may be NULL to skip that
+ * field.  Row t holds what analyse.py:214-229 appends in iteration t: the movement state
+ * (`e.player_state`, analyse.py:218), its time_remaining and the observation the policy saw
+ * (analyse.py:219) BEFORE the tick; the action (analyse.py:220); the move command ActionDecoder.map
+ * makes of it (analyse.py:215-216, 221-224); reward and done of the tick (analyse.py:226-228).
+ * Field widths are the reference's (EvalSimResult, analyse.py:71-82) except obs, which is f32 like
+ * every observation of this library. */
+typedef struct q1_record_view {
+    float   *vel;             /* (T,n,3) */
+    double  *z_pos;           /* (T,n)   */
+    uint8_t *on_ground;       /* (T,n)   */
+    uint8_t *jump_released;   /* (T,n)   */
+    double  *time_remaining;  /* (T,n)   */
+    float   *obs;             /* (T,n,6) */
+    uint8_t *keys;            /* (T,n,num_keys) */
+    float   *mouse;           /* (T,n)   the mouse action in the action space's dtype (env:214-215) */
+    double  *yaw;             /* (T,n)   */
+    int64_t *smove;           /* (T,n)   */
+    int64_t *fmove;           /* (T,n)   */
+    uint8_t *jump;            /* (T,n)   */
+    float   *reward;          /* (T,n)   */
+    uint8_t *done;            /* (T,n)   */
+} q1_record_view;
+
+/* record_flags */
+enum {
+    /* analyse.py:215-216 feeds its shadow ActionDecoder the OBSERVATION's z velocity (quantised and
+     * divided by 200, env:399-400) where the env's own decoder sees the raw one (env:487), so with
+     * auto_jump the `jump` it records is `obs[Z_VEL] <= 16`.  Set: record that value (EvalSimResult
+     * parity); clear: record the jump the env actually executed. */
+    Q1_RECORD_SHADOW_JUMP = 1u << 0
+};
+
+/* `ticks` consecutive vector_step calls in ONE launch (state in registers throughout), each tick's
+ * row written from the same tick routine that advances the env.  auto_reset = 0 is the reference's
+ * behaviour: an env whose episode ended keeps stepping with negative time_remaining (env:505-506)
+ * and the caller cuts its rows at the first done.  final_obs (n,6) or NULL receives the observation
+ * after the last tick.  DEVICE pointers in `actions` and `record`. */
+int q1_rollout_record(q1_env *env, const q1_action_source *actions, int ticks, int auto_reset,
+                      uint32_t record_flags, const q1_record_view *record, float *final_obs,
+                      void *stream);
+/* Same with HOST pointers in `actions`, `record` and final_obs_host; synchronises. */
+int q1_rollout_record_host(q1_env *env, const q1_action_source *actions, int ticks, int auto_reset,
+                           uint32_t record_flags, const q1_record_view *record, float *final_obs_host);
+
+/* Adds `delta` to the handle's tick counter (q1_env_info.ticks; the position of q1_rollout's built-in
+ * action streams).  For callers that replay a captured CUDA graph: the library counts a q1_step only
+ * when it is called, i.e. during capture, not when the graph is replayed. */
+int q1_advance_ticks(q1_env *env, int64_t delta);
 
 /* Observation of the current state without stepping (env:392-400). */
 int q1_observe(q1_env *env, float *obs, void *stream);

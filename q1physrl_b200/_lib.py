@@ -16,7 +16,9 @@ Q1_OK, Q1_EINVAL, Q1_ECUDA, Q1_ENODEV, Q1_ENOMEM = 0, -1, -2, -3, -4
 Q1_F_TRACK_RETURNS, Q1_F_FORCE_F64_STAMPS, Q1_F_IEEE_DIVISION = 1, 2, 4
 Q1_MOUSE_F32, Q1_MOUSE_I32, Q1_MOUSE_F64 = 0, 1, 2
 Q1_POLICY_RANDOM, Q1_POLICY_STRAFE_JUMP = 0, 1
-Q1_ABI_VERSION = 1
+Q1_ACTIONS_ARRAYS, Q1_ACTIONS_BUILTIN = 0, 1
+Q1_RECORD_SHADOW_JUMP = 1
+Q1_ABI_VERSION = 2
 
 
 class Q1Error(RuntimeError):
@@ -81,6 +83,19 @@ class Q1Metrics(ctypes.Structure):
     ]
 
 
+class Q1ActionSource(ctypes.Structure):
+    _fields_ = [("kind", c_i32), ("builtin_policy", c_i32), ("policy_seed", c_u64),
+                ("keys", c_void_p), ("mouse", c_void_p), ("mouse_kind", c_i32), ("reserved", c_i32)]
+
+
+RECORD_FIELDS = ("vel", "z_pos", "on_ground", "jump_released", "time_remaining", "obs", "keys",
+                 "mouse", "yaw", "smove", "fmove", "jump", "reward", "done")
+
+
+class Q1RecordView(ctypes.Structure):
+    _fields_ = [(name, c_void_p) for name in RECORD_FIELDS]
+
+
 # name -> (restype, argtypes); every symbol include/q1phys.h declares.
 SIGNATURES = {
     "q1_last_error": (c_char_p, []),
@@ -105,6 +120,11 @@ SIGNATURES = {
     "q1_host_alloc": (c_int, [c_u64, ctypes.POINTER(c_void_p)]),
     "q1_host_free": (c_int, [c_void_p]),
     "q1_rollout": (c_int, [c_void_p, c_int, c_int, c_u64, c_void_p, c_void_p, c_void_p]),
+    "q1_rollout_record": (c_int, [c_void_p, ctypes.POINTER(Q1ActionSource), c_int, c_int, c_u32,
+                                  ctypes.POINTER(Q1RecordView), c_void_p, c_void_p]),
+    "q1_rollout_record_host": (c_int, [c_void_p, ctypes.POINTER(Q1ActionSource), c_int, c_int, c_u32,
+                                       ctypes.POINTER(Q1RecordView), c_void_p]),
+    "q1_advance_ticks": (c_int, [c_void_p, c_i64]),
     "q1_observe": (c_int, [c_void_p, c_void_p, c_void_p]),
     "q1_get_state_host": (c_int, [c_void_p, ctypes.POINTER(Q1StateView)]),
     "q1_set_state_host": (c_int, [c_void_p, ctypes.POINTER(Q1StateView)]),

@@ -1,28 +1,47 @@
-"""The analysis helpers of `q1physrl/analyse.py` that touch the movement step, on the B200 env:
-`eval_sim` (single-env rollout recorder, analyse.py:197-240) and `EvalSimResult` with its derived
-arrays (analyse.py:71-118).  `hypothetical_delta_speeds` runs the whole (360, frames) sweep as ONE
-`k_delta_speed_sweep` launch (`q1_delta_speed_sweep_host`) instead of 360 `phys.apply` calls.
+"""The analysis entry points of `q1physrl/analyse.py` that touch the movement step, on the B200 env.
 
-Plotting (matplotlib / cv2), the .dem parser and the RLLib checkpoint loader are out of scope
-(SURVEY.md section 2, rows 6-9); any object with a `compute_action(obs)` method drives `eval_sim`.
+`eval_sim` (analyse.py:197-240) is a front end of the ON-DEVICE TRAJECTORY RECORDER
+(`q1_rollout_record`, include/q1phys.h): the kernel that advances the envs writes, per tick, the
+movement state and observation the policy saw, the action, the decoded move command, reward and
+done -- from the same `tick<>()` that steps the env, not from a shadow `ActionDecoder` plus state
+round trips.  Three ways to drive it, picked from what the `trainer` object offers:
+
+  * `trainer.action_script(num_ticks)` -> (keys (T, nk), mouse (T,)): an open-loop script; the whole
+    episode is ONE launch;
+  * `trainer.device_policy`: a `policy.FusedMLPPolicy`; the episode runs closed loop on the device;
+  * `trainer.compute_action(obs)` (RLLib's trainer API, the reference's only form): one recorder
+    launch per frame that records the frame and returns the next observation.
+
+`EvalSimResult` keeps the reference's fields and derived arrays (analyse.py:71-118);
+`hypothetical_delta_speeds` is one `k_delta_speed_sweep` launch instead of 360 `phys.apply` calls.
+`record_rollout` is the N-env form.  Plotting (matplotlib / cv2), the .dem parser and the RLLib
+checkpoint loader are out of scope.
 """
 import ctypes
 import dataclasses
+import math
 
 import numpy as np
 
 from . import _lib, env, phys
 
-__all__ = ("EvalSimResult", "eval_sim")
+__all__ = ("EvalSimResult", "eval_sim", "record_rollout")
 
 
 def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def _to_degrees(radians):
+    """radians * 180 / pi rounded the way analyse.py:84-89 rounds it (two operations in the
+    array's own dtype: NumPy treats the two Python floats as weak scalars)."""
+    t = radians.dtype.type
+    return np.divide(np.multiply(radians, t(180.)), t(math.pi))
+
+
 @dataclasses.dataclass
 class EvalSimResult:
-    """Per-frame record of one simulated episode (analyse.py:71-82)."""
+    """Per-frame record of one simulated episode; the reference's fields (analyse.py:71-82)."""
     time_delta: float
     player_state: phys.PlayerState
     action: np.ndarray
@@ -33,13 +52,32 @@ class EvalSimResult:
     fmove: np.ndarray
     jump: np.ndarray
 
+    @classmethod
+    def from_record(cls, record, time_delta, env_index=0, frames=None):
+        """One env's column of a `record_rollout` result, cut after `frames` rows (default: at the
+        env's first `done`, the frame on which the reference's loop stops)."""
+        if frames is None:
+            ended = np.flatnonzero(record["done"][:, env_index])
+            frames = int(ended[0]) + 1 if ended.size else record["done"].shape[0]
+        col = {k: record[k][:frames, env_index] for k in _lib.RECORD_FIELDS if k in record}
+        action = np.concatenate([col["keys"].astype(np.float64),
+                                 col["mouse"].astype(np.float64)[:, None]], axis=1)
+        state = phys.PlayerState(z_pos=col["z_pos"], vel=col["vel"], on_ground=col["on_ground"],
+                                 jump_released=col["jump_released"])
+        return cls(time_delta=time_delta, player_state=state, action=action, obs=col["obs"],
+                   reward=col["reward"], yaw=col["yaw"], smove=col["smove"], fmove=col["fmove"],
+                   jump=col["jump"])
+
     @property
     def move_angle(self):
-        return 180. * np.arctan2(self.player_state.vel[:, 1], self.player_state.vel[:, 0]) / np.pi
+        """Direction of travel in degrees (analyse.py:84-85)."""
+        v = self.player_state.vel
+        return _to_degrees(np.arctan2(v[:, 1], v[:, 0]))
 
     @property
     def wish_angle(self):
-        return self.yaw - (180. * np.arctan2(self.smove, self.fmove) / np.pi)
+        """Direction of the wish velocity in degrees (analyse.py:87-89)."""
+        return self.yaw - _to_degrees(np.arctan2(self.smove, self.fmove))
 
     def delta_speeds(self, rel_wish_angles, fmove=800., smove=0., time_delta=0.014, device=0):
         """Speed change of one tick for every (relative wish angle, frame) pair -> (A, frames) f32.
@@ -74,41 +112,61 @@ class EvalSimResult:
         return self.delta_speeds(np.arange(-180, 180))
 
 
-def eval_sim(trainer, env_config, **env_kwargs) -> EvalSimResult:
-    """Run `trainer.compute_action` on one zero-start-capable env until the episode ends, recording
-    state, observation, action and the decoded move command every frame (analyse.py:197-240)."""
+def record_rollout(vec_env, ticks, actions=None, policy=None, policy_seed=0, auto_reset=False,
+                   shadow_jump=True, fields=None):
+    """`ticks` lockstep ticks of `vec_env` in one launch, recorded per tick -> dict of NumPy arrays
+    shaped (ticks, num_envs, ...) with the keys of `q1_record_view` (include/q1phys.h) plus
+    "final_obs" (num_envs, 6).  `actions` = (keys (T, N, nk), mouse (T, N)), or `policy` =
+    'random' / 'strafe_jump' (generated on the device)."""
+    return vec_env.record(ticks, actions=actions, policy=policy, policy_seed=policy_seed,
+                          auto_reset=auto_reset, shadow_jump=shadow_jump, fields=fields)
+
+
+def _episode_frames(config, time_remaining):
+    """Upper bound on the frames until `time_remaining` drops below zero (env:505-506)."""
+    return int(math.ceil(max(float(time_remaining), 0.0) / float(config.time_delta))) + 2
+
+
+def eval_sim(trainer, env_config, initial_state=None, shadow_jump=True, **env_kwargs) -> EvalSimResult:
+    """Simulate one episode of `trainer` on a single env and return its per-frame record
+    (analyse.py:197-240).  `initial_state`: a `VectorPhysEnv.set_state` dict applied after the reset
+    (the reference draws it from the global np.random stream).  `shadow_jump` keeps the `jump` column
+    the reference records with auto_jump (see Q1_RECORD_SHADOW_JUMP)."""
     if isinstance(env_config, dict):
         env_config = env.Config(**env_config)
-    e = env.VectorPhysEnv(dataclasses.asdict(env_config), **env_kwargs)
-    o, = e.vector_reset()
-    action_decoder = env.ActionDecoder(env_config)
-    action_decoder.vector_reset(e._yaw)
+    config = dataclasses.replace(env_config, num_envs=1)
+    sim = env.VectorPhysEnv(config, **env_kwargs)
+    try:
+        sim.vector_reset()              # analyse.py:199: the episode is the env's SECOND reset draw
+        if initial_state is not None:
+            sim.set_state(initial_state)
+        frames = _episode_frames(config, sim._time_remaining[0])
 
-    obs, reward, actions, player_states = [], [], [], []
-    yaws, smoves, fmoves, jumps = [], [], [], []
-    done = False
-    while not done:
-        a = trainer.compute_action(o)
-        (yaw,), (smove,), (fmove,), (jump,) = action_decoder.map(
-            [a], o[None, env.Obs.Z_VEL], e._time_remaining)
-        player_states.append(e.player_state)
-        obs.append(o)
-        actions.append(np.array([np.ravel(x)[0] for x in a], dtype=np.float64))
-        yaws.append(yaw)
-        smoves.append(smove)
-        fmoves.append(fmove)
-        jumps.append(jump)
-        (o,), (r,), (done,), _ = e.vector_step([a])
-        reward.append(r)
-    e.close()
-    return EvalSimResult(
-        time_delta=env_config.time_delta,
-        player_state=phys.PlayerState.concatenate(player_states),
-        action=np.stack(actions),
-        obs=np.stack(obs),
-        reward=np.stack(reward),
-        yaw=np.stack(yaws),
-        smove=np.stack(smoves),
-        fmove=np.stack(fmoves),
-        jump=np.stack(jumps),
-    )
+        if hasattr(trainer, "action_script"):                 # open loop: the episode is one launch
+            keys, mouse = trainer.action_script(frames)
+            rec = sim.record(frames, actions=(np.asarray(keys)[:, None, :], np.asarray(mouse)[:, None]),
+                             shadow_jump=shadow_jump)
+            return EvalSimResult.from_record(rec, config.time_delta)
+
+        device_policy = getattr(trainer, "device_policy", None)
+        if device_policy is not None:                         # closed loop on the device
+            rec = device_policy.record_episode(sim, frames, deterministic=True, shadow_jump=shadow_jump)
+            return EvalSimResult.from_record(rec, config.time_delta)
+
+        # RLLib's trainer API: a Python call per frame.  Each frame is one recorder launch writing
+        # row t of the preallocated record in place and handing back the next observation.
+        width = sim._num_keys + (1 if config.allow_yaw else 0)
+        tape = sim.new_record(frames)
+        obs = sim._get_obs()[0]
+        t = 0
+        while True:
+            if t == tape["done"].shape[0]:                    # stepped on past the estimate: grow
+                tape = sim.grow_record(tape, 2 * t)
+            row = env._fix_actions([trainer.compute_action(obs)], width)
+            obs = sim.record_frame(tape, t, row, shadow_jump=shadow_jump)[0]
+            t += 1
+            if tape["done"][t - 1, 0]:
+                break
+        return EvalSimResult.from_record(tape, config.time_delta, frames=t)
+    finally:
+        sim.close()

@@ -21,6 +21,9 @@
 #ifndef Q1_POLY_SINCOS
 #define Q1_POLY_SINCOS 0
 #endif
+#ifndef Q1_TICK_LIBDEVICE_HUGE
+#define Q1_TICK_LIBDEVICE_HUGE 0
+#endif
 
 namespace q1 {
 
@@ -286,15 +289,33 @@ __device__ __forceinline__ void sincos_rad(double a, double &s, double &c)
 }
 
 /* sin and cos of a (radians) with the bits np.sin / np.cos return in the reference (phys:58-59,
- * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh.  HUGE = true (phys.apply, the
- * sweep, resets, q1_sincos_host): every finite argument; HUGE = false (the per-tick kernels): up to
- * |a| < 105414350, i.e. yaw below 6e9 degrees -- beyond that, and for infinities / NaN, libdevice's
- * sincos answers (accurate, NaN like libm, not necessarily the same last bit). */
+ * env:475-476): glibc's __sin / __cos restated in q1_libm_sincos.cuh, exact for every finite
+ * argument everywhere.  HUGE = true (phys.apply, the sweep, q1_sincos_host) carries __branred
+ * inline; HUGE = false (the per-tick kernels, resets) keeps the hot path to |a| < 105414350 (yaw
+ * below 6e9 degrees) and hands anything beyond to sincos_cold(), one out-of-line copy of the
+ * general routine: a call that a lockstep episode never makes, but the one that keeps "bit-identical
+ * for every finite input" free of footnotes.  Infinities and NaN give NaN like libm. */
+static __device__ __noinline__ void sincos_cold(double a, double *s, double *c)
+{
+    double sv, cv;
+    if (!q1libm::sincos<true>(a, sv, cv))
+        sincos(a, &sv, &cv);   /* inf / NaN only */
+    *s = sv;
+    *c = cv;
+}
 template <bool HUGE = true>
 __device__ __forceinline__ void sincos_ref(double a, double &s, double &c)
 {
-    if (__builtin_expect(!q1libm::sincos<HUGE>(a, s, c), 0))
-        sincos(a, &s, &c);
+    if (__builtin_expect(!q1libm::sincos<HUGE>(a, s, c), 0)) {
+#if Q1_TICK_LIBDEVICE_HUGE
+        sincos(a, &s, &c);         /* A/B timing only: libdevice beyond 1.05e8 (not bit-exact there) */
+#else
+        if (HUGE)
+            sincos(a, &s, &c);     /* inf / NaN only */
+        else
+            sincos_cold(a, &s, &c);
+#endif
+    }
 }
 
 /* ------------------------------------------------------------------ observation -------------- */
@@ -458,9 +479,16 @@ __device__ __forceinline__ void move_body(float &vx, float &vy, float &vz, doubl
  * mouse action as f64 (continuous value or the discrete index). */
 /* COMMON: the configuration every shipped setup uses (mouse action present and continuous, no
  * hover, reward = y velocity) is compiled in; otherwise those switches are read from Params. */
+/* The move command ActionDecoder.map returns (env:269), for callers that record it. */
+struct Move {
+    double yaw;      /* decoder yaw after this tick's mouse movement (env:258) */
+    double smove, fmove;
+    bool jump;
+};
+
 template <bool STAMPS, bool LEAN, bool COMMON>
 __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, double mouse,
-                                     float &reward, bool &done)
+                                     float &reward, bool &done, Move *move = nullptr)
 {
     const bool hover = COMMON ? false : (bool)P.hover;
     const bool allow_yaw = COMMON ? true : (bool)P.allow_yaw;
@@ -533,6 +561,12 @@ __device__ __forceinline__ void tick(const Params &P, Env &e, uint32_t keybits, 
 
     e.yaw = add64(e.yaw, mouse_x);                                                       /* env:258 */
     e.bits = (e.bits & ~(0xFu << F_LAST_KEY_SHIFT)) | (down << F_LAST_KEY_SHIFT);       /* env:256 */
+    if (move) {                     /* a compile-time nullptr in the step kernels: folds away */
+        move->yaw = e.yaw;
+        move->smove = smove;
+        move->fmove = fmove;
+        move->jump = jump;
+    }
 
     /* ---- phys.apply ---- pitch = roll = 0 (env:490-491) so the matrix is [[cy, sy], [sy, -cy]] */
     double sy, cy;

@@ -595,17 +595,35 @@ k_observe(const __grid_constant__ Params P, float *__restrict__ obs)
     store_obs(obs, i, o);
 }
 
-/* -- multi-tick rollout with a device-side policy: state stays in registers -------------------- */
+/* -- multi-tick rollout: state stays in registers for all ticks -------------------------------- */
 
-template <bool STAMPS, bool TRACK, bool LEAN>
+/* Where a rollout's actions come from: a built-in device-side policy, or (RECORD launches) caller
+ * arrays laid out [tick][env]. */
+struct ActionFeed {
+    int policy;                 /* Q1_POLICY_*; -1: the arrays below */
+    uint64_t policy_seed;
+    const uint8_t *keys;        /* (ticks, n, num_keys) */
+    const void *mouse;          /* (ticks, n) of mouse_kind */
+    int mouse_kind;
+};
+
+/* RECORD: the per-tick trajectory recorder behind analyse.eval_sim (q1physrl/analyse.py:197-240),
+ * N envs at once: before each tick the env's movement state and observation (analyse.py:218-219),
+ * the action, the move command ActionDecoder.map makes of it (analyse.py:215-216, taken from the
+ * SAME tick<>() that advances the env rather than from a shadow decoder) and, after the tick, reward
+ * and done are written as row t of the [tick][env] arrays of q1_record_view.  auto_reset = 0 keeps
+ * the reference's behaviour (an env whose episode ended keeps stepping, env:505-506). */
+template <bool STAMPS, bool TRACK, bool LEAN, bool RECORD>
 __global__ void __launch_bounds__(kBlock)
-k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick_base,
-          uint64_t policy_seed, float *__restrict__ obs, float *__restrict__ reward_sum)
+k_rollout(const __grid_constant__ Params P, const ActionFeed feed, int ticks, uint32_t tick_base,
+          float *__restrict__ obs, float *__restrict__ reward_sum, int auto_reset, uint32_t record_flags,
+          const q1_record_view rec)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = i < P.n;
     const int64_t ii = active ? i : 0;
     const uint64_t gidx = P.env_index_base + (uint64_t)ii;
+    const int nk = P.num_keys;
     Env e;
     load_env<STAMPS>(P, ii, e);
     uint32_t ep = P.epoch[ii];
@@ -614,16 +632,79 @@ k_rollout(const __grid_constant__ Params P, int policy, int ticks, uint32_t tick
     for (int t = 0; t < ticks; t++) {
         uint32_t keybits;
         double m;
-        policy_action(P, policy, policy_seed, gidx, tick_base + (uint32_t)t, keybits, m);
+        if (!RECORD || feed.policy >= 0) {
+            policy_action(P, feed.policy, feed.policy_seed, gidx, tick_base + (uint32_t)t, keybits, m);
+        } else {
+            const int64_t row = (int64_t)t * P.n + ii;
+            keybits = load_keys(feed.keys, row, nk);
+            m = P.allow_yaw ? load_mouse(feed.mouse, feed.mouse_kind, row) : 0.0;
+        }
         float r;
         bool d;
-        tick<STAMPS, LEAN, false>(P, e, keybits, m, r, d);
+        if (RECORD) {
+            const int64_t row = (int64_t)t * P.n + ii;
+            float o[6];
+            observe<LEAN>(P, e, o);           /* what the policy saw (the hover override, env:483-485,
+                                                 happens inside the tick, after it) */
+            if (active) {
+                if (rec.vel) {
+                    rec.vel[3 * row] = e.vx;
+                    rec.vel[3 * row + 1] = e.vy;
+                    rec.vel[3 * row + 2] = e.vz;
+                }
+                if (rec.z_pos)
+                    rec.z_pos[row] = e.z;
+                if (rec.on_ground)
+                    rec.on_ground[row] = (e.bits & F_ON_GROUND) != 0;
+                if (rec.jump_released)
+                    rec.jump_released[row] = (e.bits & F_JUMP_RELEASED) != 0;
+                if (rec.time_remaining)
+                    rec.time_remaining[row] = e.trem;
+                if (rec.obs)
+                    store_obs(rec.obs, row, o);
+                if (rec.keys)
+                    for (int k = 0; k < nk; k++)
+                        rec.keys[row * nk + k] = (keybits >> k) & 1u;
+                if (rec.mouse)
+                    rec.mouse[row] = (float)m;
+            }
+            Move mv;
+            tick<STAMPS, LEAN, false>(P, e, keybits, m, r, d, &mv);
+            if (active) {
+                if (rec.yaw)
+                    rec.yaw[row] = mv.yaw;
+                if (rec.smove)
+                    rec.smove[row] = (int64_t)mv.smove;
+                if (rec.fmove)
+                    rec.fmove[row] = (int64_t)mv.fmove;
+                if (rec.jump) {
+                    /* analyse.py:215-216 hands its shadow decoder the OBSERVATION's z velocity
+                     * (quantised, divided by 200), so with auto_jump it records obs <= 16 */
+                    bool j = mv.jump;
+                    if ((record_flags & Q1_RECORD_SHADOW_JUMP) && P.jump_mode == 2)
+                        j = o[5] <= 16.0f;
+                    rec.jump[row] = j;
+                }
+                if (rec.reward)
+                    rec.reward[row] = r;
+                if (rec.done)
+                    rec.done[row] = d;
+            }
+        } else {
+            tick<STAMPS, LEAN, false>(P, e, keybits, m, r, d);
+        }
         rsum = add32(rsum, r);
         if (TRACK) {
             ret = add64(ret, (double)r);
-            report_episodes(P, active && d, e.bits & F_ZERO_START, ret);
+            bool finished = active && d;
+            if (RECORD && !auto_reset) {            /* report an episode once, as the step kernels do */
+                finished = finished && !(e.bits & F_DONE_SEEN);
+                if (finished)
+                    e.bits |= F_DONE_SEEN;
+            }
+            report_episodes(P, finished, e.bits & F_ZERO_START, ret);
         }
-        if (d) {
+        if (d && (!RECORD || auto_reset)) {
             ep += 1u;
             reset_env<STAMPS>(P, e, gidx, ep);
             ret = 0.0;
@@ -1660,6 +1741,25 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
     return Q1_OK;
 }
 
+static int rollout_launch(q1_env *env, const ActionFeed &feed, int ticks, float *obs, float *reward_sum,
+                          int auto_reset, uint32_t record_flags, const q1_record_view *rec, cudaStream_t s)
+{
+    int rc = dispatch(env, [&](auto st, auto tr, auto ln) {
+        if (rec)
+            k_rollout<decltype(st)::value, decltype(tr)::value, decltype(ln)::value, true>
+                <<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, feed, ticks, (uint32_t)env->ticks, obs,
+                                                       reward_sum, auto_reset, record_flags, *rec);
+        else
+            k_rollout<decltype(st)::value, decltype(tr)::value, decltype(ln)::value, false>
+                <<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, feed, ticks, (uint32_t)env->ticks, obs,
+                                                       reward_sum, 1, 0u, q1_record_view{});
+        return check_launch("k_rollout");
+    });
+    if (rc == Q1_OK)
+        env->ticks += (uint64_t)ticks;
+    return rc;
+}
+
 int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *obs,
                float *reward_sum, void *stream)
 {
@@ -1670,16 +1770,122 @@ int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *
     if (ticks < 0)
         return fail(Q1_EINVAL, "ticks must be >= 0");
     DeviceGuard guard(env->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = dispatch(env, [&](auto st, auto tr, auto ln) {
-        k_rollout<decltype(st)::value, decltype(tr)::value, decltype(ln)::value>
-            <<<grid_for(env->P.n), kBlock, 0, s>>>(
-            env->P, policy, ticks, (uint32_t)env->ticks, policy_seed, obs, reward_sum);
-        return check_launch("k_rollout");
-    });
-    if (rc == Q1_OK)
-        env->ticks += (uint64_t)ticks;
-    return rc;
+    const ActionFeed feed = {policy, policy_seed, nullptr, nullptr, Q1_MOUSE_F32};
+    return rollout_launch(env, feed, ticks, obs, reward_sum, 1, 0u, nullptr,
+                          static_cast<cudaStream_t>(stream));
+}
+
+static int check_record_args(const q1_env *env, const q1_action_source *src, int ticks,
+                             const q1_record_view *rec)
+{
+    if (!env || !src || !rec)
+        return fail(Q1_EINVAL, "env / actions / record is NULL");
+    if (ticks < 0)
+        return fail(Q1_EINVAL, "ticks must be >= 0");
+    if (src->kind == Q1_ACTIONS_BUILTIN) {
+        if (src->builtin_policy != Q1_POLICY_RANDOM && src->builtin_policy != Q1_POLICY_STRAFE_JUMP)
+            return fail(Q1_EINVAL, "unknown built-in policy");
+    } else if (src->kind == Q1_ACTIONS_ARRAYS) {
+        if (src->mouse_kind != Q1_MOUSE_F32 && src->mouse_kind != Q1_MOUSE_I32 && src->mouse_kind != Q1_MOUSE_F64)
+            return fail(Q1_EINVAL, "unknown mouse_kind");
+        if (ticks > 0 && (!src->keys || (env->P.allow_yaw && !src->mouse)))
+            return fail(Q1_EINVAL, "action arrays are NULL");
+    } else {
+        return fail(Q1_EINVAL, "unknown action source kind");
+    }
+    return Q1_OK;
+}
+
+int q1_rollout_record(q1_env *env, const q1_action_source *actions, int ticks, int auto_reset,
+                      uint32_t record_flags, const q1_record_view *record, float *final_obs, void *stream)
+{
+    int rc = check_record_args(env, actions, ticks, record);
+    if (rc != Q1_OK)
+        return rc;
+    DeviceGuard guard(env->device);
+    const ActionFeed feed = {actions->kind == Q1_ACTIONS_BUILTIN ? actions->builtin_policy : -1,
+                             actions->policy_seed, actions->keys, actions->mouse, actions->mouse_kind};
+    return rollout_launch(env, feed, ticks, final_obs, nullptr, auto_reset, record_flags, record,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int q1_rollout_record_host(q1_env *env, const q1_action_source *actions, int ticks, int auto_reset,
+                           uint32_t record_flags, const q1_record_view *record, float *final_obs_host)
+{
+    int rc = check_record_args(env, actions, ticks, record);
+    if (rc != Q1_OK)
+        return rc;
+    DeviceGuard guard(env->device);
+    const size_t n = (size_t)env->P.n, nk = (size_t)env->P.num_keys, rows = n * (size_t)ticks;
+    /* one staging buffer: [actions in | every requested record array | final obs] */
+    struct Field { const void *host; size_t bytes, off; };
+    Field f[15];
+    const void *hosts[15] = {record->vel, record->z_pos, record->on_ground, record->jump_released,
+                             record->time_remaining, record->obs, record->keys, record->mouse,
+                             record->yaw, record->smove, record->fmove, record->jump, record->reward,
+                             record->done, final_obs_host};
+    const size_t width[15] = {12, 8, 1, 1, 8, 24, nk, 4, 8, 8, 8, 1, 4, 1, 0};
+    const bool arrays = actions->kind == Q1_ACTIONS_ARRAYS;
+    const size_t mouse_size = actions->mouse_kind == Q1_MOUSE_F64 ? 8 : 4;
+    size_t off = 0;
+    const size_t o_keys = off;
+    off = align_up(off + (arrays ? rows * nk : 0));
+    const size_t o_mouse = off;
+    off = align_up(off + (arrays && env->P.allow_yaw ? rows * mouse_size : 0));
+    for (int k = 0; k < 15; k++) {
+        f[k].host = hosts[k];
+        f[k].bytes = hosts[k] ? (k == 14 ? 24 * n : rows * width[k]) : 0;
+        f[k].off = off;
+        off = align_up(off + f[k].bytes);
+    }
+    rc = ensure_scratch(env, off + 256);
+    if (rc != Q1_OK)
+        return rc;
+    char *d = static_cast<char *>(env->scratch);
+    cudaStream_t s = env->host_stream;
+    if (arrays && rows) {
+        Q1_CUDA(cudaMemcpyAsync(d + o_keys, actions->keys, rows * nk, cudaMemcpyHostToDevice, s));
+        if (env->P.allow_yaw)
+            Q1_CUDA(cudaMemcpyAsync(d + o_mouse, actions->mouse, rows * mouse_size, cudaMemcpyHostToDevice, s));
+    }
+    auto dev = [&](int k) -> void * { return f[k].bytes ? d + f[k].off : nullptr; };
+    q1_record_view dv;
+    dv.vel = static_cast<float *>(dev(0));
+    dv.z_pos = static_cast<double *>(dev(1));
+    dv.on_ground = static_cast<uint8_t *>(dev(2));
+    dv.jump_released = static_cast<uint8_t *>(dev(3));
+    dv.time_remaining = static_cast<double *>(dev(4));
+    dv.obs = static_cast<float *>(dev(5));
+    dv.keys = static_cast<uint8_t *>(dev(6));
+    dv.mouse = static_cast<float *>(dev(7));
+    dv.yaw = static_cast<double *>(dev(8));
+    dv.smove = static_cast<int64_t *>(dev(9));
+    dv.fmove = static_cast<int64_t *>(dev(10));
+    dv.jump = static_cast<uint8_t *>(dev(11));
+    dv.reward = static_cast<float *>(dev(12));
+    dv.done = static_cast<uint8_t *>(dev(13));
+    const ActionFeed feed = {arrays ? -1 : actions->builtin_policy, actions->policy_seed,
+                             reinterpret_cast<const uint8_t *>(d + o_keys), d + o_mouse, actions->mouse_kind};
+    rc = rollout_launch(env, feed, ticks, static_cast<float *>(dev(14)), nullptr, auto_reset, record_flags,
+                        &dv, s);
+    if (rc != Q1_OK)
+        return rc;
+    for (int k = 0; k < 15; k++)
+        if (f[k].bytes)
+            Q1_CUDA(cudaMemcpyAsync(const_cast<void *>(f[k].host), d + f[k].off, f[k].bytes,
+                                    cudaMemcpyDeviceToHost, s));
+    Q1_CUDA(cudaStreamSynchronize(s));
+    return Q1_OK;
+}
+
+int q1_advance_ticks(q1_env *env, int64_t delta)
+{
+    if (!env)
+        return fail(Q1_EINVAL, "env is NULL");
+    if (delta < 0 && (uint64_t)(-delta) > env->ticks)
+        return fail(Q1_EINVAL, "tick counter would become negative");
+    env->ticks += (uint64_t)delta;
+    return Q1_OK;
 }
 
 int q1_observe(q1_env *env, float *obs, void *stream)

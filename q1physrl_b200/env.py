@@ -576,6 +576,99 @@ class VectorPhysEnv(VectorEnv):
                                         ctypes.c_void_p(rsum.data_ptr()), stream))
         return obs, rsum
 
+    # ------------------------------------------------------------------ trajectory recorder
+    def _record_spec(self):
+        nk = self._num_keys
+        return {"vel": ((3,), np.float32), "z_pos": ((), np.float64), "on_ground": ((), np.bool_),
+                "jump_released": ((), np.bool_), "time_remaining": ((), np.float64),
+                "obs": ((6,), np.float32), "keys": ((nk,), np.uint8), "mouse": ((), np.float32),
+                "yaw": ((), np.float64), "smove": ((), np.int64), "fmove": ((), np.int64),
+                "jump": ((), np.bool_), "reward": ((), np.float32), "done": ((), np.bool_)}
+
+    def new_record(self, ticks, fields=None) -> dict:
+        """Zeroed arrays (ticks, num_envs, ...) for `record` / `record_frame`: the fields of
+        `q1_record_view` (include/q1phys.h), or the subset `fields`."""
+        spec = self._record_spec()
+        names = _lib.RECORD_FIELDS if fields is None else tuple(fields)
+        return {k: np.zeros((int(ticks), self.num_envs) + spec[k][0], spec[k][1]) for k in names}
+
+    def grow_record(self, tape, ticks) -> dict:
+        """A record of `ticks` rows holding the rows of `tape`."""
+        out = self.new_record(ticks, tape.keys())
+        for k, v in tape.items():
+            out[k][:v.shape[0]] = v
+        return out
+
+    def _record_view(self, tape, row):
+        view = _lib.Q1RecordView()
+        for k, v in tape.items():
+            setattr(view, k, v.ctypes.data + row * v.strides[0])
+        return view
+
+    def record(self, ticks, actions=None, policy=None, policy_seed=0, auto_reset=False,
+               shadow_jump=False, fields=None, tape=None, row=0) -> dict:
+        """`ticks` lockstep ticks in ONE launch with a per-tick record (`q1_rollout_record_host`; the
+        on-device form of q1physrl/analyse.py:197-240 for all envs at once) -> dict of arrays
+        (ticks, num_envs, ...) + "final_obs" (num_envs, 6).
+
+        actions  (keys (T, N, nk) 0/1, mouse (T, N) float32 / float64 / int32), or
+        policy   'random' / 'strafe_jump': actions generated on the device (as `rollout`).
+        auto_reset=False keeps the reference's behaviour (finished envs keep stepping; cut a column
+        at its first `done`).  shadow_jump: see Q1_RECORD_SHADOW_JUMP.  `tape` / `row`: write into
+        rows [row, row + ticks) of an existing record instead of a new one."""
+        ticks = int(ticks)
+        n, nk = self.num_envs, self._num_keys
+        src = _lib.Q1ActionSource()
+        keep = []
+        if actions is not None:
+            keys = np.ascontiguousarray(actions[0], dtype=np.uint8)
+            if keys.shape != (ticks, n, nk):
+                raise ValueError(f"keys must have shape ({ticks}, {n}, {nk}), got {keys.shape}")
+            src.kind, src.keys, src.mouse_kind = _lib.Q1_ACTIONS_ARRAYS, keys.ctypes.data, _lib.Q1_MOUSE_F32
+            keep.append(keys)
+            if self._config.allow_yaw:
+                mouse = np.asarray(actions[1])
+                if mouse.dtype == np.float32:
+                    kind = _lib.Q1_MOUSE_F32
+                elif mouse.dtype == np.int32:
+                    kind = _lib.Q1_MOUSE_I32
+                else:
+                    mouse, kind = mouse.astype(np.float64), _lib.Q1_MOUSE_F64
+                mouse = np.ascontiguousarray(mouse)
+                if mouse.shape != (ticks, n):
+                    raise ValueError(f"mouse must have shape ({ticks}, {n}), got {mouse.shape}")
+                src.mouse, src.mouse_kind = mouse.ctypes.data, kind
+                keep.append(mouse)
+        elif policy is not None:
+            src.kind = _lib.Q1_ACTIONS_BUILTIN
+            src.builtin_policy = {"random": _lib.Q1_POLICY_RANDOM,
+                                  "strafe_jump": _lib.Q1_POLICY_STRAFE_JUMP}.get(policy, policy)
+            src.policy_seed = int(policy_seed)
+        else:
+            raise ValueError("record() needs `actions` or a built-in `policy`")
+        if tape is None:
+            tape, row = self.new_record(ticks, fields), 0
+        elif next(iter(tape.values())).shape[0] < row + ticks:
+            raise ValueError("the record has fewer rows than row + ticks")
+        final_obs = np.empty((n, 6), np.float32)
+        view = self._record_view(tape, row)
+        _lib.check(self._lib.q1_rollout_record_host(
+            self._handle, ctypes.byref(src), ticks, int(bool(auto_reset)),
+            _lib.Q1_RECORD_SHADOW_JUMP if shadow_jump else 0, ctypes.byref(view), _ptr(final_obs)))
+        self._step_num += ticks
+        tape["final_obs"] = final_obs
+        return tape
+
+    def record_frame(self, tape, t, action_rows, shadow_jump=False):
+        """One recorded tick written as row `t` of `tape` (from `new_record`): `action_rows`
+        (num_envs, nk [+ 1]) as `_fix_actions` returns them -> the next observation (N, 6)."""
+        rows = np.asarray(action_rows, np.float64)
+        keys = (rows[:, :self._num_keys].astype(np.int64) & 1).astype(np.uint8)[None]
+        mouse = rows[:, self._num_keys][None] if self._config.allow_yaw else None
+        tape.pop("final_obs", None)
+        return self.record(1, actions=(keys, mouse), shadow_jump=shadow_jump, tape=tape,
+                           row=int(t)).pop("final_obs")
+
     def metrics(self, clear: bool = False) -> dict:
         """On-device episode statistics (q1physrl/train.py:54-57, 67-71); needs track_returns."""
         m = _lib.Q1Metrics()

@@ -139,3 +139,48 @@ def test_oracle_hypothetical_delta_speeds():
                                      np.zeros_like(ma), g["jump"], np.full_like(ma, 0.014),
                                      g["z_pos"], g["vel"], g["on_ground"], g["jump_released"])
         assert np.array_equal(np.linalg.norm(vel[:, :2], axis=1) - before, g["delta_speeds"][a]), rel
+
+
+def eval_sim_case(tag):
+    """One case of tests/golden/eval_sim.npz (the reference's own eval_sim output) as a dict."""
+    import json
+    with np.load(harness.GOLDEN_DIR + "/eval_sim.npz") as z:
+        g = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + "_")}
+    cfg = json.loads(str(g["config"]))
+    cfg["initial_yaw_range"] = tuple(cfg["initial_yaw_range"])
+    g["config"] = cfg
+    g["state0"] = {f: g["state0_" + f] for f in harness.STATE_FIELDS}
+    return g
+
+
+@pytest.mark.parametrize("tag", ["strafe", "autojump", "random"])
+def test_oracle_reproduces_reference_eval_sim(tag):
+    """q1physrl/analyse.py:197-240 run unmodified on the reference env (make_eval_sim_fixture.py):
+    the oracle, stepped with the recorded actions plus a shadow decoder fed like analyse.py:215-216
+    (the OBSERVATION's z velocity), reproduces every array of the reference's EvalSimResult."""
+    g = eval_sim_case(tag)
+    cfg = g["config"]
+    o = qo.OracleEnv(cfg)
+    o.set_state(g["state0"])
+    nk = o.nk
+    shadow_keys = np.zeros((1, nk), np.uint8)
+    shadow_press = np.full((1, nk), -cfg["key_press_delay"], np.float64)
+    shadow_yaw = o.yaw.copy()
+    T = g["reward"].shape[0]
+    assert g["action"].shape == (T, nk + 1)
+    obs = o.observe()
+    for t in range(T):
+        keys = g["action"][t, :nk].astype(np.uint8)[None]
+        mouse = g["action"][t, nk:nk + 1]
+        assert np.array_equal(o.z_pos, g["z_pos"][t:t + 1]) and np.array_equal(o.vel, g["vel"][t:t + 1])
+        assert bool(o.on_ground[0]) == bool(g["on_ground"][t])
+        assert bool(o.jump_released[0]) == bool(g["jump_released"][t])
+        assert np.array_equal(obs[0], g["obs"][t])
+        y, sm, fm, jp = qo.decode(cfg, shadow_keys, shadow_press, shadow_yaw, keys, mouse,
+                                  obs[:, 5].astype(np.float32), o.time_remaining)
+        shadow_yaw = y
+        assert y[0] == g["yaw"][t] and sm[0] == g["smove"][t] and fm[0] == g["fmove"][t]
+        assert bool(jp[0]) == bool(g["jump"][t])
+        obs, rew, done = o.step(keys, mouse)
+        assert rew[0] == g["reward"][t] and bool(done[0]) == (t == T - 1)
+        assert o.yaw[0] == y[0]                      # the env's decoder and the shadow agree on yaw
