@@ -38,8 +38,11 @@ enum {
 enum {
     Q1_F_TRACK_RETURNS = 1u << 0,   /* keep a per-env f64 episode return + on-device episode metrics */
     Q1_F_FORCE_F64_STAMPS = 1u << 1, /* keep env:200 key time stamps in f64 even when u8 tick counters are exact */
-    Q1_F_IEEE_DIVISION = 1u << 2    /* divide with the CUDA IEEE intrinsics instead of the (equally exact,
+    Q1_F_IEEE_DIVISION = 1u << 2,   /* divide with the CUDA IEEE intrinsics instead of the (equally exact,
                                        branch-free) reciprocal-multiply sequences: slower, for self-checks */
+    Q1_F_NUMPY1_PROMOTION = 1u << 3 /* env:230 `np.float32(720) * time_delta` as NumPy < 2 evaluates it (in
+                                       float64) -- the reference pins numpy 1.18.2; the default is NumPy 2's
+                                       float32 product, which the oracle and all fixtures were recorded with */
 };
 
 /* Element type of the `mouse` array handed to q1_step / q1_step_host. */
@@ -75,7 +78,8 @@ typedef struct q1_config {
     int32_t smooth_keys;
     int32_t auto_jump;
     int32_t allow_jump;
-    int32_t reserved;
+    int32_t reserved;           /* 0; q1_decode_host (which has no flags argument) reads bit 0 as
+                                   Q1_F_NUMPY1_PROMOTION */
 } q1_config;
 
 typedef struct q1_env q1_env; /* opaque */

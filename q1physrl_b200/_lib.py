@@ -13,7 +13,7 @@ c_i64, c_u64, c_i32, c_u32, c_int = (ctypes.c_int64, ctypes.c_uint64, ctypes.c_i
 c_double, c_void_p, c_char_p = ctypes.c_double, ctypes.c_void_p, ctypes.c_char_p
 
 Q1_OK, Q1_EINVAL, Q1_ECUDA, Q1_ENODEV, Q1_ENOMEM = 0, -1, -2, -3, -4
-Q1_F_TRACK_RETURNS, Q1_F_FORCE_F64_STAMPS, Q1_F_IEEE_DIVISION = 1, 2, 4
+Q1_F_TRACK_RETURNS, Q1_F_FORCE_F64_STAMPS, Q1_F_IEEE_DIVISION, Q1_F_NUMPY1_PROMOTION = 1, 2, 4, 8
 Q1_MOUSE_F32, Q1_MOUSE_I32, Q1_MOUSE_F64 = 0, 1, 2
 Q1_POLICY_RANDOM, Q1_POLICY_STRAFE_JUMP = 0, 1
 Q1_ACTIONS_ARRAYS, Q1_ACTIONS_BUILTIN = 0, 1

@@ -139,7 +139,128 @@ done:
     return result;
 }
 
+/* split_actions(actions, num_keys, has_mouse, keys_out, mouse_out) -> None
+ * The same walk, written straight into the two arrays q1_step_host consumes: keys_out (N, num_keys)
+ * uint8 = bit 0 of the key action truncated to an integer (env:228 `.astype(np.int)`, env:243 `&`
+ * against 0/1 values), mouse_out (N,) float64 (ignored when has_mouse is 0). */
+static PyObject *split_actions(PyObject *self, PyObject *args)
+{
+    PyObject *actions, *keys_obj, *mouse_obj;
+    Py_ssize_t nk;
+    int has_mouse;
+    if (!PyArg_ParseTuple(args, "OnpOO", &actions, &nk, &has_mouse, &keys_obj, &mouse_obj))
+        return NULL;
+    PyObject *outer = PySequence_Fast(actions, "actions must be a sequence of per-env action tuples");
+    if (!outer)
+        return NULL;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(outer);
+    const Py_ssize_t width = nk + (has_mouse ? 1 : 0);
+    Py_buffer kb, mb;
+    mb.buf = NULL;
+    if (PyObject_GetBuffer(keys_obj, &kb, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) != 0) {
+        Py_DECREF(outer);
+        return NULL;
+    }
+    if (has_mouse && PyObject_GetBuffer(mouse_obj, &mb, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) != 0) {
+        PyBuffer_Release(&kb);
+        Py_DECREF(outer);
+        return NULL;
+    }
+    PyObject *result = NULL;
+    if (nk < 1 || kb.len != n * nk || (has_mouse && mb.len != (Py_ssize_t)(n * sizeof(double)))) {
+        PyErr_SetString(PyExc_ValueError, "keys_out / mouse_out do not match len(actions)");
+        goto done;
+    }
+    unsigned char *keys = (unsigned char *)kb.buf;
+    double *mouse = has_mouse ? (double *)mb.buf : NULL;
+    for (Py_ssize_t i = 0; i < n; i++) {
+        PyObject *row = PySequence_Fast_GET_ITEM(outer, i);
+        if (!(PyTuple_Check(row) || PyList_Check(row))) {
+            PyErr_SetString(PyExc_TypeError, "each action must be a tuple or a list");
+            goto done;
+        }
+        if (PySequence_Fast_GET_SIZE(row) < width) {
+            PyErr_SetString(PyExc_ValueError, "action with too few elements");
+            goto done;
+        }
+        for (Py_ssize_t j = 0; j < width; j++) {
+            double v;
+            if (element_value(PySequence_Fast_GET_ITEM(row, j), &v) != 0) {
+                if (!PyErr_Occurred())
+                    PyErr_SetString(PyExc_TypeError, "unsupported action element");
+                goto done;
+            }
+            if (j < nk) {
+                if (!(v > -9.2e18 && v < 9.2e18)) {      /* astype(int) of nan / inf / huge: NumPy's business */
+                    PyErr_SetString(PyExc_ValueError, "key action outside the int64 range");
+                    goto done;
+                }
+                keys[i * nk + j] = (unsigned char)((long long)v & 1);
+            } else {
+                mouse[i] = v;
+            }
+        }
+    }
+    result = Py_None;
+    Py_INCREF(result);
+done:
+    if (mb.buf)
+        PyBuffer_Release(&mb);
+    PyBuffer_Release(&kb);
+    Py_DECREF(outer);
+    return result;
+}
+
+/* step(fn, handle, keys, mouse | None, mouse_kind, obs, reward, done, zero_start | None, auto_reset)
+ * -> the int q1_step_host returns.  `fn` is the address of q1_step_host (include/q1phys.h) and
+ * `handle` the q1_env*, both as integers.  Takes the array addresses through the buffer protocol
+ * and makes the C call directly: at RLLib's 100 envs per worker the ctypes marshalling of nine
+ * arguments and seven `ndarray.ctypes` objects costs as much as the GPU work. */
+typedef int (*step_host_fn)(void *, const void *, const void *, int, void *, void *, void *, void *, int);
+
+static PyObject *step(PyObject *self, PyObject *args)
+{
+    unsigned long long fn, handle;
+    PyObject *objs[6];   /* keys, mouse, obs, reward, done, zero_start */
+    int mouse_kind, auto_reset;
+    if (!PyArg_ParseTuple(args, "KKOOiOOOOp", &fn, &handle, &objs[0], &objs[1], &mouse_kind, &objs[2],
+                          &objs[3], &objs[4], &objs[5], &auto_reset))
+        return NULL;
+    static const int writable[6] = {0, 0, 1, 1, 1, 1};
+    Py_buffer view[6];
+    void *ptr[6] = {NULL, NULL, NULL, NULL, NULL, NULL};
+    int got = 0;
+    for (; got < 6; got++) {
+        view[got].buf = NULL;
+        if (objs[got] == Py_None)
+            continue;
+        if (PyObject_GetBuffer(objs[got], &view[got],
+                               (writable[got] ? PyBUF_WRITABLE : 0) | PyBUF_C_CONTIGUOUS) != 0)
+            break;
+        ptr[got] = view[got].buf;
+    }
+    PyObject *result = NULL;
+    if (got == 6) {
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = ((step_host_fn)(uintptr_t)fn)((void *)(uintptr_t)handle, ptr[0], ptr[1], mouse_kind, ptr[2],
+                                           ptr[3], ptr[4], ptr[5], auto_reset);
+        Py_END_ALLOW_THREADS
+        result = PyLong_FromLong(rc);
+    }
+    for (int k = 0; k < got; k++)
+        if (view[k].buf)
+            PyBuffer_Release(&view[k]);
+    return result;
+}
+
 static PyMethodDef methods[] = {
+    {"split_actions", split_actions, METH_VARARGS,
+     "split_actions(actions, num_keys, has_mouse, keys_out, mouse_out): RLLib's nested action format -> "
+     "the uint8 key array and float64 mouse array q1_step_host consumes (reference env.py:221-228)."},
+    {"step", step, METH_VARARGS,
+     "step(fn, handle, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset) -> rc of "
+     "q1_step_host called through its address."},
     {"fix_actions", fix_actions, METH_VARARGS,
      "fix_actions(actions, width, out): normalise RLLib's nested action format into the (N, width) "
      "float64 buffer `out` (reference env.py:221-223)."},

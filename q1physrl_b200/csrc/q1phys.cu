@@ -41,6 +41,7 @@ constexpr int kBlock = kTile;      /* threads per CTA: one env per thread, one s
 #define Q1_STEP_CTAS 6
 #endif
 constexpr int kStepCtasPerSm = Q1_STEP_CTAS;
+constexpr int kStepCtasSmall = 7;   /* the variant for launches of few tiles per SM, see k_step_tma */
 
 __device__ __forceinline__ unsigned char *state_block(const Params &P, int64_t i)
 {
@@ -329,8 +330,12 @@ constexpr int kOutStages = 2;
 #define Q1_PASSTHROUGH 0
 #endif
 
-template <bool TRACK, bool LEAN, bool COMMON>
-__global__ void __launch_bounds__(kBlock, kStepCtasPerSm)
+/* CTAS: resident CTAs per SM the build is register-limited for.  6 x 80 registers is the fastest at
+ * 2^20 envs; 7 x 72 wins when a launch has few tiles per SM: 131 072 envs are 1024 tiles, which 148 x 7
+ * = 1036 resident CTAs take in one wave where 148 x 6 = 888 need a second one for 136 of them
+ * (5.6 vs 6.0 us per tick; 262 144 envs: 8.5 vs 8.9). */
+template <bool TRACK, bool LEAN, bool COMMON, int CTAS>
+__global__ void __launch_bounds__(kBlock, CTAS)
 k_step_tma(const __grid_constant__ Params P, const uint8_t *__restrict__ keys,
            const void *__restrict__ mouse, int mouse_kind, float *__restrict__ obs,
            float *__restrict__ reward, uint8_t *__restrict__ done,
@@ -1022,6 +1027,7 @@ struct q1_env {
     bool pdl = true; /* launch the step kernel with programmatic stream serialization */
     int host_chunks = 2; /* pipeline depth of q1_step_host for large page-locked batches */
     bool balance_grid = false; /* step kernel: shrink the grid so that all CTAs walk equally many tiles */
+    int64_t small_launch_tiles = 0; /* launches of at most this many tiles take the 7-CTAs-per-SM build */
     bool host_direct = true; /* q1_step_host: let the step kernel read / write page-locked host buffers
                                 itself (mapped memory over PCIe) instead of staging them through HBM */
     cudaStream_t host_stream = nullptr;
@@ -1031,6 +1037,13 @@ struct q1_env {
     size_t scratch_bytes = 0;
     void *bounce = nullptr;      /* page-locked, device-mapped staging of q1_step_host for small batches */
     size_t bounce_bytes = 0;
+    char *bounce_dev = nullptr;  /* the address the device reaches `bounce` under */
+    /* Set by every entry point that launches on a CALLER's stream (q1_step, q1_reset_all / _masked,
+     * q1_rollout, q1_rollout_record, q1_observe).  The *_host entry points run on the handle's private
+     * stream and return synchronised; when the handle has also been driven on caller streams they
+     * first wait for the device, so that a host call never reads or writes state a caller-stream
+     * launch is still working on.  Handles used through the *_host calls only never pay for it. */
+    bool caller_streams_used = false;
 };
 
 namespace {
@@ -1042,7 +1055,10 @@ struct DeviceGuard {
     {
         if (cudaGetDevice(&prev) != cudaSuccess)
             prev = -1;
-        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev)
+            prev = -1;          /* already current: nothing to switch, nothing to restore */
+        else
+            ok = cudaSetDevice(dev) == cudaSuccess;
     }
     ~DeviceGuard()
     {
@@ -1053,8 +1069,21 @@ struct DeviceGuard {
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+/* see q1_env::caller_streams_used */
+int order_after_caller_streams(q1_env *env)
+{
+    if (env->caller_streams_used) {
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) {
+            g_error = std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(err);
+            return Q1_ECUDA;
+        }
+    }
+    return Q1_OK;
+}
+
 /* env.Config -> the numbers the kernels use, each in the width the reference computes it in. */
-int derive_params(const q1_config &c, Params &P, bool &counters_exact)
+int derive_params(const q1_config &c, Params &P, bool &counters_exact, bool numpy1_promotion = false)
 {
     if (c.num_envs <= 0)
         return fail(Q1_EINVAL, "num_envs must be positive");
@@ -1068,7 +1097,12 @@ int derive_params(const q1_config &c, Params &P, bool &counters_exact)
     P.dt = c.time_delta;
     P.time_limit = c.time_limit;
     P.key_delay = c.key_press_delay;
-    P.max_yaw_delta = (double)(720.0f * (float)c.time_delta); /* env:230 under NEP 50 */
+    /* env:230 `_MAX_YAW_SPEED * time_delta`, np.float32(720) times a Python float: float32 under
+     * NumPy 2 (NEP 50, what the oracle and the golden fixtures were recorded with), float64 under the
+     * NumPy 1.18 the reference pins (requirements_q1physrl.txt:33).  Equal only when time_delta is a
+     * float32 value such as nothing the shipped configs use except through rounding: 1/72 and
+     * 0.013888888888888 give 10 +- 4e-7 vs 10 exactly. */
+    P.max_yaw_delta = numpy1_promotion ? 720.0 * c.time_delta : (double)(720.0f * (float)c.time_delta);
     P.action_range = c.action_range;
     P.yaw_steps = (double)c.discrete_yaw_steps;
     P.accel_dt = 10.0 * c.time_delta;
@@ -1237,7 +1271,7 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
     env->device = device;
     env->flags = flags;
     bool counters_exact = false;
-    int rc = derive_params(*cfg, env->P, counters_exact);
+    int rc = derive_params(*cfg, env->P, counters_exact, (flags & Q1_F_NUMPY1_PROMOTION) != 0);
     if (rc != Q1_OK) {
         delete env;
         return rc;
@@ -1251,6 +1285,9 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
         env->balance_grid = atoi(bg) != 0;
     if (const char *hd = getenv("Q1PHYS_HOST_DIRECT"))
         env->host_direct = atoi(hd) != 0;
+    env->small_launch_tiles = 4 * 7 * 148;    /* up to four waves of the small build (measured: see k_step_tma) */
+    if (const char *sl = getenv("Q1PHYS_SMALL_TILES"))
+        env->small_launch_tiles = atoll(sl);
     /* the reciprocal sequences assume positive divisors in a sane exponent range */
     auto sane = [](double v) { return v > 1e-100 && v < 1e100; };
     /* ... and that q = RN(a * RN(1/b)) is a faithful quotient (div_const3 in q1_tick.cuh) */
@@ -1286,17 +1323,28 @@ int q1_create(const q1_config *cfg, int device, uint64_t seed, uint64_t env_inde
         delete env;
         return fail(Q1_ECUDA, "cudaSetDevice failed");
     }
-    cudaDeviceGetAttribute(&env->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (env->sm_count <= 0)
-        env->sm_count = 148;
+    if (cudaDeviceGetAttribute(&env->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        env->sm_count <= 0) {
+        delete env;
+        return fail(Q1_ECUDA, "cudaDeviceGetAttribute(multiProcessorCount) failed");
+    }
     /* kStepCtasPerSm CTAs x 21 KB of staging must fit: ask for the large shared-memory carveout */
     {
-        const void *fns[] = {(const void *)k_step_tma<false, false, false>, (const void *)k_step_tma<false, false, true>,
-                             (const void *)k_step_tma<false, true, false>,  (const void *)k_step_tma<false, true, true>,
-                             (const void *)k_step_tma<true, false, false>,  (const void *)k_step_tma<true, false, true>,
-                             (const void *)k_step_tma<true, true, false>,   (const void *)k_step_tma<true, true, true>};
-        for (const void *f : fns)
-            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define Q1_TMA_VARIANTS(C)                                                                              \
+    (const void *)k_step_tma<false, false, false, C>, (const void *)k_step_tma<false, false, true, C>,      \
+    (const void *)k_step_tma<false, true, false, C>, (const void *)k_step_tma<false, true, true, C>,        \
+    (const void *)k_step_tma<true, false, false, C>, (const void *)k_step_tma<true, false, true, C>,        \
+    (const void *)k_step_tma<true, true, false, C>, (const void *)k_step_tma<true, true, true, C>
+        const void *fns[] = {Q1_TMA_VARIANTS(kStepCtasPerSm), Q1_TMA_VARIANTS(kStepCtasSmall)};
+#undef Q1_TMA_VARIANTS
+        for (const void *f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (e != cudaSuccess) {
+                delete env;
+                return fail(Q1_ECUDA, std::string("cudaFuncSetAttribute(shared-memory carveout): ") +
+                                          cudaGetErrorString(e));
+            }
+        }
     }
     cudaError_t err = cudaMalloc(&env->pool, env->pool_bytes);
     if (err != cudaSuccess) {
@@ -1325,23 +1373,31 @@ int q1_destroy(q1_env *env)
     if (!env)
         return Q1_OK;
     DeviceGuard guard(env->device);
+    /* everything is released whatever fails; the first failure is what the caller hears about */
+    cudaError_t first = cudaSuccess;
+    auto note = [&](cudaError_t e) {
+        if (e != cudaSuccess && first == cudaSuccess)
+            first = e;
+    };
     if (env->scratch)
-        cudaFree(env->scratch);
+        note(cudaFree(env->scratch));
     if (env->bounce)
-        cudaFreeHost(env->bounce);
+        note(cudaFreeHost(env->bounce));
     if (env->host_stream)
-        cudaStreamDestroy(env->host_stream);
+        note(cudaStreamDestroy(env->host_stream));
     if (env->in_stream) {
-        cudaStreamDestroy(env->in_stream);
-        cudaStreamDestroy(env->out_stream);
+        note(cudaStreamDestroy(env->in_stream));
+        note(cudaStreamDestroy(env->out_stream));
         for (int c = 0; c < 8; c++) {
-            cudaEventDestroy(env->ev_in[c]);
-            cudaEventDestroy(env->ev_done[c]);
+            note(cudaEventDestroy(env->ev_in[c]));
+            note(cudaEventDestroy(env->ev_done[c]));
         }
     }
     if (env->pool)
-        cudaFree(env->pool);
+        note(cudaFree(env->pool));
     delete env;
+    if (first != cudaSuccess)
+        return fail(Q1_ECUDA, std::string("q1_destroy: ") + cudaGetErrorString(first));
     return Q1_OK;
 }
 
@@ -1387,6 +1443,7 @@ int q1_reset_all(q1_env *env, float *obs, void *stream)
     if (!env)
         return fail(Q1_EINVAL, "env is NULL");
     DeviceGuard guard(env->device);
+    env->caller_streams_used = true;
     return reset_launch(env, nullptr, -1, obs, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -1395,6 +1452,7 @@ int q1_reset_masked(q1_env *env, const uint8_t *mask, float *obs, void *stream)
     if (!env || !mask)
         return fail(Q1_EINVAL, "env / mask is NULL");
     DeviceGuard guard(env->device);
+    env->caller_streams_used = true;
     return reset_launch(env, mask, -1, obs, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -1405,6 +1463,8 @@ static int reset_host(q1_env *env, const uint8_t *mask_host, float *obs_host)
     const size_t n = (size_t)env->P.n;
     size_t o_obs = align_up(n);
     int rc = ensure_scratch(env, o_obs + align_up(24 * n));
+    if (rc == Q1_OK)
+        rc = order_after_caller_streams(env);
     if (rc != Q1_OK)
         return rc;
     char *d = static_cast<char *>(env->scratch);
@@ -1448,6 +1508,8 @@ int q1_reset_at_host(q1_env *env, int64_t index, float *obs6_host)
         return fail(Q1_EINVAL, "env index out of range");
     DeviceGuard guard(env->device);
     int rc = ensure_scratch(env, 64);
+    if (rc == Q1_OK)
+        rc = order_after_caller_streams(env);
     if (rc != Q1_OK)
         return rc;
     float *d_obs = static_cast<float *>(env->scratch);
@@ -1487,7 +1549,8 @@ static int step_range(q1_env *env, const uint8_t *keys, const void *mouse, int m
                             !env->P.speed_reward && mouse_kind == Q1_MOUSE_F32;
         rc = dispatch(env, [&](auto, auto tr, auto ln) {
             const int64_t ntiles = tile_end - tile_begin;
-            const int64_t resident = (int64_t)env->sm_count * kStepCtasPerSm;
+            const bool small = ntiles <= env->small_launch_tiles;
+            const int64_t resident = (int64_t)env->sm_count * (small ? kStepCtasSmall : kStepCtasPerSm);
             int64_t g = std::min<int64_t>(ntiles, resident);
             if (env->balance_grid && ntiles > resident) {
                 /* same number of rounds, but every CTA walks (almost) the same number of tiles */
@@ -1504,13 +1567,18 @@ static int step_range(q1_env *env, const uint8_t *keys, const void *mouse, int m
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = env->pdl ? 1 : 0;
-            cudaError_t err =
-                common ? cudaLaunchKernelEx(&cfg, k_step_tma<decltype(tr)::value, decltype(ln)::value, true>,
-                                            env->P, keys, mouse, mouse_kind, obs, reward, done,
-                                            zero_start, auto_reset, tile_begin, tile_end)
-                       : cudaLaunchKernelEx(&cfg, k_step_tma<decltype(tr)::value, decltype(ln)::value, false>,
-                                            env->P, keys, mouse, mouse_kind, obs, reward, done,
-                                            zero_start, auto_reset, tile_begin, tile_end);
+            constexpr bool TR = decltype(tr)::value, LN = decltype(ln)::value;
+            auto launch = [&](auto kernel) {
+                return cudaLaunchKernelEx(&cfg, kernel, env->P, keys, mouse, mouse_kind, obs, reward, done,
+                                          zero_start, auto_reset, tile_begin, tile_end);
+            };
+            cudaError_t err;
+            if (small)
+                err = common ? launch(k_step_tma<TR, LN, true, kStepCtasSmall>)
+                             : launch(k_step_tma<TR, LN, false, kStepCtasSmall>);
+            else
+                err = common ? launch(k_step_tma<TR, LN, true, kStepCtasPerSm>)
+                             : launch(k_step_tma<TR, LN, false, kStepCtasPerSm>);
             if (err != cudaSuccess)
                 return fail(Q1_ECUDA, std::string("k_step_tma launch: ") + cudaGetErrorString(err));
             return check_launch("k_step_tma");
@@ -1550,6 +1618,7 @@ int q1_step(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_kind,
     if (env->P.allow_yaw && !mouse)
         return fail(Q1_EINVAL, "mouse is NULL but allow_yaw is set");
     DeviceGuard guard(env->device);
+    env->caller_streams_used = true;
     int rc = step_range(env, keys, mouse, mouse_kind, obs, reward, done, zero_start, auto_reset, 0,
                         env->P.n, static_cast<cudaStream_t>(stream));
     if (rc == Q1_OK)
@@ -1605,9 +1674,16 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
     if (!env->host_stream)
         Q1_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
     cudaStream_t s = env->host_stream;
-    int rc = Q1_OK;
+    int rc = order_after_caller_streams(env);
+    if (rc != Q1_OK)
+        return rc;
 
-    const bool all_pinned = is_pinned(keys) && is_pinned(obs) && is_pinned(reward) && is_pinned(done) &&
+    /* Up to kBounceAlways envs -- RLLib's 100 per worker, the gym-style single env -- the bounce route
+     * below is taken without asking the driver what kind of memory the seven buffers are (six pointer
+     * queries cost more than copying a few KB); larger batches are worth the question. */
+    constexpr size_t kBounceAlways = 8192;
+    const bool ask = n > kBounceAlways || !env->host_direct;
+    const bool all_pinned = ask && is_pinned(keys) && is_pinned(obs) && is_pinned(reward) && is_pinned(done) &&
                             (!env->P.allow_yaw || is_pinned(mouse)) && (!zero_start || is_pinned(zero_start));
     if (all_pinned && env->host_direct) {
         /* Page-locked buffers are mapped into the device's address space: the step kernel bulk-loads
@@ -1640,9 +1716,10 @@ int q1_step_host(q1_env *env, const uint8_t *keys, const void *mouse, int mouse_
             env->bounce_bytes = 0;
             Q1_CUDA(cudaHostAlloc(&env->bounce, total, cudaHostAllocMapped));
             env->bounce_bytes = total;
+            env->bounce_dev = device_view(static_cast<char *>(env->bounce));
         }
         char *h = static_cast<char *>(env->bounce);
-        char *m = device_view(h);
+        char *m = env->bounce_dev;
         if (m) {
             std::memcpy(h + o_keys, keys, n * nk);
             if (env->P.allow_yaw)
@@ -1771,6 +1848,7 @@ int q1_rollout(q1_env *env, int policy, int ticks, uint64_t policy_seed, float *
         return fail(Q1_EINVAL, "ticks must be >= 0");
     DeviceGuard guard(env->device);
     const ActionFeed feed = {policy, policy_seed, nullptr, nullptr, Q1_MOUSE_F32};
+    env->caller_streams_used = true;
     return rollout_launch(env, feed, ticks, obs, reward_sum, 1, 0u, nullptr,
                           static_cast<cudaStream_t>(stream));
 }
@@ -1805,6 +1883,7 @@ int q1_rollout_record(q1_env *env, const q1_action_source *actions, int ticks, i
     DeviceGuard guard(env->device);
     const ActionFeed feed = {actions->kind == Q1_ACTIONS_BUILTIN ? actions->builtin_policy : -1,
                              actions->policy_seed, actions->keys, actions->mouse, actions->mouse_kind};
+    env->caller_streams_used = true;
     return rollout_launch(env, feed, ticks, final_obs, nullptr, auto_reset, record_flags, record,
                           static_cast<cudaStream_t>(stream));
 }
@@ -1839,6 +1918,8 @@ int q1_rollout_record_host(q1_env *env, const q1_action_source *actions, int tic
         off = align_up(off + f[k].bytes);
     }
     rc = ensure_scratch(env, off + 256);
+    if (rc == Q1_OK)
+        rc = order_after_caller_streams(env);
     if (rc != Q1_OK)
         return rc;
     char *d = static_cast<char *>(env->scratch);
@@ -1888,17 +1969,22 @@ int q1_advance_ticks(q1_env *env, int64_t delta)
     return Q1_OK;
 }
 
-int q1_observe(q1_env *env, float *obs, void *stream)
+static int observe_launch(q1_env *env, float *obs, cudaStream_t s)
 {
-    if (!env || !obs)
-        return fail(Q1_EINVAL, "env / obs is NULL");
-    DeviceGuard guard(env->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     return dispatch(env, [&](auto st, auto, auto ln) {
         k_observe<decltype(st)::value, decltype(ln)::value>
             <<<grid_for(env->P.n), kBlock, 0, s>>>(env->P, obs);
         return check_launch("k_observe");
     });
+}
+
+int q1_observe(q1_env *env, float *obs, void *stream)
+{
+    if (!env || !obs)
+        return fail(Q1_EINVAL, "env / obs is NULL");
+    DeviceGuard guard(env->device);
+    env->caller_streams_used = true;
+    return observe_launch(env, obs, static_cast<cudaStream_t>(stream));
 }
 
 int q1_observe_host(q1_env *env, float *obs_host)
@@ -1911,7 +1997,10 @@ int q1_observe_host(q1_env *env, float *obs_host)
     if (rc != Q1_OK)
         return rc;
     float *d_obs = static_cast<float *>(env->scratch);
-    rc = q1_observe(env, d_obs, env->host_stream);
+    rc = order_after_caller_streams(env);
+    if (rc != Q1_OK)
+        return rc;
+    rc = observe_launch(env, d_obs, env->host_stream);
     if (rc != Q1_OK)
         return rc;
     Q1_CUDA(cudaMemcpyAsync(obs_host, d_obs, 24 * n, cudaMemcpyDeviceToHost, env->host_stream));
@@ -1928,7 +2017,24 @@ struct SnapshotHeader {
     uint64_t magic, pool_bytes, ticks, seed, env_index_base;
     int64_t n;
     int32_t num_keys, stamps, track, abi;
+    uint64_t config_hash;   /* FNV-1a of the q1_config and the create flags the image was taken under */
 };
+
+uint64_t config_hash(const q1_env *env)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&](const void *p, size_t bytes) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < bytes; i++)
+            h = (h ^ b[i]) * 0x100000001b3ull;
+    };
+    q1_config c = env->cfg;
+    c.reserved = 0;
+    mix(&c, sizeof c);
+    const uint32_t flags = env->flags & (Q1_F_NUMPY1_PROMOTION | Q1_F_IEEE_DIVISION);
+    mix(&flags, sizeof flags);
+    return h;
+}
 constexpr uint64_t kSnapshotMagic = 0x51315048595353ull; /* "Q1PHYSS" */
 } // namespace
 
@@ -1949,7 +2055,8 @@ int q1_snapshot_save_host(q1_env *env, void *buffer, uint64_t bytes)
     DeviceGuard guard(env->device);
     Q1_CUDA(cudaDeviceSynchronize());
     SnapshotHeader h = {kSnapshotMagic, env->pool_bytes, env->ticks, env->P.seed, env->P.env_index_base,
-                        env->P.n, env->P.num_keys, env->stamps ? 1 : 0, env->track ? 1 : 0, Q1_ABI_VERSION};
+                        env->P.n, env->P.num_keys, env->stamps ? 1 : 0, env->track ? 1 : 0, Q1_ABI_VERSION,
+                        config_hash(env)};
     std::memcpy(buffer, &h, sizeof h);
     Q1_CUDA(cudaMemcpy(static_cast<char *>(buffer) + sizeof h, env->pool, env->pool_bytes,
                        cudaMemcpyDeviceToHost));
@@ -1970,6 +2077,9 @@ int q1_snapshot_load_host(q1_env *env, const void *buffer, uint64_t bytes)
         h.track != (env->track ? 1 : 0) || h.pool_bytes != env->pool_bytes ||
         bytes < sizeof h + h.pool_bytes)
         return fail(Q1_EINVAL, "snapshot was taken from a handle with another size / key count / flags");
+    if (h.config_hash != config_hash(env))
+        return fail(Q1_EINVAL, "snapshot was taken under another Config (time_delta, time_limit, key_press_delay "
+                               "... differ): it would not continue the run it was saved from");
     DeviceGuard guard(env->device);
     Q1_CUDA(cudaDeviceSynchronize());
     Q1_CUDA(cudaMemcpy(env->pool, static_cast<const char *>(buffer) + sizeof h, env->pool_bytes,
@@ -2312,7 +2422,7 @@ int q1_decode_host(const q1_config *cfg, int device, int64_t n, uint8_t *last_ke
     c.num_envs = n;
     Params P{};
     bool unused = false;
-    int rc = derive_params(c, P, unused);
+    int rc = derive_params(c, P, unused, (cfg->reserved & 1) != 0);
     if (rc != Q1_OK)
         return rc;
     DeviceGuard guard(device);

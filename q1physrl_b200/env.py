@@ -23,6 +23,8 @@ There is no CPU implementation here: without `libq1phys.so` and a CUDA device ev
 import ctypes
 import dataclasses
 import enum
+import warnings
+import weakref
 from collections.abc import Sequence
 from typing import Optional, Tuple, Union
 
@@ -180,6 +182,8 @@ try:                                     # built by _build.build_fastfix(); opti
     from . import _fastfix
 except ImportError:                      # pragma: no cover - the NumPy routes below serve
     _fastfix = None
+if _fastfix is not None and not hasattr(_fastfix, "step"):   # a stale build of an older source
+    _fastfix = None
 
 
 def _fix_actions(actions, width):
@@ -229,10 +233,11 @@ class ActionDecoder:
     _last_keys: np.ndarray
     _yaw: np.ndarray
 
-    def __init__(self, config: Config, device: int = 0):
+    def __init__(self, config: Config, device: int = 0, numpy1_promotion: bool = False):
         self._config = config
         self._num_keys = _num_keys(config)
         self._device = device
+        self._numpy1_promotion = bool(numpy1_promotion)   # see VectorPhysEnv(numpy1_promotion=...)
 
     @property
     def action_space(self):
@@ -263,6 +268,7 @@ class ActionDecoder:
         fmove = np.empty(n, np.int64)
         jump = np.empty(n, np.uint8)
         cfg = _pod_config(self._config, n)
+        cfg.reserved = int(self._numpy1_promotion)
         _lib.check(_lib.load().q1_decode_host(
             ctypes.byref(cfg), self._device, n, _ptr(last_keys), _ptr(last_press), _ptr(yaw),
             _ptr(keys), _ptr(mouse), _ptr(z_vel), _ptr(tr), _ptr(smove), _ptr(fmove), _ptr(jump)))
@@ -306,26 +312,35 @@ except ImportError:
     VectorEnv = object
 
 
+class _PinnedBlock:
+    """One page-locked allocation of q1_host_alloc.  NumPy arrays made from it keep it alive through
+    their `.base`; the memory is returned with q1_host_free when the LAST such array (and the pool
+    that handed it out) is gone -- never while a caller still holds a view, e.g. the observations a
+    `vector_step` with reuse_output_buffers returned from an env that has since been closed."""
+
+    def __init__(self, nbytes):
+        p = ctypes.c_void_p()
+        _lib.check(_lib.load().q1_host_alloc(max(1, nbytes), ctypes.byref(p)))
+        self.__array_interface__ = {"data": (p.value, False), "shape": (max(1, nbytes),),
+                                    "typestr": "|u1", "version": 3}
+        weakref.finalize(self, _lib.load().q1_host_free, p)
+
+
 class _PinnedPool:
-    """Page-locked host arrays from q1_host_alloc, freed with the env."""
+    """Page-locked host arrays; see _PinnedBlock for their lifetime."""
 
     def __init__(self):
-        self._ptrs = []
+        self._blocks = []
 
     def empty(self, shape, dtype):
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
-        p = ctypes.c_void_p()
-        _lib.check(_lib.load().q1_host_alloc(max(1, count * dtype.itemsize), ctypes.byref(p)))
-        self._ptrs.append(p)
-        buf = (ctypes.c_char * max(1, count * dtype.itemsize)).from_address(p.value)
-        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        block = _PinnedBlock(count * dtype.itemsize)
+        self._blocks.append(block)
+        return np.asarray(block)[:count * dtype.itemsize].view(dtype).reshape(shape)
 
     def close(self):
-        lib = _lib.load()
-        for p in self._ptrs:
-            lib.q1_host_free(p)
-        self._ptrs = []
+        self._blocks = []          # blocks still referenced by live arrays stay allocated
 
 
 _STATE_FIELDS = ("vel", "z_pos", "yaw", "time_remaining", "on_ground", "jump_released",
@@ -346,6 +361,10 @@ class VectorPhysEnv(VectorEnv):
                         whenever those are provably equivalent)
       ieee_division     divide with the CUDA IEEE intrinsics instead of the branch-free reciprocal
                         sequences (same results, slower; used by the self-checks)
+      numpy1_promotion  evaluate env:230 `np.float32(720) * time_delta` in float64, as the NumPy 1.18
+                        the reference pins does (default: NumPy 2's float32 product, which is what
+                        the oracle and every golden fixture were recorded under; the two differ by
+                        ~4e-8 relative in every yaw increment unless time_delta is a float32 value)
       reuse_output_buffers  return views of two alternating page-locked buffer sets from
                         `vector_step` instead of fresh arrays (default: only for num_envs >= 65536)
 
@@ -358,7 +377,7 @@ class VectorPhysEnv(VectorEnv):
     def __init__(self, config, *, device: int = 0, seed: Optional[int] = None,
                  env_index_base: int = 0, track_returns: bool = False,
                  f64_key_stamps: bool = False, ieee_division: bool = False,
-                 reuse_output_buffers: Optional[bool] = None):
+                 numpy1_promotion: bool = False, reuse_output_buffers: Optional[bool] = None):
         if isinstance(config, dict):
             config = Config(**config)
         self._config = config
@@ -381,11 +400,13 @@ class VectorPhysEnv(VectorEnv):
         self._seed = int(seed)
         flags = (_lib.Q1_F_TRACK_RETURNS if track_returns else 0) | \
                 (_lib.Q1_F_FORCE_F64_STAMPS if f64_key_stamps else 0) | \
-                (_lib.Q1_F_IEEE_DIVISION if ieee_division else 0)
+                (_lib.Q1_F_IEEE_DIVISION if ieee_division else 0) | \
+                (_lib.Q1_F_NUMPY1_PROMOTION if numpy1_promotion else 0)
         self._handle = ctypes.c_void_p()
         cfg = _pod_config(self._config, self.num_envs)
         _lib.check(self._lib.q1_create(ctypes.byref(cfg), self._device, self._seed,
                                        int(env_index_base), flags, ctypes.byref(self._handle)))
+        self._step_host_addr = ctypes.cast(self._lib.q1_step_host, ctypes.c_void_p).value
         self._track_returns = bool(track_returns)
         if reuse_output_buffers is None:
             reuse_output_buffers = self.num_envs >= 65536
@@ -397,15 +418,20 @@ class VectorPhysEnv(VectorEnv):
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
+        """Release the device state.  Raises if the library reports a failure; page-locked arrays
+        this env handed out stay valid for as long as the caller keeps them."""
         h, self._handle = getattr(self, "_handle", None), None
         if h:
-            self._lib.q1_destroy(h)
+            self._out_sets = []
             self._pinned.close()
+            _lib.check(self._lib.q1_destroy(h))
 
-    def __del__(self):
+    def __del__(self, _error=_lib.Q1Error, _warn=warnings.warn):
         try:
             self.close()
-        except Exception:
+        except _error as exc:            # cannot raise from a finaliser: say so instead of hiding it
+            _warn(f"VectorPhysEnv.__del__: {exc}", ResourceWarning)
+        except Exception:                # interpreter shutdown: modules are already torn down
             pass
 
     @property
@@ -430,14 +456,14 @@ class VectorPhysEnv(VectorEnv):
     def _outputs(self):
         n = self.num_envs
         if not self._reuse:
-            return (np.empty((n, 6), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8),
-                    np.empty(n, np.uint8))
+            return (np.empty((n, 6), np.float32), np.empty(n, np.float32), np.empty(n, np.bool_),
+                    np.empty(n, np.bool_))
         if not self._out_sets:
             for _ in range(2):
                 self._out_sets.append((self._pinned.empty((n, 6), np.float32),
                                        self._pinned.empty((n,), np.float32),
-                                       self._pinned.empty((n,), np.uint8),
-                                       self._pinned.empty((n,), np.uint8)))
+                                       self._pinned.empty((n,), np.bool_),
+                                       self._pinned.empty((n,), np.bool_)))
         self._out_turn ^= 1
         return self._out_sets[self._out_turn]
 
@@ -490,7 +516,7 @@ class VectorPhysEnv(VectorEnv):
             else:
                 mouse, kind = np.ascontiguousarray(mouse, dtype=np.float64), _lib.Q1_MOUSE_F64
         else:
-            keys, mouse = _split_actions(self._config, self._num_keys, actions)
+            keys, mouse = self._split_fast(actions)
             kind = _lib.Q1_MOUSE_F64
         if keys.shape != (self.num_envs, self._num_keys):
             raise ValueError(f"expected {self.num_envs} actions with {self._num_keys} keys, "
@@ -498,10 +524,32 @@ class VectorPhysEnv(VectorEnv):
         if mouse is not None and mouse.shape != (self.num_envs,):
             raise ValueError(f"mouse action must have shape ({self.num_envs},), got {mouse.shape}")
         obs, reward, done, zs = self._outputs()
-        _lib.check(self._lib.q1_step_host(self._handle, _ptr(keys), _ptr(mouse), kind, _ptr(obs),
-                                          _ptr(reward), _ptr(done), _ptr(zs), int(bool(auto_reset))))
+        if _fastfix is not None:
+            # the C call made directly on the arrays' buffers (csrc/fastfix.c `step`): no ctypes
+            # marshalling, which at RLLib's 100 envs per worker costs as much as the GPU work
+            rc = _fastfix.step(self._step_host_addr, self._handle.value, keys, mouse, kind, obs, reward,
+                               done, zs, bool(auto_reset))
+            if rc:
+                _lib.check(rc)
+        else:
+            _lib.check(self._lib.q1_step_host(self._handle, _ptr(keys), _ptr(mouse), kind, _ptr(obs),
+                                              _ptr(reward), _ptr(done), _ptr(zs), int(bool(auto_reset))))
         self._step_num += 1
-        return obs, reward, done.view(np.bool_), _InfoList(zs.view(np.bool_))
+        return obs, reward, done, _InfoList(zs)
+
+    def _split_fast(self, actions):
+        """RLLib's list of per-env tuples -> (keys, mouse) in one C walk (csrc/fastfix.c
+        `split_actions`); anything that walk does not recognise goes the general way."""
+        if _fastfix is not None and isinstance(actions, (list, tuple)) and len(actions) \
+                and isinstance(actions[0], (list, tuple)):
+            keys = np.empty((len(actions), self._num_keys), np.uint8)
+            mouse = np.empty(len(actions), np.float64) if self._config.allow_yaw else None
+            try:
+                _fastfix.split_actions(actions, self._num_keys, bool(self._config.allow_yaw), keys, mouse)
+                return keys, mouse
+            except (TypeError, ValueError):
+                pass
+        return _split_actions(self._config, self._num_keys, actions)
 
     def get_unwrapped(self):
         return []

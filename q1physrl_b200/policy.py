@@ -189,6 +189,10 @@ def rollout(env, policy, ticks, deterministic=False, graph=True, ticks_per_graph
         for _ in range(ticks - 3 - replays * per):
             tick()
         torch.cuda.current_stream(dev).synchronize()
+        # the library (and this wrapper) counted the captured ticks once, when they were captured;
+        # the capture executed nothing and the replays executed replays * per ticks
+        _lib.check(_lib.load().q1_advance_ticks(env.handle, (replays - 1) * per))
+        env._step_num += (replays - 1) * per
         if timing is not None:
             timing.update(ticks=replays * per, seconds=e0.elapsed_time(e1) * 1e-3)
     finally:

@@ -35,6 +35,11 @@ def test_pod_layouts_match_header():
     assert ctypes.sizeof(_lib.Q1EnvInfo) == 8 + 6 * 4 + 3 * 8
     assert ctypes.sizeof(_lib.Q1StateView) == 10 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.Q1Metrics) == 5 * 8
+    assert ctypes.sizeof(_lib.Q1ActionSource) == 4 + 4 + 8 + 8 + 8 + 4 + 4   # q1_action_source
+    assert ctypes.sizeof(_lib.Q1RecordView) == 14 * ctypes.sizeof(ctypes.c_void_p)
+    header = open(os.path.join(ROOT, "include", "q1phys.h")).read()
+    view = header[header.index("typedef struct q1_record_view"):header.index("} q1_record_view;")]
+    assert tuple(re.findall(r"\*(\w+);", view)) == _lib.RECORD_FIELDS    # same members, same order
 
 
 def test_no_device_is_a_loud_error():
@@ -159,6 +164,65 @@ def test_fast_action_normalisation_equals_the_reference_expression():
         ref_env, _ = refshim.load()
         dec = ref_env.ActionDecoder(ref_env.Config.get_default())
         assert np.array_equal(np.asarray(dec._fix_actions(actions), np.float64), want)
+
+
+def test_split_actions_equals_the_reference_expressions():
+    """csrc/fastfix.c `split_actions` (the list-of-tuples route of vector_step) == env.py:221-223 followed
+    by env.py:228 `.astype(np.int)` (& 1, which is all env:243 sees of 0/1 keys) and the mouse column."""
+    from q1physrl_b200 import env as benv
+    assert benv._fastfix is not None
+    rng = np.random.default_rng(6)
+    n, nk = 301, 4
+    wrap = [int, float, np.int64, np.float32, lambda v: np.array([v]), lambda v: np.array([v], np.float32),
+            lambda v: [v]]
+    actions = []
+    for i in range(n):
+        keys = [wrap[rng.integers(len(wrap))](int(rng.integers(0, 2))) for _ in range(nk)]
+        if i % 7 == 0:
+            keys[1] = 3.7                                          # truncates to 3 -> bit 0 = 1
+        mouse = [float, np.float32, lambda v: np.array([v], np.float32)][rng.integers(3)](rng.uniform(-10, 10))
+        actions.append(tuple(keys + [mouse]))
+    ref = np.array([[np.ravel(x)[0] for x in a] for a in actions], dtype=np.float64)
+    want_keys = (ref[:, :nk].astype(np.int64) & 1).astype(np.uint8)
+    for allow_yaw in (True, False):
+        keys = np.empty((n, nk), np.uint8)
+        mouse = np.empty(n, np.float64) if allow_yaw else None
+        benv._fastfix.split_actions(actions, nk, allow_yaw, keys, mouse)
+        assert np.array_equal(keys, want_keys)
+        if allow_yaw:
+            assert np.array_equal(mouse, ref[:, nk])
+    with pytest.raises((TypeError, ValueError)):
+        benv._fastfix.split_actions([(1, 0, 1)], nk, True, np.empty((1, nk), np.uint8), np.empty(1))
+    with pytest.raises((TypeError, ValueError)):
+        benv._fastfix.split_actions([(1, 0, 1, float("nan"), 0.0)], nk, True, np.empty((1, nk), np.uint8), np.empty(1))
+    with pytest.raises((TypeError, ValueError)):
+        benv._fastfix.split_actions(actions, nk, True, np.empty((n - 1, nk), np.uint8), np.empty(n))
+
+
+def test_gym_make_registration_with_a_stub_gym():
+    """env.py:516-521: importing the env module registers 'Q1PhysEnv-v0' with gym.  Neither gym nor
+    gymnasium is installed here, so the branch is exercised with the stub the oracle's shim uses, in
+    a fresh interpreter (the module must be imported AFTER gym exists)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import refshim\n"
+        "refshim._install_gym_stub()\n"
+        "import gym\n"
+        "from q1physrl_b200 import env\n"
+        "spec = gym.envs.registration.registry['Q1PhysEnv-v0']\n"
+        "assert spec['entry_point'] == 'q1physrl_b200.env:PhysEnv' and spec['nondeterministic'] is False\n"
+        "assert spec['kwargs'] == {'config': env.Config.get_default()}\n"
+        "import importlib\n"
+        "mod, cls = spec['entry_point'].split(':')\n"
+        "assert getattr(importlib.import_module(mod), cls) is env.PhysEnv\n"
+        "assert issubclass(env.PhysEnv, gym.Env)\n"
+        "import q1physrl_env.env as alias       # the alias package must not register twice / fail\n"
+        "assert alias.PhysEnv is env.PhysEnv\n"
+        "print('registered')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "registered" in out.stdout, out.stderr
 
 
 def test_cpu_binding_is_a_no_op_without_a_gpu():

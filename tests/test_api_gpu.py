@@ -254,3 +254,111 @@ def test_mkdemo_adapters_golden(tag):
     assert np.array_equal(np.array([int(x["buttons"]) for x in m]), g[f"{tag}_move_buttons"])
     assert all(x["pitch"] == 0 and x["roll"] == 0 and x["up"] == 0 and x["impulse"] == 0 for x in m)
     assert np.array_equal(dec._last_key_press_time, g[f"{tag}_final_last_press"])
+
+
+def test_page_locked_outputs_outlive_the_env():
+    """with reuse_output_buffers the arrays vector_step returns are views of page-locked
+    memory; closing (or dropping) the env must not free it under them."""
+    import gc
+    from q1physrl_b200 import env as benv
+
+    def step_and_drop():
+        e = benv.VectorPhysEnv(dict(harness.PARAMS_100M, num_envs=4096), seed=3, reuse_output_buffers=True)
+        keys = e.pinned_empty((4096, 4), np.uint8)
+        keys[...] = 1
+        mouse = e.pinned_empty((4096,), np.float32)
+        mouse[...] = 0.5
+        obs, rew, done, _ = e.vector_step((keys, mouse))
+        copy = obs.copy()
+        e.close()
+        return obs, copy, keys
+
+    obs, copy, keys = step_and_drop()
+    gc.collect()
+    junk = [np.ones(1 << 20) for _ in range(8)]               # churn the allocator
+    assert np.array_equal(obs, copy) and keys.all()
+    obs[...] = 7                                               # still writable memory
+    assert (obs == 7).all()
+    del junk
+
+
+def test_host_calls_are_ordered_after_caller_stream_launches():
+    """the *_host entry points run on the handle's own stream; after launches on a caller's
+    stream (step_tensors, rollout) they must wait for that work instead of racing it."""
+    import torch
+    from q1physrl_b200 import env as benv
+    n = 1 << 18
+    cfg = dict(harness.PARAMS_100M, num_envs=n)
+    a = benv.VectorPhysEnv(cfg, seed=5)
+    b = benv.VectorPhysEnv(cfg, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    keys = torch.randint(0, 2, (n, 4), generator=g, device="cuda", dtype=torch.uint8)
+    mouse = torch.rand(n, generator=g, device="cuda") * 20 - 10
+    side = torch.cuda.Stream()
+    for rep in range(5):
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                a.step_tensors(keys, mouse)                    # asynchronous on `side`
+        ra = a.reset_at(17)                                    # host path, right behind them
+        oa = a._get_obs()
+        hk, hm = keys.cpu().numpy(), mouse.cpu().numpy()
+        sa = a.vector_step((hk, hm))
+        for _ in range(20):
+            b.step_tensors(keys, mouse)
+        torch.cuda.synchronize()
+        rb = b.reset_at(17)
+        ob = b._get_obs()
+        sb = b.vector_step((hk, hm))
+        assert np.array_equal(ra, rb) and np.array_equal(oa, ob)
+        assert all(np.array_equal(x, y) for x, y in zip(sa[:3], sb[:3]))
+    sa, sb = a.get_state(), b.get_state()
+    assert all(np.array_equal(sa[f], sb[f]) for f in sa)
+
+
+def test_numpy1_promotion_flag():
+    """env:230 is float32 under NumPy 2 (default, what every fixture was recorded with) and
+    float64 under the NumPy 1.18 the reference pins; the flag selects the latter."""
+    from q1physrl_b200 import env as benv
+    cfg = dict(harness.PARAMS_100M, num_envs=64, time_delta=0.014, action_range=float(np.float32(10.08)),
+               zero_start_prob=1.0)
+    e2 = benv.VectorPhysEnv(cfg, seed=1)
+    e1 = benv.VectorPhysEnv(cfg, seed=1, numpy1_promotion=True)
+    keys = np.zeros((64, 4), np.uint8)
+    mouse = np.linspace(-10, 10, 64).astype(np.float32)
+    e2.vector_step((keys, mouse))
+    e1.vector_step((keys, mouse))
+    m = mouse.astype(np.float64)
+    assert np.array_equal(e2._yaw, 90 + m * np.float64(np.float32(720) * np.float32(0.014)) / np.float64(np.float32(10.08)))
+    assert np.array_equal(e1._yaw, 90 + m * (720.0 * 0.014) / np.float64(np.float32(10.08)))
+    assert not np.array_equal(e1._yaw, e2._yaw)
+    d1 = benv.ActionDecoder(benv.Config(**dict(cfg, num_envs=64)), numpy1_promotion=True)
+    d1.vector_reset(np.full(64, 90.0))
+    yaw, _, _, _ = d1.map((keys, mouse) and np.concatenate([keys, m[:, None]], axis=1), np.zeros(64, np.float32),
+                          np.full(64, 10.0))
+    assert np.array_equal(yaw, e1._yaw)
+
+
+def test_snapshot_refuses_another_config():
+    from q1physrl_b200 import env as benv, _lib
+    cfg = dict(harness.PARAMS_100M, num_envs=512)
+    a = benv.VectorPhysEnv(cfg, seed=1)
+    snap = a.snapshot()
+    benv.VectorPhysEnv(cfg, seed=9).restore(snap)              # same config: fine
+    for other in (dict(cfg, time_limit=5), dict(cfg, time_delta=1. / 72), dict(cfg, key_press_delay=0.2),
+                  dict(cfg, smove_max=700)):
+        with pytest.raises(_lib.Q1Error):
+            benv.VectorPhysEnv(other, seed=1).restore(snap)
+
+
+def test_graph_replays_advance_the_tick_counter():
+    import os
+    import torch  # noqa: F401
+    from q1physrl_b200 import env as benv, policy as bpolicy
+    path = os.path.join(harness.GOLDEN_DIR, "wr_policy.npz")
+    pol, env_config = bpolicy.FusedMLPPolicy.from_npz(path, seed=1)
+    cfg = dict(env_config, initial_yaw_range=tuple(env_config["initial_yaw_range"]), num_envs=2048)
+    e = benv.VectorPhysEnv(cfg, seed=2)
+    bpolicy.rollout(e, pol, 100)
+    assert e.info.ticks == 100 and e._step_num == 100
+    bpolicy.rollout(e, pol, 5, graph=False)
+    assert e.info.ticks == 105

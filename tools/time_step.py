@@ -13,7 +13,7 @@ from q1physrl_b200 import _lib, env as benv  # noqa: E402
 
 label = sys.argv[1] if len(sys.argv) > 1 else os.path.basename(_lib.library_path())
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
-ring = max(4, (1 << 22) // n)
+ring = int(os.environ.get("Q1_TIME_RING", max(4, (1 << 22) // n)))   # 1: the same shard every tick (L2-resident when small)
 steps, warmup = max(500, 8000 * (1 << 20) // n), 200
 dev = torch.device("cuda", 0)
 cfg = bench.workload_config(n)
@@ -30,8 +30,34 @@ outs = [(torch.empty((n, 6), dtype=torch.float32, device=dev), torch.empty(n, dt
 sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 calls = [(envs[r].handle, ctypes.c_void_p(keys[r].data_ptr()), ctypes.c_void_p(mouse[r].data_ptr()),
           _lib.Q1_MOUSE_F32, *(ctypes.c_void_p(o.data_ptr()) for o in outs[r]), 1, sp) for r in range(ring)]
+use_graph = bool(int(os.environ.get("Q1_TIME_GRAPH", "0")))   # 1: replay a CUDA graph of `ring` steps
+if use_graph:
+    for i in range(2 * ring):
+        lib.q1_step(*calls[i % ring])
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    sp2 = ctypes.c_void_p(side.cuda_stream)
+    gcalls = [c[:-1] + (sp2,) for c in calls]
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for i in range(ring):
+            lib.q1_step(*gcalls[i])
+    label += "+graph"
 best = 0.0
 for rep in range(3):
+    if use_graph:
+        for i in range(max(1, warmup // ring)):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(1, steps // ring)
+        e0.record()
+        for i in range(reps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, n * reps * ring / (e0.elapsed_time(e1) * 1e-3))
+        continue
     for i in range(warmup):
         lib.q1_step(*calls[i % ring])
     torch.cuda.synchronize()
