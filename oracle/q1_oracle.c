@@ -176,15 +176,17 @@ static void decode_one(const q1o_config *cfg, int nk, uint8_t *last_keys, double
                        double *yaw_state, const uint8_t *key, double mouse, float z_vel,
                        double time_remaining, command_t *out)
 {
-    /* env:230: np.float32(720) * python float -> f32 under NEP 50 */
-    float max_yaw_delta = Q_MAX_YAW_SPEED * (float)cfg->time_delta;
+    /* env:230: np.float32(720) * python float -> f32 under NEP 50 (NumPy 2, the default here); with
+     * cfg->reserved & 1 the float64 product NumPy < 2 forms (the reference pins numpy 1.18.2) */
+    double max_yaw_delta = (cfg->reserved & 1) ? 720.0 * cfg->time_delta
+                                               : (double)(Q_MAX_YAW_SPEED * (float)cfg->time_delta);
     double mouse_x;
     if (!cfg->allow_yaw)
         mouse_x = 0.;                                                            /* env:234 */
     else if (cfg->discrete_yaw_steps == -1)
-        mouse_x = mouse * (double)max_yaw_delta / cfg->action_range;             /* env:236 */
+        mouse_x = mouse * max_yaw_delta / cfg->action_range;                     /* env:236 */
     else
-        mouse_x = (mouse - cfg->discrete_yaw_steps) * (double)max_yaw_delta
+        mouse_x = (mouse - cfg->discrete_yaw_steps) * max_yaw_delta
                   / cfg->discrete_yaw_steps;                                     /* env:238 */
 
     double now = cfg->time_limit - time_remaining;

@@ -41,7 +41,7 @@ typedef struct q1o_config {
     int32_t smooth_keys;
     int32_t auto_jump;
     int32_t allow_jump;
-    int32_t reserved;
+    int32_t reserved;          /* bit 0: evaluate env:230 in float64, as NumPy < 2 does */
 } q1o_config;
 
 /* Per-env state, struct of arrays, the reference's own widths (SURVEY.md 8(a) "canonical state"). */

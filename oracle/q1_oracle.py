@@ -99,7 +99,7 @@ def make_config(cfg) -> OracleConfig:
         discrete_yaw_steps=int(val("discrete_yaw_steps")), allow_yaw=int(bool(val("allow_yaw"))),
         speed_reward=int(bool(val("speed_reward"))), hover=int(bool(val("hover"))),
         smooth_keys=int(bool(val("smooth_keys"))), auto_jump=int(bool(val("auto_jump"))),
-        allow_jump=int(bool(val("allow_jump"))), reserved=0)
+        allow_jump=int(bool(val("allow_jump"))), reserved=int(bool(_get(cfg, "numpy1_promotion", False))))
 
 
 def _ptr(a):

@@ -1,9 +1,10 @@
-"""Import the UNMODIFIED reference (`/root/reference/q1physrl_env`) in the build container.
+"""Import the UNMODIFIED reference env package: from the checkout (`/root/reference`, the build
+container) or, where that is absent (the GPU box), from the byte-for-byte staging `oracle/_ref/` that
+`oracle/stage_ref.py` makes.
 
-TEST INFRASTRUCTURE ONLY.  Used by `tests/golden/make_golden.py` (fixture generation) and by the
-`not gpu` tests that pin the oracle against the real reference when the checkout is mounted.  The
-reference cannot travel to the GPU box, so nothing on the `-m gpu` / smoke / bench path imports
-this module.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Used by `tests/golden/make_*.py` (fixture generation), by the
+`not gpu` tests that pin the oracle against the real reference, and by `oracle/numpy_tiers.py`
+(bench.py's NumPy cpu_baseline tiers).  Nothing under `q1physrl_b200/` imports this module.
 
 Two shims are needed; both live here, never in the reference tree:
   * a stub `gym` package (`gym.Env`, `gym.spaces.{Box,Discrete,Tuple}`, `gym.envs.registration`),
@@ -16,11 +17,17 @@ import types
 
 import numpy as np
 
+def _has_env(root):
+    return os.path.isfile(os.path.join(root, "q1physrl_env", "q1physrl_env", "env.py"))
+
+
 REFERENCE_ROOT = os.environ.get("Q1_REFERENCE_ROOT", "/root/reference")
+if not _has_env(REFERENCE_ROOT):
+    REFERENCE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "q1physrl_env", "q1physrl_env", "env.py"))
+    return _has_env(REFERENCE_ROOT)
 
 
 def _install_gym_stub():

@@ -283,6 +283,8 @@ def main():
         record("integer_delay_n16", dict(DEFAULT, key_press_delay=0.25, time_delta=0.0125,
                                          time_limit=4.0), 16, 340, seed=8)
         record("noyaw_n8", dict(DEFAULT, allow_yaw=False, zero_start_prob=0.5), 8, 300, seed=9)
+        # divisors whose rounded reciprocal does not qualify for the short division (IEEE kernels)
+        record("odd_divisors_n16", dict(PARAMS_100M, action_range=7.3, time_limit=7.3), 16, 560, seed=15)
         record_phys_apply("phys_apply_n4096", 4096, seed=10)
         record_phys_apply_dt32("phys_apply_dt32_n4096", 4096, seed=13)
         record_delta_speeds("delta_speeds", seed=14)

@@ -10,7 +10,7 @@ GOLDEN_DIR = os.path.join(HERE, "golden")
 
 ENV_FIXTURES = ["default_n1", "params100m_n16", "zero_autojump_n16", "dummy_trainer",
                 "discrete_speed_n16", "hover_nojump_n16", "strafe_jump_n8", "integer_delay_n16",
-                "noyaw_n8"]
+                "noyaw_n8", "odd_divisors_n16"]
 STATE_FIELDS = ("vel", "z_pos", "yaw", "time_remaining", "on_ground", "jump_released",
                 "zero_start", "last_keys", "last_press")
 

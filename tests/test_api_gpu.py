@@ -333,7 +333,7 @@ def test_numpy1_promotion_flag():
     assert not np.array_equal(e1._yaw, e2._yaw)
     d1 = benv.ActionDecoder(benv.Config(**dict(cfg, num_envs=64)), numpy1_promotion=True)
     d1.vector_reset(np.full(64, 90.0))
-    yaw, _, _, _ = d1.map((keys, mouse) and np.concatenate([keys, m[:, None]], axis=1), np.zeros(64, np.float32),
+    yaw, _, _, _ = d1.map(np.concatenate([keys, m[:, None]], axis=1), np.zeros(64, np.float32),
                           np.full(64, 10.0))
     assert np.array_equal(yaw, e1._yaw)
 

@@ -11,14 +11,14 @@ from oracle import q1_oracle as qo, refshim
 pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference checkout not mounted")
 
 
-def _run(cfgkw, n, ticks, seed):
+def _run(cfgkw, n, ticks, seed, numpy1_promotion=False):
     ref_env, _ = refshim.load()
     cfg = ref_env.Config(**cfgkw)
     np.random.seed(seed)
     with np.errstate(invalid="ignore", divide="ignore"):
         e = ref_env.VectorPhysEnv(cfg)
         e._action_decoder._fix_actions = lambda a: a          # array-fed: same arithmetic, no loop
-        o = qo.OracleEnv(cfg)
+        o = qo.OracleEnv(dict(dataclasses.asdict(cfg), numpy1_promotion=numpy1_promotion))
         o.load_reference(e)
         rng = np.random.default_rng(seed)
         for t in range(ticks):
@@ -63,3 +63,39 @@ def test_discrete_yaw_speed_reward_no_smoothing():
 
 def test_hover_no_jump_zero_delay():
     _run(dict(_default(256), hover=True, allow_jump=False, key_press_delay=0.), 256, 400, 4)
+
+
+# the four configurations the CUDA path is checked against the ORACLE on (tests/test_cuda_parity.py
+# CONFIGS) that round 1 pinned to the reference only through small fixtures, or not at all
+
+def test_integer_delay():
+    """key_press_delay / time_delta = 20 exactly: the f64 time stamps decide, to the last bit."""
+    _run(dict(_default(256), action_range=10, key_press_delay=0.25, time_delta=0.0125, time_limit=4.0),
+         256, 700, 5)
+
+
+def test_no_yaw_action():
+    _run(dict(_default(256), allow_yaw=False, zero_start_prob=0.5, time_delta=0.013888888888888), 256, 760, 6)
+
+
+def test_odd_divisors():
+    """action_range = time_limit = 7.3: divisors whose rounded reciprocal is not good enough for the
+    three-operation division, so the CUDA handle takes its IEEE-division kernels."""
+    _run(dict(_default(256), action_range=7.3, time_limit=7.3, time_delta=0.013888888888888), 256, 760, 7)
+
+
+def test_rules_1_72():
+    _run(dict(_default(256), time_delta=1. / 72, action_range=float(np.float32(10.08))), 256, 760, 8)
+
+
+def test_numpy1_promotion_of_max_yaw_delta(monkeypatch):
+    """env.py:230 under the NumPy 1.18 the reference pins: np.float32(720) * python float is float64.
+    Emulated on the live reference by making _MAX_YAW_SPEED a Python float (the only effect legacy
+    promotion has on this path); the oracle's numpy1_promotion switch must follow it,
+    and the default must NOT (dt = 0.014 is not a float32 value)."""
+    ref_env, _ = refshim.load()
+    monkeypatch.setattr(ref_env, "_MAX_YAW_SPEED", 720.0)
+    cfg = dict(_default(64), time_delta=0.014, time_limit=5)
+    _run(cfg, 64, 400, 9, numpy1_promotion=True)
+    with pytest.raises(AssertionError):
+        _run(cfg, 64, 400, 9, numpy1_promotion=False)
