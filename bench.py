@@ -135,7 +135,7 @@ def cpu_port_throughput(num_envs, threads, min_seconds, min_ticks=1, seed=0):
         t.join()
     elapsed = max(ends) - t0[0]
     env_steps = sum(int(bounds[i + 1] - bounds[i]) * ticks_done[i] for i in range(threads))
-    return env_steps / elapsed, elapsed, min(ticks_done)
+    return env_steps / elapsed, elapsed, round(env_steps / num_envs, 1)    # ticks of the whole batch
 
 
 def numpy_reference_tiers(seconds=2.5):

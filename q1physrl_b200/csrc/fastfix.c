@@ -254,7 +254,87 @@ static PyObject *step(PyObject *self, PyObject *args)
     return result;
 }
 
+/* step_arrays(fn, handle, n, num_keys, has_mouse, keys, mouse, obs, reward, done, zero_start, auto_reset)
+ * -> rc of q1_step_host, or -100 when the action arrays are not in a layout the library takes as it
+ * is (the caller then normalises them in Python and calls `step`).  Accepted: keys C-contiguous, 1-byte
+ * integer / bool items, n * num_keys of them; mouse C-contiguous n items of float32 ('f'), int32 ('i')
+ * or float64 ('d'); the element type selects Q1_MOUSE_*.  The checks a Python caller would make on
+ * dtype / shape / contiguity are made here on the buffer views instead. */
+static PyObject *step_arrays(PyObject *self, PyObject *args)
+{
+    unsigned long long fn, handle;
+    Py_ssize_t n, nk;
+    int has_mouse, auto_reset;
+    PyObject *keys_obj, *mouse_obj, *out_obj[4];
+    if (!PyArg_ParseTuple(args, "KKnnpOOOOOOp", &fn, &handle, &n, &nk, &has_mouse, &keys_obj, &mouse_obj,
+                          &out_obj[0], &out_obj[1], &out_obj[2], &out_obj[3], &auto_reset))
+        return NULL;
+    Py_buffer kb, mb, ob[4];
+    if (PyObject_GetBuffer(keys_obj, &kb, PyBUF_FORMAT | PyBUF_C_CONTIGUOUS) != 0) {
+        PyErr_Clear();
+        return PyLong_FromLong(-100);
+    }
+    long rc = -100;
+    int have_mouse = 0, outs = 0, mouse_kind = 0;
+    const char *kf = kb.format ? kb.format : "B";
+    if (kb.itemsize != 1 || kb.len != n * nk || !(kf[0] == 'B' || kf[0] == 'b' || kf[0] == '?') ||
+        kb.ndim != 2)
+        goto done;
+    if (has_mouse) {
+        if (PyObject_GetBuffer(mouse_obj, &mb, PyBUF_FORMAT | PyBUF_C_CONTIGUOUS) != 0) {
+            PyErr_Clear();
+            goto done;
+        }
+        have_mouse = 1;
+        const char *mf = mb.format ? mb.format : "";
+        while (*mf == '@' || *mf == '=' || *mf == '<')
+            mf++;
+        if (mb.ndim != 1 || mb.shape[0] != n || mf[1] != '\0')
+            goto done;
+        if (mf[0] == 'f' && mb.itemsize == 4)
+            mouse_kind = 0;                                      /* Q1_MOUSE_F32 */
+        else if (mf[0] == 'i' && mb.itemsize == 4)
+            mouse_kind = 1;                                      /* Q1_MOUSE_I32 */
+        else if (mf[0] == 'd' && mb.itemsize == 8)
+            mouse_kind = 2;                                      /* Q1_MOUSE_F64 */
+        else
+            goto done;
+    }
+    for (; outs < 4; outs++)
+        if (PyObject_GetBuffer(out_obj[outs], &ob[outs], PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) != 0)
+            break;
+    if (outs < 4) {
+        for (int k = 0; k < outs; k++)
+            PyBuffer_Release(&ob[k]);
+        if (have_mouse)
+            PyBuffer_Release(&mb);
+        PyBuffer_Release(&kb);
+        return NULL;
+    }
+    if (ob[0].len != n * 24 || ob[1].len != n * 4 || ob[2].len != n || ob[3].len != n) {
+        PyErr_SetString(PyExc_ValueError, "output arrays do not match num_envs");
+        rc = -101;
+        goto done;
+    }
+    Py_BEGIN_ALLOW_THREADS
+    rc = ((step_host_fn)(uintptr_t)fn)((void *)(uintptr_t)handle, kb.buf, have_mouse ? mb.buf : NULL, mouse_kind,
+                                       ob[0].buf, ob[1].buf, ob[2].buf, ob[3].buf, auto_reset);
+    Py_END_ALLOW_THREADS
+done:
+    for (int k = 0; k < outs; k++)
+        PyBuffer_Release(&ob[k]);
+    if (have_mouse)
+        PyBuffer_Release(&mb);
+    PyBuffer_Release(&kb);
+    if (rc == -101)
+        return NULL;
+    return PyLong_FromLong(rc);
+}
+
 static PyMethodDef methods[] = {
+    {"step_arrays", step_arrays, METH_VARARGS,
+     "step_arrays(fn, handle, n, num_keys, has_mouse, keys, mouse, obs, reward, done, zero_start, auto_reset) "
+     "-> rc of q1_step_host, or -100 if the action arrays need normalising first."},
     {"split_actions", split_actions, METH_VARARGS,
      "split_actions(actions, num_keys, has_mouse, keys_out, mouse_out): RLLib's nested action format -> "
      "the uint8 key array and float64 mouse array q1_step_host consumes (reference env.py:221-228)."},

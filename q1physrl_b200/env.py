@@ -182,7 +182,7 @@ try:                                     # built by _build.build_fastfix(); opti
     from . import _fastfix
 except ImportError:                      # pragma: no cover - the NumPy routes below serve
     _fastfix = None
-if _fastfix is not None and not hasattr(_fastfix, "step"):   # a stale build of an older source
+if _fastfix is not None and not hasattr(_fastfix, "step_arrays"):   # a stale build of an older source
     _fastfix = None
 
 
@@ -407,6 +407,7 @@ class VectorPhysEnv(VectorEnv):
         _lib.check(self._lib.q1_create(ctypes.byref(cfg), self._device, self._seed,
                                        int(env_index_base), flags, ctypes.byref(self._handle)))
         self._step_host_addr = ctypes.cast(self._lib.q1_step_host, ctypes.c_void_p).value
+        self._allow_yaw = bool(self._config.allow_yaw)
         self._track_returns = bool(track_returns)
         if reuse_output_buffers is None:
             reuse_output_buffers = self.num_envs >= 65536
@@ -500,6 +501,21 @@ class VectorPhysEnv(VectorEnv):
         `(keys, mouse)` of arrays (keys (N, nk) 0/1, mouse (N,) float32 / float64 / int32).
         A pair of CUDA `torch.Tensor`s is forwarded to `step_tensors` and returns tensors.
         """
+        if _fastfix is not None and type(actions) is tuple and len(actions) == 2 \
+                and type(actions[0]) is np.ndarray:
+            # (keys, mouse) NumPy arrays already in a layout the library takes: dtype / shape /
+            # contiguity are checked on the buffer views in C (csrc/fastfix.c `step_arrays`)
+            obs, reward, done, zs = self._outputs()
+            rc = _fastfix.step_arrays(self._step_host_addr, self._handle.value, self.num_envs, self._num_keys,
+                                      self._allow_yaw, actions[0], actions[1], obs, reward, done, zs,
+                                      auto_reset)
+            if rc != -100:
+                if rc:
+                    _lib.check(rc)
+                self._step_num += 1
+                return obs, reward, done, _InfoList(zs)
+            if self._reuse:
+                self._out_turn ^= 1                    # hand the untouched buffer set back
         if (isinstance(actions, tuple) and len(actions) == 2
                 and getattr(actions[0], "ndim", 0) == 2 and hasattr(actions[1], "shape")):
             if type(actions[0]).__module__.startswith("torch"):

@@ -199,6 +199,57 @@ def test_split_actions_equals_the_reference_expressions():
         benv._fastfix.split_actions(actions, nk, True, np.empty((n - 1, nk), np.uint8), np.empty(n))
 
 
+def test_direct_step_call_marshals_buffers_and_validates_layouts():
+    """csrc/fastfix.c `step` / `step_arrays`: the NumPy-facing step makes the C call on the arrays' own
+    buffers.  Checked here without a GPU against a ctypes callback standing in for q1_step_host."""
+    from q1physrl_b200 import env as benv
+    ff = benv._fastfix
+    assert ff is not None
+    proto = ctypes.CFUNCTYPE(ctypes.c_int, *([ctypes.c_void_p] * 3), ctypes.c_int, *([ctypes.c_void_p] * 4),
+                             ctypes.c_int)
+    seen = []
+
+    def fake_step_host(handle, keys, mouse, kind, obs, reward, done, zs, auto_reset):
+        seen.append((handle, keys, mouse, kind, obs, reward, done, zs, auto_reset))
+        ctypes.memset(done, 1, 5)
+        return -2 if auto_reset == 1 and kind == 1 else 0
+
+    cb = proto(fake_step_host)
+    fn = ctypes.cast(cb, ctypes.c_void_p).value
+    n, nk = 5, 4
+    keys = np.zeros((n, nk), np.uint8)
+    outs = (np.empty((n, 6), np.float32), np.empty(n, np.float32), np.zeros(n, np.bool_), np.empty(n, np.bool_))
+    for dtype, kind in ((np.float32, 0), (np.int32, 1), (np.float64, 2)):
+        mouse = np.zeros(n, dtype)
+        rc = ff.step_arrays(fn, 0x1234, n, nk, True, keys, mouse, *outs, False)
+        assert rc == 0 and seen[-1] == (0x1234, keys.ctypes.data, mouse.ctypes.data, kind,
+                                        *(o.ctypes.data for o in outs), 0)
+        assert outs[2].all()
+    assert ff.step_arrays(fn, 1, n, nk, True, keys, np.zeros(n, np.int32), *outs, True) == -2   # rc passes through
+    assert ff.step_arrays(fn, 1, n, nk, False, keys.view(np.bool_), None, *outs, True) == 0 and seen[-1][2] is None
+    calls = len(seen)
+    for bad_keys, bad_mouse in ((keys[:, ::-1], np.zeros(n, np.float32)),          # not contiguous
+                                (np.zeros((n, nk), np.int64), np.zeros(n, np.float32)),
+                                (np.zeros((n + 1, nk), np.uint8), np.zeros(n, np.float32)),
+                                (np.zeros(n * nk, np.uint8), np.zeros(n, np.float32)),   # 1-D keys
+                                (keys, np.zeros(n, np.float16)), (keys, np.zeros((n, 1), np.float32)),
+                                (keys, np.zeros(n + 1, np.float32)), (keys, np.zeros(2 * n, np.float32)[::2]),
+                                (keys, [0.0] * n)):
+        assert ff.step_arrays(fn, 1, n, nk, True, bad_keys, bad_mouse, *outs, False) == -100
+    assert len(seen) == calls                                   # none of those reached the library
+    with pytest.raises(ValueError):
+        ff.step_arrays(fn, 1, n, nk, True, keys, np.zeros(n, np.float32), outs[0], outs[1], outs[2],
+                       np.empty(n + 1, np.bool_), False)
+    with pytest.raises((TypeError, BufferError, ValueError)):   # read-only output
+        ro = np.empty(n, np.float32)
+        ro.flags.writeable = False
+        ff.step_arrays(fn, 1, n, nk, True, keys, np.zeros(n, np.float32), outs[0], ro, outs[2], outs[3], False)
+    m64 = np.zeros(n)
+    assert ff.step(fn, 7, keys, m64, 2, *outs, True) == 0
+    assert seen[-1] == (7, keys.ctypes.data, m64.ctypes.data, 2, *(o.ctypes.data for o in outs), 1)
+    assert ff.step(fn, 7, keys, None, 0, outs[0], outs[1], outs[2], None, False) == 0 and seen[-1][7] is None
+
+
 def test_gym_make_registration_with_a_stub_gym():
     """env.py:516-521: importing the env module registers 'Q1PhysEnv-v0' with gym.  Neither gym nor
     gymnasium is installed here, so the branch is exercised with the stub the oracle's shim uses, in

@@ -2,7 +2,7 @@
 # usage: tools/ncu_range.sh [envs] [launches] -> gpurun_out/r2_range_<envs>.csv + profiles/r2_step_tma_range.json
 n=${1:-1048576}; l=${2:-16}
 mkdir -p gpurun_out
-ncu --replay-mode application-range --profile-from-start off --clock-control none \
+ncu --replay-mode app-range --profile-from-start off --clock-control none \
     --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum \
     --csv --log-file gpurun_out/r2_range_$n.csv python tools/ncu_range.py $n $l > gpurun_out/r2_range_$n.log 2>&1
 python - "$n" "$l" <<'PY'
@@ -19,7 +19,7 @@ for r in rows[1:]:
 out = {"envs_per_launch": n, "launches": l, "dram_bytes_read": vals["dram__bytes_read.sum"],
        "dram_bytes_write": vals["dram__bytes_write.sum"], "range_ns": vals.get("gpu__time_duration.sum"),
        "algorithmic_bytes_per_launch": 117 * n,
-       "how": f"ncu --replay-mode application-range over {l} consecutive k_step_tma launches of the bench ring "
+       "how": f"ncu --replay-mode app-range over {l} consecutive k_step_tma launches of the bench ring "
               f"(tools/ncu_range.sh); bytes = (dram__bytes_read.sum + dram__bytes_write.sum) / {l}"}
 name = "profiles/r2_step_tma_range.json" if n == 1048576 else f"profiles/r2_step_tma_range_{n}.json"
 json.dump(out, open("gpurun_out/" + name.split("/")[1], "w"), indent=1)
