@@ -316,9 +316,10 @@ int q1_sample_actions(int device, int64_t n, int num_keys, const float *logits, 
 
 /* The shipped policy network fused into one kernel: RLLib fcnet obs(6) -> tanh 256
  * -> tanh 256 -> 2 * num_keys + 2 outputs (checkpoint arrays default_policy/fc_1, fc_2, fc_out), then
- * q1_sample_actions' sampling.  Layer 1 in fp32, layers 2 and 3 on the tensor cores (tcgen05, bf16
- * operands, fp32 accumulation in TMEM).  Weights are HOST arrays in the checkpoint's (in, out)
- * layout: w1 (6, 256), w2 (256, 256), w3 (256, 2 * num_keys + 2). */
+ * q1_sample_actions' sampling.  All three layers on the tensor cores (tcgen05, bf16 operands, fp32
+ * accumulation in TMEM; layer 1 with the observation and its weights split into bf16 pieces, so that
+ * it is as exact as an fp32 product).  Weights are HOST arrays in the checkpoint's (in, out) layout:
+ * w1 (6, 256), w2 (256, 256), w3 (256, 2 * num_keys + 2). */
 typedef struct q1_policy q1_policy; /* opaque */
 int q1_policy_create(int device, int num_keys, const float *w1, const float *b1, const float *w2,
                      const float *b2, const float *w3, const float *b3, q1_policy **out);
@@ -329,6 +330,22 @@ int q1_policy_act(q1_policy *policy, int64_t n, const float *obs, double action_
                   double action_high, int deterministic, uint64_t seed, uint64_t step,
                   const uint64_t *step_device, uint64_t env_index_base, uint8_t *keys, float *mouse,
                   float *logits_out, void *stream);
+
+/* The closed loop policy -> sample -> env tick -> observation -> policy ... for `ticks` ticks in ONE
+ * launch (q1physrl/action_dist.py:84-101, 186-243 + env:482-510; BASELINE config 5): every CTA keeps the
+ * state of its envs in shared memory and the activations in tensor memory, so a tick costs no launch and
+ * no HBM traffic.  The sampling noise is keyed by (seed, global env index, the handle's tick counter).
+ * auto_reset as q1_step; deterministic as q1_sample_actions.  record / record_flags (may be NULL / 0):
+ * the per-tick record of q1_rollout_record, DEVICE pointers; final_obs (n,6) and reward_sum (n,) f32
+ * DEVICE arrays or NULL.  Needs the counter form of the key timers (q1_env_info.f64_stamps == 0). */
+int q1_policy_rollout(q1_policy *policy, q1_env *env, int ticks, int auto_reset, int deterministic,
+                      uint64_t seed, double action_low, double action_high, uint32_t record_flags,
+                      const q1_record_view *record, float *final_obs, float *reward_sum, void *stream);
+/* Same with HOST pointers in `record` and final_obs_host; synchronises.  This is analyse.eval_sim
+ * (q1physrl/analyse.py:197-240) for a policy that lives on the device. */
+int q1_policy_rollout_host(q1_policy *policy, q1_env *env, int ticks, int auto_reset, int deterministic,
+                           uint64_t seed, double action_low, double action_high, uint32_t record_flags,
+                           const q1_record_view *record, float *final_obs_host);
 
 /* Self-check of the branch-free reciprocal-multiply division sequences the kernels use against the
  * CUDA IEEE intrinsics, on ~`samples` random operand pairs per class (bit comparison):

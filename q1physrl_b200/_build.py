@@ -10,10 +10,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libq1phys.so")
-SOURCES = [os.path.join(_HERE, "csrc", "q1phys.cu"), os.path.join(_HERE, "csrc", "q1_policy.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "q1phys.cu"), os.path.join(_HERE, "csrc", "q1_actor.cu")]
 DEPENDS = SOURCES + [os.path.join(_HERE, "csrc", n) for n in (
     "q1_tick.cuh", "q1_sample.cuh", "q1_libm_sincos.cuh", "q1_libm_sincos_tab.inc",
-    "q1_libm_branred_tab.inc")] + [
+    "q1_libm_branred_tab.inc", "q1_internal.h", "q1_device_common.cuh")] + [
     os.path.join(REPO_ROOT, "include", "q1phys.h")]
 
 NVCC_FLAGS = [

@@ -139,6 +139,10 @@ SIGNATURES = {
     "q1_policy_destroy": (c_int, [c_void_p]),
     "q1_policy_act": (c_int, [c_void_p, c_i64, c_void_p, c_double, c_double, c_int, c_u64, c_u64, c_void_p,
                               c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "q1_policy_rollout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_u64, c_double, c_double, c_u32,
+                                  ctypes.POINTER(Q1RecordView), c_void_p, c_void_p, c_void_p]),
+    "q1_policy_rollout_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_u64, c_double, c_double,
+                                       c_u32, ctypes.POINTER(Q1RecordView), c_void_p]),
     "q1_selftest_division": (c_int, [c_int, c_u64, c_u64, ctypes.POINTER(c_u64 * 8)]),
     "q1_snapshot_bytes": (c_int, [c_void_p, ctypes.POINTER(c_u64)]),
     "q1_snapshot_save_host": (c_int, [c_void_p, c_void_p, c_u64]),

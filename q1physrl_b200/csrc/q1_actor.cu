@@ -1,0 +1,956 @@
+/*
+ * q1_actor.cu -- the shipped PPO policy and the env it drives as ONE warp-specialised sm_100a kernel
+ * (BASELINE config 5):
+ *
+ *   k_actor<LOOP = false>   obs -> tanh 256 -> tanh 256 -> logits -> Q1PhysActionDist sample -> the action
+ *                           arrays q1_step consumes (q1_policy_act), tile after tile of 128 envs;
+ *   k_actor<LOOP = true>    the closed loop: every CTA keeps the state of up to 8 tiles of 128 envs in
+ *                           shared memory for T ticks and runs policy -> sample -> tick<>() -> observe ->
+ *                           policy ... with no launch and no HBM traffic per tick (q1_policy_rollout);
+ *                           optionally writes the per-tick record of analyse.eval_sim.
+ * Reference: q1physrl checkpoints (RLLib fcnet default_policy/fc_1, fc_2, fc_out),
+ * q1physrl/action_dist.py:84-101, 186-243, q1physrl_env/env.py:482-510.
+ *
+ * All three layers run on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators
+ * in tensor memory); activations never leave tensor memory.  13 warps, three roles, synchronised by
+ * mbarriers only:
+ *
+ *   warps 0-3    ENV   one thread per env row: builds the layer-1 operand from the observation, reads
+ *                      the logits, samples the action and (LOOP) runs the env tick for its env
+ *   warps 4-11   EPI   tanh epilogues: tcgen05.ld accumulator columns -> (+ bias) -> tanh -> bf16 ->
+ *                      tcgen05.st as the next layer's A operand; thread = (row, column half)
+ *   warp 12      MMA   one lane issues every tcgen05.mma and tcgen05.commit
+ *
+ * The epilogues overlap the MMAs instead of alternating with them: layer 1 is issued in 8 column chunks
+ * of 32 into a double-buffered 2 x 32-column staging area, and as soon as the epilogue has turned chunk
+ * c into activations the MMA warp issues the two K-steps of layer 2 that consume them (and layer 1's
+ * chunk c + 2); layer 3's K-steps trail the layer-2 epilogue the same way, 64 columns at a time.  With
+ * two or more tiles per CTA the env tick of one tile runs under the policy phase of the next.
+ *
+ * Layer 1 on the tensor cores without bf16-quantising the observation (yaw / 90 would lose 3 degrees):
+ * x = x_hi + x_mid + x_lo (three bf16, 24 bits), w = w_hi + w_lo; the five products that matter
+ * (hi.hi, hi.lo, mid.hi, mid.lo, lo.hi) of the 6 inputs are 30 columns of one K = 32 operand, the last
+ * two carry 1 x (b_hi, b_lo): the bias comes out of the MMA too.  Relative error ~2^-17 of |x w|.
+ *
+ * Tensor memory (512 columns): H [0,128) activations (A operand of layers 2 and 3) | D2 [128,384)
+ * layer-2 accumulator | S [384,448) two layer-1 chunk buffers | X [448,480) two layer-1 operands (tile
+ * parity) | D3 [480,512) two logit accumulators (tile parity).
+ */
+#include "q1_internal.h"
+#include "q1_device_common.cuh"
+#include "q1_sample.cuh"
+
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace q1;
+
+namespace {
+
+constexpr int kRows = 128;   /* envs per tile = UMMA M */
+constexpr int kHidden = 256; /* hidden width = K of layers 2 and 3, N of layers 1 and 2 */
+constexpr int kOutPad = 16;  /* layer-3 N, zero-padded from 2 * num_keys + 2 = 8 or 10 */
+constexpr int kObs = 6;
+constexpr int kEnvWarps = 4, kEpiWarps = 8, kMmaWarp = kEnvWarps + kEpiWarps;
+constexpr int kThreads = 32 * (kMmaWarp + 1);
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kMaxTiles = 8; /* tiles of env state a CTA keeps in shared memory (LOOP) */
+
+/* shared-memory image; every UMMA operand block is 1024-byte aligned (128-byte swizzle atoms) */
+constexpr uint32_t SM_B2 = 0;                                  /* W2^T: 4 K-atoms x 256 rows x 128 B */
+constexpr uint32_t SM_B3 = SM_B2 + 4 * kHidden * 128;          /* W3^T: 4 K-atoms x 16 rows x 128 B */
+constexpr uint32_t SM_B1 = SM_B3 + 4 * kOutPad * 128;          /* layer-1 operand: 256 rows x 128 B (K = 32 used) */
+constexpr uint32_t SM_BIAS2 = SM_B1 + kHidden * 128;           /* fp32 [256] */
+constexpr uint32_t SM_BIAS3 = SM_BIAS2 + kHidden * 4;          /* fp32 [16] */
+constexpr uint32_t SM_WEIGHTS_END = SM_BIAS3 + kOutPad * 4;
+constexpr uint32_t kImageBytes = SM_WEIGHTS_END - SM_B2;        /* what the host image holds */
+static_assert(kImageBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+enum : uint32_t { /* mbarriers, 8 bytes each */
+    B_W = 0, B_X = 1 /* [2] */, B_S = 3 /* [2] */, B_H1 = 5 /* [2] */, B_H2 = 7 /* [4] */, B_D2 = 11,
+    B_D3 = 12 /* [2] */, B_E = 14 /* [2] */, B_COUNT = 16
+};
+constexpr uint32_t SM_BAR = SM_WEIGHTS_END;
+constexpr uint32_t SM_TMEM = SM_BAR + 8 * B_COUNT;
+constexpr uint32_t SM_STATE = (SM_TMEM + 16 + 127) & ~127u;    /* LOOP: kMaxTiles x kSlotBytes */
+constexpr uint32_t SLOT_EPOCH = kTileBytes;                     /* u32 [128] */
+constexpr uint32_t SLOT_RETURN = SLOT_EPOCH + 4 * kRows;        /* f64 [128] */
+constexpr uint32_t kSlotBytes = SLOT_RETURN + 8 * kRows;
+constexpr uint32_t SM_TOTAL_ACT = SM_STATE;
+constexpr uint32_t SM_TOTAL_LOOP = SM_STATE + kMaxTiles * kSlotBytes;
+static_assert(SM_TOTAL_LOOP <= 232448, "one CTA per SM: at most 227 KB of shared memory");
+
+/* tensor-memory columns (32-bit) */
+constexpr uint32_t TM_H = 0, TM_D2 = 128, TM_S = 384, TM_X = 448, TM_D3 = 480;
+
+/* instruction descriptor of tcgen05.mma kind::f16: D = f32, A = B = bf16, both K-major, M = 128 */
+__host__ __device__ constexpr uint32_t instr_desc(uint32_t n)
+{
+    return (1u << 4) /* c_format f32 */ | (1u << 7) /* a bf16 */ | (1u << 10) /* b bf16 */ |
+           ((n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+
+/* shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart */
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);       /* start address */
+    d |= (uint64_t)1u << 16;                       /* leading byte offset: unused when swizzled */
+    d |= (uint64_t)(1024u >> 4) << 32;             /* stride byte offset between 8-row atoms */
+    d |= (uint64_t)1u << 46;                       /* descriptor version (Blackwell) */
+    d |= (uint64_t)2u << 61;                       /* SWIZZLE_128B */
+    return d;
+}
+
+__device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* A operand from tensor memory (lane = row, 16-bit elements packed two per column along K) */
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            bool accumulate)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+                 "}\n" ::"r"(tmem_d),
+                 "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(bar), "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+/* tanh of two pre-activations -> packed bf16x2.  Q1_POLICY_TANH_BF16X2 rounds the inputs to bf16
+ * first and spends one MUFU on the pair (faster, ~3x the logit error); the default keeps fp32
+ * inputs (tanh.approx.f32, relative error 2^-11) and rounds only the results. */
+#ifndef Q1_POLICY_TANH_BF16X2
+#define Q1_POLICY_TANH_BF16X2 0
+#endif
+__device__ __forceinline__ uint32_t tanh2_bf16(float lo, float hi)
+{
+#if Q1_POLICY_TANH_BF16X2
+    uint32_t x = pack_bf16(lo, hi), y;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+#else
+    float a, b;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(lo));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(hi));
+    return pack_bf16(a, b);
+#endif
+}
+/* consecutive 32-bit columns of this thread's TMEM lane */
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t v[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                   "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                   "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+                   "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                   "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+/* x = hi + mid + lo in three bf16 (24 significant bits): the bit patterns */
+__device__ __forceinline__ void split3(float x, uint32_t &hi, uint32_t &mid, uint32_t &lo)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);          /* exact */
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);         /* exact */
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    hi = __bfloat16_as_ushort(h);
+    mid = __bfloat16_as_ushort(m);
+    lo = __bfloat16_as_ushort(l);
+}
+
+/* The layer-1 A operand of one env row: K = 32 bf16 in 16 packed columns.  Input k occupies K indices
+ * 5k .. 5k+4 = (hi, hi, mid, mid, lo), matching the weight rows (w_hi, w_lo, w_hi, w_lo, w_hi) the host
+ * lays out; K = 30, 31 are 1.0 against (bias_hi, bias_lo). */
+__device__ __forceinline__ void layer1_operand(const float o[kObs], uint32_t cols[16])
+{
+    uint32_t a[32];
+#pragma unroll
+    for (int k = 0; k < kObs; k++) {
+        uint32_t h, m, l;
+        split3(o[k], h, m, l);
+        a[5 * k] = h;
+        a[5 * k + 1] = h;
+        a[5 * k + 2] = m;
+        a[5 * k + 3] = m;
+        a[5 * k + 4] = l;
+    }
+    a[30] = a[31] = 0x3F80u; /* bf16 1.0 */
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        cols[j] = a[2 * j] | (a[2 * j + 1] << 16);
+}
+
+struct ActorArgs {
+    const unsigned char *image;
+    int64_t n;                 /* envs (ACT: rows of obs; LOOP: the handle's num_envs) */
+    int num_keys;
+    float low, high;
+    int deterministic;
+    uint64_t seed;             /* of the sampling noise */
+    uint64_t step;             /* position of the noise stream (ACT: this call; LOOP: first tick) */
+    const uint64_t *step_device;
+    uint64_t env_index_base;
+    /* ACT */
+    const float *obs;
+    uint8_t *keys;
+    float *mouse;
+    float *logits_out;
+    /* LOOP */
+    int ticks;
+    int auto_reset;
+    int64_t tile_begin, tile_end; /* tiles [begin, end) of the handle go to this launch */
+    uint32_t record_flags;
+    q1_record_view rec;
+    int64_t rec_tick0;         /* record row of this launch's first tick */
+    float *final_obs;
+    float *reward_sum;
+};
+
+/* one env out of / into a shared-memory state block */
+__device__ __forceinline__ void slot_load(const unsigned char *blk, int l, Env &e)
+{
+    const float4 a = reinterpret_cast<const float4 *>(blk + kTileRecA)[l];
+    const double2 b = reinterpret_cast<const double2 *>(blk + kTileRecB)[l];
+    e.vx = a.x;
+    e.vy = a.y;
+    e.vz = a.z;
+    e.bits = __float_as_uint(a.w);
+    e.z = b.x;
+    e.yaw = b.y;
+    e.trem = reinterpret_cast<const double *>(blk + kTileTrem)[l];
+}
+__device__ __forceinline__ void slot_store(unsigned char *blk, int l, const Env &e)
+{
+    reinterpret_cast<float4 *>(blk + kTileRecA)[l] = make_float4(e.vx, e.vy, e.vz, __uint_as_float(e.bits));
+    reinterpret_cast<double2 *>(blk + kTileRecB)[l] = make_double2(e.z, e.yaw);
+    reinterpret_cast<double *>(blk + kTileTrem)[l] = e.trem;
+}
+
+template <bool LOOP, bool TRACK, bool LEAN, bool RECORD>
+__global__ void __launch_bounds__(kThreads, 1)
+k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t s0 = saddr_of(smem);
+    auto bar = [&](uint32_t b) { return s0 + SM_BAR + 8u * b; };
+
+    /* this CTA's work: LOOP: tiles tile_begin + blockIdx.x + j * gridDim.x (j < k), each for `ticks`
+     * ticks, visited round-robin; ACT: the same tile walk, each tile once */
+    const int64_t all_tiles = LOOP ? A.tile_end - A.tile_begin : (A.n + kRows - 1) / kRows;
+    const int64_t first_tile = (LOOP ? A.tile_begin : 0) + blockIdx.x;
+    const int64_t mine = ((LOOP ? A.tile_begin : 0) + all_tiles - first_tile + gridDim.x - 1) / gridDim.x;
+    const int k = LOOP ? (int)mine : 1;                         /* tile slots of this CTA */
+    const int64_t S = LOOP ? (int64_t)k * A.ticks : mine;      /* policy evaluations ("sequences") */
+    auto tile_of = [&](int64_t s) { return first_tile + (LOOP ? (s % k) : s) * (int64_t)gridDim.x; };
+
+    if (tid == 0) {
+        bar_init(bar(B_W), 1);
+        for (int b = 0; b < 2; b++) {
+            bar_init(bar(B_X + b), kRows);
+            bar_init(bar(B_S + b), 1);
+            bar_init(bar(B_H1 + b), kEpiThreads);
+            bar_init(bar(B_D3 + b), 1);
+            bar_init(bar(B_E + b), kRows);
+        }
+        for (int b = 0; b < 4; b++)
+            bar_init(bar(B_H2 + b), kEpiThreads);
+        bar_init(bar(B_D2), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        /* the weight image -> shared memory, in 32 KB bulk copies */
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar(B_W)), "r"(kImageBytes)
+                     : "memory");
+        for (uint32_t off = 0; off < kImageBytes; off += 32768u) {
+            const uint32_t len = kImageBytes - off < 32768u ? kImageBytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(s0 + SM_B2 + off), "l"(A.image + off), "r"(len), "r"(bar(B_W))
+                         : "memory");
+        }
+    }
+    if (warp == 0) { /* one warp owns the TMEM allocation: all 512 columns */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s0 + SM_TMEM), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (LOOP) { /* the CTA's env state: HBM -> shared memory, once */
+        for (int j = 0; j < k; j++) {
+            const int64_t tile = tile_of(j);
+            unsigned char *slot = smem + SM_STATE + j * kSlotBytes;
+            const int4 *src = reinterpret_cast<const int4 *>(P.state + tile * kTileBytes);
+            for (uint32_t x = tid; x < kTileBytes / 16; x += kThreads)
+                reinterpret_cast<int4 *>(slot)[x] = src[x];
+            for (uint32_t x = tid; x < kRows; x += kThreads) {
+                const int64_t i = tile * kRows + x;
+                reinterpret_cast<uint32_t *>(slot + SLOT_EPOCH)[x] = i < P.n ? P.epoch[i] : 0u;
+                if (TRACK)
+                    reinterpret_cast<double *>(slot + SLOT_RETURN)[x] = i < P.n ? P.ep_return[i] : 0.0;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + SM_TMEM);
+    uint64_t step = A.step;
+    if (A.step_device)
+        step = *A.step_device;
+
+    if (warp == kMmaWarp) {
+        /* ================================================================ MMA issuer ============ */
+        if (lane == 0) {
+            bar_wait(bar(B_W), 0);
+            uint32_t nX[2] = {0, 0}, nH1[2] = {0, 0}, nE[2] = {0, 0}, nH2 = 0;
+            for (int64_t s = 0; s < S; s++) {
+                const uint32_t par = (uint32_t)s & 1u;
+                bar_wait(bar(B_X + par), nX[par]++ & 1u);
+                tc_fence_after();
+                /* layer-1 chunk c: S[c & 1] (128 x 32) = X (128 x 32) . W1op rows 32c .. 32c+31 */
+                auto layer1_chunk = [&](uint32_t c) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 2; ks++)
+                        mma_bf16_ts(tmem + TM_S + 32u * (c & 1u), tmem + TM_X + 16u * par + 8u * ks,
+                                    smem_desc(s0 + SM_B1 + c * 4096u + ks * 32u), instr_desc(32), ks > 0);
+                    mma_commit(bar(B_S + (c & 1u)));
+                };
+                layer1_chunk(0);
+                layer1_chunk(1);
+#pragma unroll 1
+                for (uint32_t c = 0; c < 8; c++) {
+                    /* the epilogue has turned chunk c into activations (and is done with S[c & 1]) */
+                    bar_wait(bar(B_H1 + (c & 1u)), nH1[c & 1u]++ & 1u);
+                    tc_fence_after();
+                    if (c + 2 < 8)
+                        layer1_chunk(c + 2);
+                    /* layer 2, K-steps 2c and 2c+1: D2 (128 x 256) += H1[:, 32c .. 32c+31] . W2 */
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 2; kk++) {
+                        const uint32_t ks = 2u * c + kk;
+                        mma_bf16_ts(tmem + TM_D2, tmem + TM_H + ks * 8u,
+                                    smem_desc(s0 + SM_B2 + (ks >> 2) * (kHidden * 128u) + (ks & 3u) * 32u),
+                                    instr_desc(kHidden), ks > 0);
+                    }
+                }
+                mma_commit(bar(B_D2));
+                if (s >= 2) { /* the env warps have read the logits this accumulator held two tiles ago */
+                    bar_wait(bar(B_E + par), nE[par]++ & 1u);
+                    tc_fence_after();
+                }
+#pragma unroll 1
+                for (uint32_t j = 0; j < 4; j++) {
+                    bar_wait(bar(B_H2 + j), nH2 & 1u);
+                    tc_fence_after();
+                    /* layer 3, K-steps 4j .. 4j+3: D3 (128 x 16) += H2[:, 64j .. 64j+63] . W3 (padded) */
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; kk++) {
+                        const uint32_t ks = 4u * j + kk;
+                        mma_bf16_ts(tmem + TM_D3 + 16u * par, tmem + TM_H + ks * 8u,
+                                    smem_desc(s0 + SM_B3 + (ks >> 2) * (kOutPad * 128u) + (ks & 3u) * 32u),
+                                    instr_desc(kOutPad), ks > 0);
+                    }
+                }
+                nH2++;
+                mma_commit(bar(B_D3 + par));
+            }
+        }
+    } else if (warp >= kEnvWarps) {
+        /* ================================================================ tanh epilogues ======== */
+        const uint32_t quad = warp & 3u, half = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column half */
+        const uint32_t lane_base = tmem + ((quad * 32u) << 16);
+        bar_wait(bar(B_W), 0);
+        const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2);
+        uint32_t nS[2] = {0, 0}, nD2 = 0;
+        for (int64_t s = 0; s < S; s++) {
+            /* ---- layer-1 epilogue: S chunk (bias already in the MMA) -> tanh -> H1 ---- */
+#pragma unroll 1
+            for (uint32_t c = 0; c < 8; c++) {
+                bar_wait(bar(B_S + (c & 1u)), nS[c & 1u]++ & 1u);
+                tc_fence_after();
+                uint32_t v[16], p[8];
+                tmem_ld16(lane_base + TM_S + 32u * (c & 1u) + 16u * half, v);
+#pragma unroll
+                for (uint32_t e = 0; e < 8; e++)
+                    p[e] = tanh2_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                if (c == 0 && s >= 1) { /* H still holds the previous tile's layer-2 activations until its
+                                           layer-3 MMAs have completed */
+                    bar_wait(bar(B_D3 + ((uint32_t)(s - 1) & 1u)), (uint32_t)((s - 1) >> 1) & 1u);
+                    tc_fence_after();
+                }
+                tmem_st8(lane_base + TM_H + 16u * c + 8u * half, p);
+                tmem_st_wait();
+                tc_fence_before();
+                bar_arrive(bar(B_H1 + (c & 1u)));
+            }
+            /* ---- layer-2 epilogue: D2 + bias -> tanh -> H2 (over H1, which layer 2 has consumed) ---- */
+            bar_wait(bar(B_D2), nD2++ & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t j = 0; j < 4; j++) {
+                uint32_t v[32], p[16];
+                const uint32_t col0 = 64u * j + 32u * half;
+                tmem_ld32(lane_base + TM_D2 + col0, v);
+#pragma unroll
+                for (uint32_t e = 0; e < 16; e++)
+                    p[e] = tanh2_bf16(__uint_as_float(v[2 * e]) + bias2[col0 + 2u * e],
+                                      __uint_as_float(v[2 * e + 1]) + bias2[col0 + 2u * e + 1u]);
+                tmem_st16(lane_base + TM_H + 32u * j + 16u * half, p);
+                tmem_st_wait();
+                tc_fence_before();
+                bar_arrive(bar(B_H2 + j));
+            }
+        }
+    } else {
+        /* ================================================================ env rows =============== */
+        const uint32_t row = tid; /* warp w owns TMEM lanes 32w .. 32w+31 = rows 32w .. 32w+31 */
+        const uint32_t lane_base = tmem + ((warp * 32u) << 16);
+        const float *bias3 = reinterpret_cast<const float *>(smem + SM_BIAS3);
+        const int width = 2 * A.num_keys + 2;
+        const int64_t stride = (LOOP && k < 2) ? 1 : 2; /* how far ahead the layer-1 operand is prepared */
+
+        /* the layer-1 operand of sequence s2 -> X[s2 & 1] */
+        auto prepare = [&](int64_t s2) {
+            const int64_t i = tile_of(s2) * kRows + row;
+            float o[kObs] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (LOOP) {
+                Env e;
+                slot_load(smem + SM_STATE + (s2 % k) * kSlotBytes, row, e);
+                observe<LEAN>(P, e, o);
+            } else if (i < A.n) {
+                if ((reinterpret_cast<uintptr_t>(A.obs) & 7u) == 0) {
+                    const float2 *p2 = reinterpret_cast<const float2 *>(A.obs + i * kObs);
+                    const float2 a = __ldg(p2), b = __ldg(p2 + 1), c = __ldg(p2 + 2);
+                    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kObs; q++)
+                        o[q] = __ldg(A.obs + i * kObs + q);
+                }
+            }
+            uint32_t cols[16];
+            layer1_operand(o, cols);
+            tmem_st16(lane_base + TM_X + 16u * ((uint32_t)s2 & 1u), cols);
+            tmem_st_wait();
+            tc_fence_before();
+            bar_arrive(bar(B_X + ((uint32_t)s2 & 1u)));
+        };
+        bar_wait(bar(B_W), 0);
+        for (int64_t s2 = 0; s2 < stride && s2 < S; s2++)
+            prepare(s2);
+
+        float rsum[kMaxTiles];
+#pragma unroll
+        for (int j = 0; j < kMaxTiles; j++)
+            rsum[j] = 0.0f;
+        for (int64_t s = 0; s < S; s++) {
+            const uint32_t par = (uint32_t)s & 1u;
+            bar_wait(bar(B_D3 + par), (uint32_t)(s >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[16];
+            tmem_ld16(lane_base + TM_D3 + 16u * par, v);
+            tc_fence_before();
+            bar_arrive(bar(B_E + par));
+            float lg[10];
+#pragma unroll
+            for (int q = 0; q < 10; q++)
+                lg[q] = __uint_as_float(v[q]) + bias3[q];
+            const int64_t tile = tile_of(s);
+            const int64_t i = tile * kRows + row;
+            const bool active = i < (LOOP ? P.n : A.n);
+            if (!LOOP) {
+                if (active) {
+                    float m;
+                    const uint32_t kb = sample_action_row(lg, A.num_keys, A.low, A.high, A.deterministic != 0,
+                                                          A.seed, step, A.env_index_base + (uint64_t)i, &m);
+                    for (int q = 0; q < A.num_keys; q++)
+                        A.keys[i * A.num_keys + q] = (kb >> q) & 1u;
+                    A.mouse[i] = m;
+                    if (A.logits_out)
+                        for (int q = 0; q < width; q++)
+                            A.logits_out[i * width + q] = lg[q];
+                }
+            } else {
+                /* ---- one env tick: env.VectorPhysEnv.vector_step (env:482-510) on the sampled action ---- */
+                const int slot_no = (int)(s % k);
+                const int64_t tick_no = s / k;
+                unsigned char *slot = smem + SM_STATE + slot_no * kSlotBytes;
+                const uint64_t gidx = P.env_index_base + (uint64_t)i;
+                float m;
+                const uint32_t keybits = sample_action_row(lg, A.num_keys, A.low, A.high, A.deterministic != 0,
+                                                           A.seed, step + (uint64_t)tick_no, gidx, &m);
+                Env e;
+                slot_load(slot, row, e);
+                float r;
+                bool d;
+                if (RECORD) {
+                    const int64_t rrow = (A.rec_tick0 + tick_no) * P.n + i;
+                    float o[6];
+                    observe<LEAN>(P, e, o);
+                    if (active)
+                        record_before(A.rec, rrow, A.num_keys, e, o, keybits, (double)m);
+                    Move mv;
+                    tick<false, LEAN, false>(P, e, keybits, (double)m, r, d, &mv);
+                    if (active)
+                        record_after(A.rec, rrow, A.record_flags, P.jump_mode, mv, o, r, d);
+                } else {
+                    tick<false, LEAN, false>(P, e, keybits, (double)m, r, d);
+                }
+#pragma unroll
+                for (int j = 0; j < kMaxTiles; j++)
+                    if (j == slot_no)
+                        rsum[j] = add32(rsum[j], r);
+                if (TRACK) {
+                    double *retp = reinterpret_cast<double *>(slot + SLOT_RETURN) + row;
+                    double ret = add64(*retp, (double)r);
+                    bool finished = active && d;
+                    if (!A.auto_reset) { /* report an episode once, as the step kernels do */
+                        finished = finished && !(e.bits & F_DONE_SEEN);
+                        if (finished)
+                            e.bits |= F_DONE_SEEN;
+                    }
+                    report_episodes(P, finished, e.bits & F_ZERO_START, ret);
+                    *retp = (d && A.auto_reset) ? 0.0 : ret;
+                }
+                if (d && A.auto_reset) {
+                    uint32_t *epp = reinterpret_cast<uint32_t *>(slot + SLOT_EPOCH) + row;
+                    const uint32_t ep = *epp + 1u;
+                    *epp = ep;
+                    reset_env<false>(P, e, gidx, ep);
+                }
+                slot_store(slot, row, e);
+            }
+            if (s + stride < S)
+                prepare(s + stride); /* reads only this thread's own row of the slot */
+        }
+        if (LOOP) { /* results of the launch: final observation and per-env reward sum */
+            for (int j = 0; j < k; j++) {
+                const int64_t i = tile_of(j) * kRows + row;
+                if (i >= P.n)
+                    continue;
+                if (A.final_obs) {
+                    Env e;
+                    slot_load(smem + SM_STATE + j * kSlotBytes, row, e);
+                    float o[6];
+                    observe<LEAN>(P, e, o);
+                    store_obs(A.final_obs, i, o);
+                }
+                if (A.reward_sum) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < kMaxTiles; q++)
+                        if (q == j)
+                            acc = rsum[q];
+                    A.reward_sum[i] = acc;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (LOOP) { /* the CTA's env state: shared memory -> HBM */
+        for (int j = 0; j < k; j++) {
+            const int64_t tile = tile_of(j);
+            const unsigned char *slot = smem + SM_STATE + j * kSlotBytes;
+            int4 *dst = reinterpret_cast<int4 *>(P.state + tile * kTileBytes);
+            for (uint32_t x = tid; x < kTileBytes / 16; x += kThreads)
+                dst[x] = reinterpret_cast<const int4 *>(slot)[x];
+            for (uint32_t x = tid; x < kRows; x += kThreads) {
+                const int64_t i = tile * kRows + x;
+                if (i < P.n) {
+                    P.epoch[i] = reinterpret_cast<const uint32_t *>(slot + SLOT_EPOCH)[x];
+                    if (TRACK)
+                        P.ep_return[i] = reinterpret_cast<const double *>(slot + SLOT_RETURN)[x];
+                }
+            }
+        }
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+uint16_t to_bf16(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u)
+        return (uint16_t)((u >> 16) | 0x40u);
+    u += 0x7FFFu + ((u >> 16) & 1u); /* round to nearest even */
+    return (uint16_t)(u >> 16);
+}
+float from_bf16(uint16_t h)
+{
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+struct DeviceScope { /* switch to a device for the duration of a call */
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess)
+            prev = -1;
+        if (prev == dev)
+            prev = -1;
+        else
+            ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceScope()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+template <typename K> cudaError_t allow_smem(K kernel, uint32_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+} // namespace
+
+extern "C" {
+
+int q1_policy_create(int device, int num_keys, const float *w1, const float *b1, const float *w2,
+                     const float *b2, const float *w3, const float *b3, q1_policy **out)
+{
+    if (!out || !w1 || !b1 || !w2 || !b2 || !w3 || !b3)
+        return q1_set_error(Q1_EINVAL, "a weight array / out is NULL");
+    *out = nullptr;
+    if (num_keys != 3 && num_keys != 4)
+        return q1_set_error(Q1_EINVAL, "num_keys must be 3 or 4");
+    const int width = 2 * num_keys + 2;
+    std::vector<unsigned char> img(kImageBytes, 0);
+    auto put = [&](uint32_t region, uint32_t rows, int nrow, int k, uint16_t h) {
+        /* element (row nrow, K index k) of an operand stored K-major with 128-byte swizzle */
+        const uint32_t c = (uint32_t)k >> 3, e = (uint32_t)k & 7u;
+        const uint32_t off = region - SM_B2 + (c >> 3) * (rows * 128u) + (uint32_t)nrow * 128u +
+                             (((c & 7u) ^ ((uint32_t)nrow & 7u)) << 4) + e * 2u;
+        memcpy(&img[off], &h, 2);
+    };
+    for (int k = 0; k < kHidden; k++)
+        for (int nrow = 0; nrow < kHidden; nrow++)
+            put(SM_B2, kHidden, nrow, k, to_bf16(w2[k * kHidden + nrow])); /* fc_2 kernel is (in, out) */
+    for (int k = 0; k < kHidden; k++)
+        for (int nrow = 0; nrow < width; nrow++)
+            put(SM_B3, kOutPad, nrow, k, to_bf16(w3[k * width + nrow]));
+    /* layer 1 as a K = 32 operand (see layer1_operand): per input (w_hi, w_lo, w_hi, w_lo, w_hi), then the
+     * bias split the same way against two columns of ones */
+    for (int u = 0; u < kHidden; u++) {
+        for (int k = 0; k < kObs; k++) {
+            const float w = w1[k * kHidden + u];            /* fc_1 kernel is (in, out) */
+            const uint16_t hi = to_bf16(w), lo = to_bf16(w - from_bf16(hi));
+            const uint16_t pat[5] = {hi, lo, hi, lo, hi};
+            for (int q = 0; q < 5; q++)
+                put(SM_B1, kHidden, u, 5 * k + q, pat[q]);
+        }
+        const uint16_t bh = to_bf16(b1[u]), bl = to_bf16(b1[u] - from_bf16(bh));
+        put(SM_B1, kHidden, u, 30, bh);
+        put(SM_B1, kHidden, u, 31, bl);
+    }
+    memcpy(&img[SM_BIAS2 - SM_B2], b2, kHidden * 4);
+    memcpy(&img[SM_BIAS3 - SM_B2], b3, width * 4);
+
+    DeviceScope scope(device);
+    if (!scope.ok)
+        return q1_set_error(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    q1_policy *p = new (std::nothrow) q1_policy();
+    if (!p)
+        return q1_set_error(Q1_ENOMEM, "out of host memory");
+    p->device = device;
+    p->num_keys = num_keys;
+    cudaError_t err = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (err == cudaSuccess)
+        err = cudaMalloc(&p->image, kImageBytes);
+    if (err == cudaSuccess)
+        err = cudaMemcpy(p->image, img.data(), kImageBytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess)
+        err = allow_smem(k_actor<false, false, true, false>, SM_TOTAL_ACT);
+#define Q1_ALLOW(TR, LN, RC)                                                    \
+    if (err == cudaSuccess)                                                     \
+        err = allow_smem(k_actor<true, TR, LN, RC>, SM_TOTAL_LOOP);
+    Q1_ALLOW(false, false, false) Q1_ALLOW(false, false, true) Q1_ALLOW(false, true, false)
+    Q1_ALLOW(false, true, true) Q1_ALLOW(true, false, false) Q1_ALLOW(true, false, true)
+    Q1_ALLOW(true, true, false) Q1_ALLOW(true, true, true)
+#undef Q1_ALLOW
+    if (err != cudaSuccess) {
+        if (p->image)
+            cudaFree(p->image);
+        delete p;
+        return q1_set_error(Q1_ECUDA, std::string("q1_policy_create: ") + cudaGetErrorString(err));
+    }
+    *out = p;
+    return Q1_OK;
+}
+
+int q1_policy_destroy(q1_policy *p)
+{
+    if (!p)
+        return Q1_OK;
+    DeviceScope scope(p->device);
+    cudaError_t err = cudaFree(p->image);
+    delete p;
+    if (err != cudaSuccess)
+        return q1_set_error(Q1_ECUDA, std::string("q1_policy_destroy: ") + cudaGetErrorString(err));
+    return Q1_OK;
+}
+
+int q1_policy_act(q1_policy *p, int64_t n, const float *obs, double action_low, double action_high,
+                  int deterministic, uint64_t seed, uint64_t step, const uint64_t *step_device,
+                  uint64_t env_index_base, uint8_t *keys, float *mouse, float *logits_out, void *stream)
+{
+    if (!p || !obs || !keys || !mouse)
+        return q1_set_error(Q1_EINVAL, "policy / obs / keys / mouse is NULL");
+    if (n < 0)
+        return q1_set_error(Q1_EINVAL, "n must be >= 0");
+    if (n == 0)
+        return Q1_OK;
+    DeviceScope scope(p->device);
+    if (!scope.ok)
+        return q1_set_error(Q1_ECUDA, "cudaSetDevice failed");
+    ActorArgs a = {};
+    a.image = p->image;
+    a.n = n;
+    a.num_keys = p->num_keys;
+    a.low = (float)action_low;
+    a.high = (float)action_high;
+    a.deterministic = deterministic;
+    a.seed = seed;
+    a.step = step;
+    a.step_device = step_device;
+    a.env_index_base = env_index_base;
+    a.obs = obs;
+    a.keys = keys;
+    a.mouse = mouse;
+    a.logits_out = logits_out;
+    const int64_t tiles = (n + kRows - 1) / kRows;
+    const unsigned grid = (unsigned)(tiles < p->sm_count ? tiles : p->sm_count);
+    Params unused = {};
+    k_actor<false, false, true, false><<<grid, kThreads, SM_TOTAL_ACT, static_cast<cudaStream_t>(stream)>>>(unused, a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return q1_set_error(Q1_ECUDA, std::string("k_actor launch: ") + cudaGetErrorString(err));
+    return Q1_OK;
+}
+
+/* see include/q1phys.h */
+static int rollout_launch(q1_policy *p, const q1_env_view &ev, int ticks, int auto_reset, int deterministic,
+                          uint64_t seed, double action_low, double action_high, uint32_t record_flags,
+                          const q1_record_view *rec, float *final_obs, float *reward_sum, cudaStream_t s)
+{
+    ActorArgs a = {};
+    a.image = p->image;
+    a.n = ev.P.n;
+    a.num_keys = p->num_keys;
+    a.low = (float)action_low;
+    a.high = (float)action_high;
+    a.deterministic = deterministic;
+    a.seed = seed;
+    a.step = ev.ticks;
+    a.env_index_base = ev.P.env_index_base;
+    a.ticks = ticks;
+    a.auto_reset = auto_reset;
+    a.record_flags = record_flags;
+    if (rec)
+        a.rec = *rec;
+    a.final_obs = final_obs;
+    a.reward_sum = reward_sum;
+    const int64_t tiles = (ev.P.n + kRows - 1) / kRows;
+    const int64_t per_launch = (int64_t)p->sm_count * kMaxTiles;
+    for (int64_t t0 = 0; t0 < tiles; t0 += per_launch) {
+        a.tile_begin = t0;
+        a.tile_end = t0 + per_launch < tiles ? t0 + per_launch : tiles;
+        const int64_t count = a.tile_end - a.tile_begin;
+        /* as many CTAs as SMs, unless there are fewer tiles; tiles spread evenly over them */
+        const unsigned grid = (unsigned)(count < p->sm_count ? count : p->sm_count);
+#define Q1_LAUNCH(TR, LN, RC) \
+    k_actor<true, TR, LN, RC><<<grid, kThreads, SM_TOTAL_LOOP, s>>>(ev.P, a)
+        const bool lean = !ev.P.ieee_div;
+        if (ev.track) {
+            if (lean) { if (rec) Q1_LAUNCH(true, true, true); else Q1_LAUNCH(true, true, false); }
+            else { if (rec) Q1_LAUNCH(true, false, true); else Q1_LAUNCH(true, false, false); }
+        } else {
+            if (lean) { if (rec) Q1_LAUNCH(false, true, true); else Q1_LAUNCH(false, true, false); }
+            else { if (rec) Q1_LAUNCH(false, false, true); else Q1_LAUNCH(false, false, false); }
+        }
+#undef Q1_LAUNCH
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess)
+            return q1_set_error(Q1_ECUDA, std::string("k_actor launch: ") + cudaGetErrorString(err));
+    }
+    return Q1_OK;
+}
+
+static int rollout_check(q1_policy *p, q1_env *env, int ticks, const q1_env_view &ev)
+{
+    (void)env;
+    if (ticks < 0)
+        return q1_set_error(Q1_EINVAL, "ticks must be >= 0");
+    if (ev.stamps)
+        return q1_set_error(Q1_EINVAL, "q1_policy_rollout needs the counter form of the key timers (not "
+                                       "Q1_F_FORCE_F64_STAMPS / a config that forces f64 stamps): step such "
+                                       "envs with q1_policy_act + q1_step");
+    if (ev.P.num_keys != p->num_keys)
+        return q1_set_error(Q1_EINVAL, "the policy's action head does not match the env's key count");
+    if (ev.device != p->device)
+        return q1_set_error(Q1_EINVAL, "policy and env live on different devices");
+    return Q1_OK;
+}
+
+int q1_policy_rollout(q1_policy *p, q1_env *env, int ticks, int auto_reset, int deterministic, uint64_t seed,
+                      double action_low, double action_high, uint32_t record_flags,
+                      const q1_record_view *record, float *final_obs, float *reward_sum, void *stream)
+{
+    if (!p || !env)
+        return q1_set_error(Q1_EINVAL, "policy / env is NULL");
+    q1_env_view ev;
+    int rc = q1_env_get_view(env, true, &ev);
+    if (rc == Q1_OK)
+        rc = rollout_check(p, env, ticks, ev);
+    if (rc != Q1_OK)
+        return rc;
+    if (ticks == 0)
+        return Q1_OK;
+    DeviceScope scope(p->device);
+    rc = rollout_launch(p, ev, ticks, auto_reset, deterministic, seed, action_low, action_high, record_flags,
+                        record, final_obs, reward_sum, static_cast<cudaStream_t>(stream));
+    if (rc == Q1_OK)
+        rc = q1_advance_ticks(env, ticks);
+    return rc;
+}
+
+int q1_policy_rollout_host(q1_policy *p, q1_env *env, int ticks, int auto_reset, int deterministic,
+                           uint64_t seed, double action_low, double action_high, uint32_t record_flags,
+                           const q1_record_view *record, float *final_obs_host)
+{
+    if (!p || !env || !record)
+        return q1_set_error(Q1_EINVAL, "policy / env / record is NULL");
+    q1_env_view ev;
+    int rc = q1_env_get_view(env, false, &ev);
+    if (rc == Q1_OK)
+        rc = rollout_check(p, env, ticks, ev);
+    if (rc != Q1_OK)
+        return rc;
+    if (ticks == 0)
+        return Q1_OK;
+    const size_t n = (size_t)ev.P.n, nk = (size_t)ev.P.num_keys, rows = n * (size_t)ticks;
+    const void *hosts[15] = {record->vel, record->z_pos, record->on_ground, record->jump_released,
+                             record->time_remaining, record->obs, record->keys, record->mouse,
+                             record->yaw, record->smove, record->fmove, record->jump, record->reward,
+                             record->done, final_obs_host};
+    const size_t width[15] = {12, 8, 1, 1, 8, 24, nk, 4, 8, 8, 8, 1, 4, 1, 0};
+    size_t bytes[15], offs[15], off = 0;
+    for (int q = 0; q < 15; q++) {
+        bytes[q] = hosts[q] ? (q == 14 ? 24 * n : rows * width[q]) : 0;
+        offs[q] = off;
+        off = (off + bytes[q] + 255) & ~(size_t)255;
+    }
+    void *scratch = nullptr, *stream = nullptr;
+    rc = q1_env_host_scratch(env, off + 256, &scratch, &stream);
+    if (rc != Q1_OK)
+        return rc;
+    DeviceScope scope(p->device);
+    char *d = static_cast<char *>(scratch);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    void *dev[15];
+    for (int q = 0; q < 15; q++)
+        dev[q] = bytes[q] ? d + offs[q] : nullptr;
+    q1_record_view dv;
+    dv.vel = static_cast<float *>(dev[0]);
+    dv.z_pos = static_cast<double *>(dev[1]);
+    dv.on_ground = static_cast<uint8_t *>(dev[2]);
+    dv.jump_released = static_cast<uint8_t *>(dev[3]);
+    dv.time_remaining = static_cast<double *>(dev[4]);
+    dv.obs = static_cast<float *>(dev[5]);
+    dv.keys = static_cast<uint8_t *>(dev[6]);
+    dv.mouse = static_cast<float *>(dev[7]);
+    dv.yaw = static_cast<double *>(dev[8]);
+    dv.smove = static_cast<int64_t *>(dev[9]);
+    dv.fmove = static_cast<int64_t *>(dev[10]);
+    dv.jump = static_cast<uint8_t *>(dev[11]);
+    dv.reward = static_cast<float *>(dev[12]);
+    dv.done = static_cast<uint8_t *>(dev[13]);
+    rc = rollout_launch(p, ev, ticks, auto_reset, deterministic, seed, action_low, action_high, record_flags,
+                        &dv, static_cast<float *>(dev[14]), nullptr, s);
+    if (rc != Q1_OK)
+        return rc;
+    for (int q = 0; q < 15; q++)
+        if (bytes[q]) {
+            cudaError_t err = cudaMemcpyAsync(const_cast<void *>(hosts[q]), dev[q], bytes[q], cudaMemcpyDeviceToHost, s);
+            if (err != cudaSuccess)
+                return q1_set_error(Q1_ECUDA, std::string("q1_policy_rollout_host: ") + cudaGetErrorString(err));
+        }
+    cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess)
+        return q1_set_error(Q1_ECUDA, std::string("q1_policy_rollout_host: ") + cudaGetErrorString(err));
+    return q1_advance_ticks(env, ticks);
+}
+
+} /* extern "C" */

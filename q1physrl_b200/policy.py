@@ -3,9 +3,10 @@
 fc_out) and sampling from `Q1PhysActionDist` (q1physrl/action_dist.py), so that rollouts of
 `VectorPhysEnv` run closed-loop on the device with no host traffic.
 
-The three GEMMs are plain library GEMMs (torch / cuBLAS); the distribution sampling is the
-`k_sample_actions` kernel of libq1phys (`q1_sample_actions`), which writes the action arrays in the
-layout `VectorPhysEnv.step_tensors` consumes.
+`MLPPolicy`: three plain library GEMMs (torch / cuBLAS, the fp32 parity reference) + the
+`k_sample_actions` kernel.  `FusedMLPPolicy`: the hand-written tcgen05 kernel `k_actor`
+(csrc/q1_actor.cu), either per call (`act`) or as the whole closed loop in one launch
+(`rollout_fused`, `record_episode`).
 """
 import ctypes
 import json
@@ -82,9 +83,10 @@ class MLPPolicy:
 
 
 class FusedMLPPolicy(MLPPolicy):
-    """The same policy as ONE sm_100a kernel (`k_policy_act`, q1_policy.cu): layer 1 in fp32 on the
-    CUDA cores, layers 2 and 3 on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators in
-    TMEM), tanh / bias / sampling in the epilogues; the hidden activations never leave the SM."""
+    """The same policy as ONE warp-specialised sm_100a kernel (`k_actor`, csrc/q1_actor.cu): all three
+    layers on the tensor cores (tcgen05.mma, bf16 operands -- layer 1 with bf16-split operands, exact
+    to ~2^-17 -- fp32 accumulators in TMEM), tanh epilogues overlapped with the MMAs, sampling and
+    (closed loop) the env tick on their own warps; the hidden activations never leave tensor memory."""
 
     def __init__(self, weights, num_keys=4, action_range=10.0, device=0, seed=0):
         super().__init__(weights, num_keys=num_keys, action_range=action_range, device=device, seed=seed)
@@ -138,11 +140,60 @@ class FusedMLPPolicy(MLPPolicy):
         self.step_count += 1
         return out
 
+    # ------------------------------------------------------------------ the closed loop, fused
+    @property
+    def device_policy(self):
+        """`analyse.eval_sim` runs the episode closed loop on the device for trainers that have one."""
+        return self
 
-def rollout(env, policy, ticks, deterministic=False, graph=True, ticks_per_graph=8, timing=None):
-    """Closed loop on the device: policy -> `step_tensors` (fused auto-reset) for `ticks` ticks.
-    Returns the last (obs, reward, done, zero_start) tensors; with `track_returns` the episode
-    statistics accumulate in `env.metrics()`.
+    def can_fuse(self, env):
+        """The fused closed-loop kernel needs the counter form of the key timers."""
+        return not env.info.f64_stamps and env._num_keys == self.num_keys
+
+    def rollout_fused(self, env, ticks, deterministic=False, auto_reset=True, want_outputs=True):
+        """`ticks` ticks of policy -> sample -> env tick -> observation in ONE launch
+        (`q1_policy_rollout`: env state in shared memory, activations in tensor memory, no launch and
+        no HBM traffic per tick), asynchronous on torch's current stream.  The sampling noise is keyed
+        by (policy seed, global env index, env tick counter).  -> (final obs (N, 6), per-env reward
+        sum (N,)) CUDA tensors, or None."""
+        torch = self._torch
+        n = env.num_envs
+        obs = rsum = None
+        if want_outputs:
+            obs = torch.empty((n, 6), dtype=torch.float32, device=self.device)
+            rsum = torch.empty(n, dtype=torch.float32, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.load().q1_policy_rollout(
+            self._handle, env.handle, int(ticks), int(bool(auto_reset)), int(bool(deterministic)), self.seed,
+            self.low, self.high, 0, None,
+            ctypes.c_void_p(obs.data_ptr()) if obs is not None else None,
+            ctypes.c_void_p(rsum.data_ptr()) if rsum is not None else None, stream))
+        env._step_num += int(ticks)
+        return (obs, rsum) if want_outputs else None
+
+    def record_episode(self, env, ticks, deterministic=True, auto_reset=False, shadow_jump=True):
+        """The fused closed loop with the per-tick record of `VectorPhysEnv.record`
+        (`q1_policy_rollout_host`) -> dict of arrays (ticks, num_envs, ...) + "final_obs"."""
+        tape = env.new_record(int(ticks))
+        final_obs = np.empty((env.num_envs, 6), np.float32)
+        view = env._record_view(tape, 0)
+        _lib.check(_lib.load().q1_policy_rollout_host(
+            self._handle, env.handle, int(ticks), int(bool(auto_reset)), int(bool(deterministic)), self.seed,
+            self.low, self.high, _lib.Q1_RECORD_SHADOW_JUMP if shadow_jump else 0, ctypes.byref(view),
+            ctypes.c_void_p(final_obs.ctypes.data)))
+        env._step_num += int(ticks)
+        tape["final_obs"] = final_obs
+        return tape
+
+
+def rollout(env, policy, ticks, deterministic=False, graph=True, ticks_per_graph=8, timing=None, fused=None):
+    """Closed loop on the device for `ticks` ticks with fused auto-reset; with `track_returns` the
+    episode statistics accumulate in `env.metrics()`.
+
+    fused (default: whenever possible): a `FusedMLPPolicy` on an env with counter key timers runs the
+    whole loop as ONE kernel launch (`FusedMLPPolicy.rollout_fused`) and returns (final obs, per-env
+    reward sum).  Otherwise: policy kernel -> `step_tensors` per tick, returning the last (obs, reward,
+    done, zero_start) tensors:
 
     graph=True captures `ticks_per_graph` ticks (policy kernel, noise counter, step kernel each) in
     one CUDA graph and replays it: the loop is launch-bound otherwise.  The sampling noise advances
@@ -151,6 +202,19 @@ def rollout(env, policy, ticks, deterministic=False, graph=True, ticks_per_graph
     torch = policy._torch
     ticks = int(ticks)
     dev = policy.device
+    if fused is None:
+        fused = hasattr(policy, "rollout_fused") and policy.can_fuse(env)
+    if fused:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = policy.rollout_fused(env, ticks, deterministic=deterministic)
+        e1.record()
+        if timing is not None:
+            torch.cuda.current_stream(dev).synchronize()
+            timing.update(ticks=ticks, seconds=e0.elapsed_time(e1) * 1e-3,
+                          how="ONE launch of the fused policy + env kernel k_actor: env state in shared "
+                              "memory, activations in tensor memory")
+        return out
     base = env.info.env_index_base
     obs = torch.as_tensor(env._get_obs()).to(dev)
     n = obs.shape[0]
@@ -194,7 +258,8 @@ def rollout(env, policy, ticks, deterministic=False, graph=True, ticks_per_graph
         _lib.check(_lib.load().q1_advance_ticks(env.handle, (replays - 1) * per))
         env._step_num += (replays - 1) * per
         if timing is not None:
-            timing.update(ticks=replays * per, seconds=e0.elapsed_time(e1) * 1e-3)
+            timing.update(ticks=replays * per, seconds=e0.elapsed_time(e1) * 1e-3,
+                          how=f"policy kernel + step kernel per tick, {per} ticks per CUDA graph")
     finally:
         policy.step_count = int(policy._step_dev.item())
         policy._step_dev = None
