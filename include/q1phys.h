@@ -324,6 +324,11 @@ typedef struct q1_policy q1_policy; /* opaque */
 int q1_policy_create(int device, int num_keys, const float *w1, const float *b1, const float *w2,
                      const float *b2, const float *w3, const float *b3, q1_policy **out);
 int q1_policy_destroy(q1_policy *policy);
+/* Waits for the device and reports whether a policy kernel's internal watchdog fired (a role of the
+ * warp-specialised kernel gave up waiting for another: a bug, never a property of the input).  The
+ * launches are asynchronous, so this is where such a fault surfaces: Q1_OK, or Q1_ECUDA with the
+ * record in q1_last_error() and the results of the launches since the last check invalid. */
+int q1_policy_check(q1_policy *policy);
 /* obs (n, 6) f32, keys (n, num_keys) u8, mouse (n,) f32, logits_out (n, 2 * num_keys + 2) f32 or
  * NULL: DEVICE arrays.  Other arguments as q1_sample_actions. */
 int q1_policy_act(q1_policy *policy, int64_t n, const float *obs, double action_low,

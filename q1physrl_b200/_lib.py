@@ -137,6 +137,7 @@ SIGNATURES = {
                                   c_void_p, c_u64, c_void_p, c_void_p, c_void_p]),
     "q1_policy_create": (c_int, [c_int, c_int] + [c_void_p] * 6 + [ctypes.POINTER(c_void_p)]),
     "q1_policy_destroy": (c_int, [c_void_p]),
+    "q1_policy_check": (c_int, [c_void_p]),
     "q1_policy_act": (c_int, [c_void_p, c_i64, c_void_p, c_double, c_double, c_int, c_u64, c_u64, c_void_p,
                               c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "q1_policy_rollout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_u64, c_double, c_double, c_u32,

@@ -70,8 +70,13 @@ constexpr uint32_t SM_WEIGHTS_END = SM_BIAS3 + kOutPad * 4;
 constexpr uint32_t kImageBytes = SM_WEIGHTS_END - SM_B2;        /* what the host image holds */
 static_assert(kImageBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 enum : uint32_t { /* mbarriers, 8 bytes each */
-    B_W = 0, B_X = 1 /* [2] */, B_S = 3 /* [2] */, B_H1 = 5 /* [2] */, B_H2 = 7 /* [4] */, B_D2 = 11,
-    B_D3 = 12 /* [2] */, B_E = 14 /* [2] */, B_COUNT = 16
+    /* A waiter tests a phase PARITY, so no barrier may complete two phases between two waits of the same
+     * waiter.  Every barrier below is either gated that way by the protocol or used once per tile: the
+     * "activations of chunk c ready" barriers are one per chunk for that reason -- with one per chunk
+     * parity the epilogue, which needs nothing more from the MMA warp once the last layer-1 chunk is
+     * issued, could publish chunks c and c + 2 before the MMA warp had looked at chunk c. */
+    B_W = 0, B_X = 1 /* [2] */, B_S = 3 /* [2] */, B_H1 = 5 /* [8] */, B_H2 = 13 /* [4] */, B_D2 = 17,
+    B_D3 = 18 /* [2] */, B_E = 20 /* [2] */, B_SE = 22 /* [2] */, B_COUNT = 24
 };
 constexpr uint32_t SM_BAR = SM_WEIGHTS_END;
 constexpr uint32_t SM_TMEM = SM_BAR + 8 * B_COUNT;
@@ -134,32 +139,86 @@ __device__ __forceinline__ void bar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
+/* Watchdog of the role handshakes: a wait that has polled kWatchdogPolls times (seconds; a healthy wait
+ * takes microseconds) records who waited for what and raises g_fault[0]; every wait in every CTA then
+ * falls through, so a protocol bug ends the launch with an error report (q1_policy_* return Q1_ECUDA
+ * at their next call) instead of hanging the GPU. */
+constexpr uint32_t kWatchdogPolls = 1u << 22;
+__device__ unsigned int g_fault[8]; /* [0] raised, [1] tag of the first waiter that gave up, [2] sequence */
+
+__device__ __forceinline__ bool bar_test(uint32_t bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile("{\n"
                  ".reg .pred p;\n"
-                 "WAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DONE_%=;\n"
-                 "bra WAIT_%=;\n"
-                 "DONE_%=:\n"
-                 "}" ::"r"(bar), "r"(parity)
-                 : "memory");
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+/* tag = role (1 MMA, 2 EPI, 3 ENV) << 12 | barrier index << 7 | sub-step << 4.
+ * Everything here is INLINE on purpose: a wait may sit between a tcgen05.ld and its wait::ld, and a
+ * function call there lets the callee (or the caller's spill code around the call) use the very
+ * registers the asynchronous load is still going to write. */
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0, int64_t seq = 0)
+{
+    for (uint32_t polls = 0; !bar_test(bar, parity); polls++) {
+        if ((polls & 1023u) == 1023u && *reinterpret_cast<volatile unsigned int *>(&g_fault[0])) {
+            /* where the other roles stood when the first waiter gave up (first of each role) */
+            atomicCAS(&g_fault[4 + ((tag >> 12) & 3u)], 0u, (tag & 0xFFFu) | ((uint32_t)seq << 12) | 0x80000000u);
+            break;
+        }
+        if (polls >= kWatchdogPolls) {
+            if (atomicExch(&g_fault[0], 1u) == 0u) {
+                g_fault[1] = tag;
+                g_fault[2] = (uint32_t)seq;
+                g_fault[3] = blockIdx.x;
+            }
+            break;
+        }
+    }
+}
+/* The lanes of a warp leave a wait at different times; the whole-warp roles re-converge explicitly
+ * because what follows a wait is a .sync.aligned tcgen05 instruction, which every lane must issue
+ * together. */
+__device__ __forceinline__ void bar_wait_warp(uint32_t bar, uint32_t parity, uint32_t tag = 0, int64_t seq = 0)
+{
+    bar_wait(bar, parity, tag, seq);
+    __syncwarp();
+}
+__device__ __forceinline__ __attribute__((unused)) uint32_t pack_bf16(float lo, float hi)
 {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
-/* tanh of two pre-activations -> packed bf16x2.  Q1_POLICY_TANH_BF16X2 rounds the inputs to bf16
- * first and spends one MUFU on the pair (faster, ~3x the logit error); the default keeps fp32
- * inputs (tanh.approx.f32, relative error 2^-11) and rounds only the results. */
-#ifndef Q1_POLICY_TANH_BF16X2
-#define Q1_POLICY_TANH_BF16X2 0
+/* tanh of two pre-activations -> packed bf16x2 (what the next layer's A operand holds).  The special-
+ * function unit is what bounds the epilogues (tanh.approx.f32 issues at half the MUFU rate: 8 per clock
+ * per SM, 65 536 of them per tile), so the default spends ONE MUFU instruction on the pair:
+ *   Q1_POLICY_TANH 1 (default)  tanh.approx.f16x2: inputs rounded to f16 (11 significant bits; |x| here
+ *                               is < 100), result error 2^-10.99 -- both below the bf16 rounding of the
+ *                               stored activation (2^-9), so the logits move by less than that rounding
+ *                               already moves them (tests/test_api_gpu.py states and checks the bound)
+ *   Q1_POLICY_TANH 0            tanh.approx.f32 per element (relative error 2^-11), two MUFU per pair
+ *   Q1_POLICY_TANH 2            tanh.approx.bf16x2: inputs rounded to bf16 first, ~3x the logit error */
+#ifndef Q1_POLICY_TANH
+#define Q1_POLICY_TANH 1
 #endif
 __device__ __forceinline__ uint32_t tanh2_bf16(float lo, float hi)
 {
-#if Q1_POLICY_TANH_BF16X2
+#if Q1_POLICY_TANH == 1
+    uint32_t h2, t2, out;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(hi), "f"(lo));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t2) : "r"(h2));
+    asm("{\n"
+        ".reg .b16 l, h;\n"
+        ".reg .f32 fl, fh;\n"
+        "mov.b32 {l, h}, %1;\n"
+        "cvt.f32.f16 fl, l;\n"
+        "cvt.f32.f16 fh, h;\n"
+        "cvt.rn.bf16x2.f32 %0, fh, fl;\n"
+        "}" : "=r"(out) : "r"(t2));
+    return out;
+#elif Q1_POLICY_TANH == 2
     uint32_t x = pack_bf16(lo, hi), y;
     asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
     return y;
@@ -186,7 +245,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32])
+/* tcgen05.ld is asynchronous: the *_issue forms only start it, tmem_ld_wait*() completes it.  The wait
+ * also "redefines" the destination registers for the compiler (empty asm with them as in/out operands),
+ * so that no use of them can be scheduled above it. */
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t v[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -197,7 +259,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32])
                    "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
                    "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t v[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                   "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void pin16(uint32_t *v)
+{
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                      "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
+                      "+r"(v[14]), "+r"(v[15]));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t v[16])
+{
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    pin16(v);
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t v[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    pin16(v);
+    pin16(v + 16);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16])
 {
@@ -314,12 +401,14 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         for (int b = 0; b < 2; b++) {
             bar_init(bar(B_X + b), kRows);
             bar_init(bar(B_S + b), 1);
-            bar_init(bar(B_H1 + b), kEpiThreads);
+            bar_init(bar(B_SE + b), kEpiThreads);
             bar_init(bar(B_D3 + b), 1);
             bar_init(bar(B_E + b), kRows);
         }
         for (int b = 0; b < 4; b++)
             bar_init(bar(B_H2 + b), kEpiThreads);
+        for (int b = 0; b < 8; b++)
+            bar_init(bar(B_H1 + b), kEpiThreads);
         bar_init(bar(B_D2), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -364,11 +453,11 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
     if (warp == kMmaWarp) {
         /* ================================================================ MMA issuer ============ */
         if (lane == 0) {
-            bar_wait(bar(B_W), 0);
-            uint32_t nX[2] = {0, 0}, nH1[2] = {0, 0}, nE[2] = {0, 0}, nH2 = 0;
+            bar_wait(bar(B_W), 0, 4096u + B_W * 128u + 0u, 0);
+            uint32_t nX[2] = {0, 0}, nSE[2] = {0, 0}, nE[2] = {0, 0}, nH = 0; /* nH: tiles done */
             for (int64_t s = 0; s < S; s++) {
                 const uint32_t par = (uint32_t)s & 1u;
-                bar_wait(bar(B_X + par), nX[par]++ & 1u);
+                bar_wait(bar(B_X + par), nX[par]++ & 1u, 4096u + B_X * 128u + 0u, s);
                 tc_fence_after();
                 /* layer-1 chunk c: S[c & 1] (128 x 32) = X (128 x 32) . W1op rows 32c .. 32c+31 */
                 auto layer1_chunk = [&](uint32_t c) {
@@ -382,11 +471,14 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 layer1_chunk(1);
 #pragma unroll 1
                 for (uint32_t c = 0; c < 8; c++) {
-                    /* the epilogue has turned chunk c into activations (and is done with S[c & 1]) */
-                    bar_wait(bar(B_H1 + (c & 1u)), nH1[c & 1u]++ & 1u);
+                    /* the epilogue has chunk c in registers: S[c & 1] can take chunk c + 2 */
+                    bar_wait(bar(B_SE + (c & 1u)), nSE[c & 1u]++ & 1u, 4096u + B_SE * 128u + (c << 4), s);
                     tc_fence_after();
                     if (c + 2 < 8)
                         layer1_chunk(c + 2);
+                    /* ... and has turned it into activations */
+                    bar_wait(bar(B_H1 + c), nH & 1u, 4096u + B_H1 * 128u + (c << 4), s);
+                    tc_fence_after();
                     /* layer 2, K-steps 2c and 2c+1: D2 (128 x 256) += H1[:, 32c .. 32c+31] . W2 */
 #pragma unroll
                     for (uint32_t kk = 0; kk < 2; kk++) {
@@ -398,12 +490,12 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 }
                 mma_commit(bar(B_D2));
                 if (s >= 2) { /* the env warps have read the logits this accumulator held two tiles ago */
-                    bar_wait(bar(B_E + par), nE[par]++ & 1u);
+                    bar_wait(bar(B_E + par), nE[par]++ & 1u, 4096u + B_E * 128u + 0u, s);
                     tc_fence_after();
                 }
 #pragma unroll 1
                 for (uint32_t j = 0; j < 4; j++) {
-                    bar_wait(bar(B_H2 + j), nH2 & 1u);
+                    bar_wait(bar(B_H2 + j), nH & 1u, 4096u + B_H2 * 128u + (j << 4), s);
                     tc_fence_after();
                     /* layer 3, K-steps 4j .. 4j+3: D3 (128 x 16) += H2[:, 64j .. 64j+63] . W3 (padded) */
 #pragma unroll
@@ -414,7 +506,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                                     instr_desc(kOutPad), ks > 0);
                     }
                 }
-                nH2++;
+                nH++;
                 mma_commit(bar(B_D3 + par));
             }
         }
@@ -422,47 +514,76 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         /* ================================================================ tanh epilogues ======== */
         const uint32_t quad = warp & 3u, half = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column half */
         const uint32_t lane_base = tmem + ((quad * 32u) << 16);
-        bar_wait(bar(B_W), 0);
+        bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u + 0u, 0);
         const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2);
         uint32_t nS[2] = {0, 0}, nD2 = 0;
         for (int64_t s = 0; s < S; s++) {
+            /* Both epilogues are software-pipelined: the tcgen05.ld of the next chunk is in flight while
+             * this one's tanh run, and a chunk is published (wait::st, fence, arrive) one chunk late, when
+             * its tcgen05.st has long completed -- no TMEM latency sits on the MUFU-bound path. */
             /* ---- layer-1 epilogue: S chunk (bias already in the MMA) -> tanh -> H1 ---- */
-#pragma unroll 1
+            uint32_t va[16], vb[16];
+            bar_wait_warp(bar(B_S + 0), nS[0]++ & 1u, 8192u + B_S * 128u + 0u, s);
+            tc_fence_after();
+            tmem_ld16_issue(lane_base + TM_S + 16u * half, va);
+#pragma unroll
             for (uint32_t c = 0; c < 8; c++) {
-                bar_wait(bar(B_S + (c & 1u)), nS[c & 1u]++ & 1u);
-                tc_fence_after();
-                uint32_t v[16], p[8];
-                tmem_ld16(lane_base + TM_S + 32u * (c & 1u) + 16u * half, v);
+                uint32_t *cur = (c & 1u) ? vb : va, *nxt = (c & 1u) ? va : vb;
+                tmem_ld_wait16(cur);
+                tc_fence_before();
+                bar_arrive(bar(B_SE + (c & 1u)));
+                if (c + 1 < 8) {
+                    bar_wait_warp(bar(B_S + ((c + 1u) & 1u)), nS[(c + 1u) & 1u]++ & 1u, 8192u + B_S * 128u + ((c + 1u) << 4), s);
+                    tc_fence_after();
+                    tmem_ld16_issue(lane_base + TM_S + 32u * ((c + 1u) & 1u) + 16u * half, nxt);
+                }
+                uint32_t p[8];
 #pragma unroll
                 for (uint32_t e = 0; e < 8; e++)
-                    p[e] = tanh2_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-                if (c == 0 && s >= 1) { /* H still holds the previous tile's layer-2 activations until its
-                                           layer-3 MMAs have completed */
-                    bar_wait(bar(B_D3 + ((uint32_t)(s - 1) & 1u)), (uint32_t)((s - 1) >> 1) & 1u);
-                    tc_fence_after();
+                    p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1]));
+                if (c == 0) {
+                    if (s >= 1) { /* H still holds the previous tile's layer-2 activations until its
+                                     layer-3 MMAs have completed */
+                        bar_wait_warp(bar(B_D3 + ((uint32_t)(s - 1) & 1u)), (uint32_t)((s - 1) >> 1) & 1u, 8192u + B_D3 * 128u, s);
+                        tc_fence_after();
+                    }
+                } else { /* publish chunk c - 1 */
+                    tmem_st_wait();
+                    tc_fence_before();
+                    bar_arrive(bar(B_H1 + c - 1u));
                 }
                 tmem_st8(lane_base + TM_H + 16u * c + 8u * half, p);
-                tmem_st_wait();
-                tc_fence_before();
-                bar_arrive(bar(B_H1 + (c & 1u)));
             }
+            tmem_st_wait();
+            tc_fence_before();
+            bar_arrive(bar(B_H1 + 7u));
             /* ---- layer-2 epilogue: D2 + bias -> tanh -> H2 (over H1, which layer 2 has consumed) ---- */
-            bar_wait(bar(B_D2), nD2++ & 1u);
+            bar_wait_warp(bar(B_D2), nD2++ & 1u, 8192u + B_D2 * 128u + 0u, s);
             tc_fence_after();
-#pragma unroll 1
+            uint32_t wa[32], wb[32];
+            tmem_ld32_issue(lane_base + TM_D2 + 32u * half, wa);
+#pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
-                uint32_t v[32], p[16];
+                uint32_t *cur = (j & 1u) ? wb : wa, *nxt = (j & 1u) ? wa : wb;
                 const uint32_t col0 = 64u * j + 32u * half;
-                tmem_ld32(lane_base + TM_D2 + col0, v);
+                tmem_ld_wait32(cur);
+                if (j + 1 < 4)
+                    tmem_ld32_issue(lane_base + TM_D2 + col0 + 64u, nxt);
+                uint32_t p[16];
 #pragma unroll
                 for (uint32_t e = 0; e < 16; e++)
-                    p[e] = tanh2_bf16(__uint_as_float(v[2 * e]) + bias2[col0 + 2u * e],
-                                      __uint_as_float(v[2 * e + 1]) + bias2[col0 + 2u * e + 1u]);
+                    p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]) + bias2[col0 + 2u * e],
+                                      __uint_as_float(cur[2 * e + 1]) + bias2[col0 + 2u * e + 1u]);
+                if (j >= 1) { /* publish sub-step j - 1 */
+                    tmem_st_wait();
+                    tc_fence_before();
+                    bar_arrive(bar(B_H2 + j - 1u));
+                }
                 tmem_st16(lane_base + TM_H + 32u * j + 16u * half, p);
-                tmem_st_wait();
-                tc_fence_before();
-                bar_arrive(bar(B_H2 + j));
             }
+            tmem_st_wait();
+            tc_fence_before();
+            bar_arrive(bar(B_H2 + 3u));
         }
     } else {
         /* ================================================================ env rows =============== */
@@ -493,12 +614,14 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             }
             uint32_t cols[16];
             layer1_operand(o, cols);
+            __syncwarp(); /* .sync.aligned below: the lanes took different paths through the tick / the
+                             bounds checks, and inline asm gives the compiler no reason to re-converge them */
             tmem_st16(lane_base + TM_X + 16u * ((uint32_t)s2 & 1u), cols);
             tmem_st_wait();
             tc_fence_before();
             bar_arrive(bar(B_X + ((uint32_t)s2 & 1u)));
         };
-        bar_wait(bar(B_W), 0);
+        bar_wait_warp(bar(B_W), 0, 12288u + B_W * 128u + 0u, 0);
         for (int64_t s2 = 0; s2 < stride && s2 < S; s2++)
             prepare(s2);
 
@@ -508,7 +631,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             rsum[j] = 0.0f;
         for (int64_t s = 0; s < S; s++) {
             const uint32_t par = (uint32_t)s & 1u;
-            bar_wait(bar(B_D3 + par), (uint32_t)(s >> 1) & 1u);
+            bar_wait_warp(bar(B_D3 + par), (uint32_t)(s >> 1) & 1u, 12288u + B_D3 * 128u + 0u, s);
             tc_fence_after();
             uint32_t v[16];
             tmem_ld16(lane_base + TM_D3 + 16u * par, v);
@@ -669,6 +792,31 @@ struct DeviceScope { /* switch to a device for the duration of a call */
     }
 };
 
+/* Reads (and clears) the watchdog record of the kernels launched so far on the current device; the
+ * caller has synchronised.  -> Q1_OK or Q1_ECUDA with the record in the error text. */
+int check_fault()
+{
+    unsigned int f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(f, g_fault, sizeof f) != cudaSuccess)
+        return q1_set_error(Q1_ECUDA, "k_actor: cannot read the watchdog record");
+    if (!f[0])
+        return Q1_OK;
+    const unsigned int zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_fault, zero, sizeof zero);
+    static const char *roles[] = {"?", "MMA", "EPI", "ENV"};
+    std::string others;
+    for (int r = 1; r <= 3; r++)
+        if (f[4 + r])
+            others += std::string("; a waiting ") + roles[r] + " thread stood at barrier " +
+                      std::to_string((f[4 + r] >> 7) & 31u) + " sub-step " + std::to_string((f[4 + r] >> 4) & 7u) +
+                      " sequence " + std::to_string((f[4 + r] >> 12) & 0x7FFFFu);
+    return q1_set_error(Q1_ECUDA, std::string("k_actor watchdog: the ") + roles[(f[1] >> 12) & 3u] +
+                                      " role gave up waiting for barrier " + std::to_string((f[1] >> 7) & 31u) +
+                                      " (sub-step " + std::to_string((f[1] >> 4) & 7u) + ") at sequence " +
+                                      std::to_string(f[2]) + " in CTA " + std::to_string(f[3]) + others +
+                                      "; the launch's results are invalid");
+}
+
 template <typename K> cudaError_t allow_smem(K kernel, uint32_t bytes)
 {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -748,6 +896,18 @@ int q1_policy_create(int device, int num_keys, const float *w1, const float *b1,
     }
     *out = p;
     return Q1_OK;
+}
+
+/* Synchronises the device and reports a watchdog record of the policy kernels, if any. */
+int q1_policy_check(q1_policy *p)
+{
+    if (!p)
+        return q1_set_error(Q1_EINVAL, "policy is NULL");
+    DeviceScope scope(p->device);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess)
+        return q1_set_error(Q1_ECUDA, std::string("q1_policy_check: ") + cudaGetErrorString(err));
+    return check_fault();
 }
 
 int q1_policy_destroy(q1_policy *p)
@@ -950,6 +1110,9 @@ int q1_policy_rollout_host(q1_policy *p, q1_env *env, int ticks, int auto_reset,
     cudaError_t err = cudaStreamSynchronize(s);
     if (err != cudaSuccess)
         return q1_set_error(Q1_ECUDA, std::string("q1_policy_rollout_host: ") + cudaGetErrorString(err));
+    rc = check_fault();
+    if (rc != Q1_OK)
+        return rc;
     return q1_advance_ticks(env, ticks);
 }
 

@@ -140,6 +140,10 @@ class FusedMLPPolicy(MLPPolicy):
         self.step_count += 1
         return out
 
+    def check(self):
+        """Synchronise and raise if a policy kernel's watchdog fired (`q1_policy_check`)."""
+        _lib.check(_lib.load().q1_policy_check(self._handle))
+
     # ------------------------------------------------------------------ the closed loop, fused
     @property
     def device_policy(self):

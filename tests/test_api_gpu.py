@@ -193,6 +193,8 @@ def test_fused_tcgen05_policy_kernel():
         o = torch.as_tensor(obs).cuda()
         a, b = ref.logits(o).cpu().numpy(), fused.logits(o).cpu().numpy()
         assert b.shape == a.shape
+        print(f"logit error vs fp32: max {np.abs(a - b).max():.4f}, mean {np.abs(a - b).mean():.5f} "
+              f"(|logit| up to {np.abs(a).max():.1f})")
         assert np.abs(a - b).max() < 0.15 and np.abs(a - b).mean() < 0.02, (np.abs(a - b).max(),)
         ka, ma = ref.act(o, deterministic=True)
         kb, mb = fused.act(o, deterministic=True)
