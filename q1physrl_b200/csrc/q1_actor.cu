@@ -21,20 +21,33 @@
  *                      tcgen05.st as the next layer's A operand; thread = (row, column half)
  *   warp 12      MMA   one lane issues every tcgen05.mma and tcgen05.commit
  *
- * The epilogues overlap the MMAs instead of alternating with them: layer 1 is issued in 8 column chunks
- * of 32 into a double-buffered 2 x 32-column staging area, and as soon as the epilogue has turned chunk
- * c into activations the MMA warp issues the two K-steps of layer 2 that consume them (and layer 1's
- * chunk c + 2); layer 3's K-steps trail the layer-2 epilogue the same way, 64 columns at a time.  With
- * two or more tiles per CTA the env tick of one tile runs under the policy phase of the next.
+ * The tanh epilogues, not the MMAs, bound the policy (65 536 MUFU.TANH per tile = 4096 cycles; the MMAs
+ * of a tile are ~2600), so the protocol is built to keep them running without ever waiting for the MMA
+ * warp mid-layer:
+ *   layer 1   both K-steps are issued at once into a 256-column accumulator; its epilogue walks the 8
+ *             chunks of 32 columns without a single wait, publishing each chunk of activations as it goes
+ *   layer 2   runs as two N = 128 halves.  Half a trails the layer-1 epilogue chunk by chunk (its K-steps
+ *             are issued as the activations appear) into its own accumulator; half b is issued in one go
+ *             when the layer-1 epilogue is done, over the layer-1 accumulator's first half, and executes
+ *             while the epilogue of half a runs
+ *   layer 3   K-steps trail the layer-2 epilogue chunk by chunk; the logits land in the (dead) first
+ *             columns of the layer-1 activations
+ * With two or more tiles per CTA the env tick of one tile runs under the policy phase of the next.
  *
  * Layer 1 on the tensor cores without bf16-quantising the observation (yaw / 90 would lose 3 degrees):
  * x = x_hi + x_mid + x_lo (three bf16, 24 bits), w = w_hi + w_lo; the five products that matter
  * (hi.hi, hi.lo, mid.hi, mid.lo, lo.hi) of the 6 inputs are 30 columns of one K = 32 operand, the last
- * two carry 1 x (b_hi, b_lo): the bias comes out of the MMA too.  Relative error ~2^-17 of |x w|.
+ * two carry 1 x (b_hi, b_lo): the bias comes out of the MMA too.  Relative error ~2^-17 of |x w|.  That
+ * operand is written by the env warps into shared memory (K-major, 128-byte swizzle, like the weights).
  *
- * Tensor memory (512 columns): H [0,128) activations (A operand of layers 2 and 3) | D2 [128,384)
- * layer-2 accumulator | S [384,448) two layer-1 chunk buffers | X [448,480) two layer-1 operands (tile
- * parity) | D3 [480,512) two logit accumulators (tile parity).
+ * Tensor memory (512 columns = four regions of 128):
+ *   R0 [0,128)    H1: layer-1 activations, A operand of layer 2; afterwards its first 16 columns take
+ *                 the logits (layer 3's accumulator)
+ *   R1 [128,256)  layer-1 accumulator, columns 0..127; then layer-2 accumulator, half b
+ *   R2 [256,384)  layer-1 accumulator, columns 128..255; then H2: layer-2 activations, A operand of layer 3
+ *   R3 [384,512)  layer-2 accumulator, half a
+ * A thread only ever touches its own lane (= env row), so within a lane program order is enough; the
+ * barriers order lanes against the MMAs, and the MMAs of one issuing thread execute in issue order.
  */
 #include "q1_internal.h"
 #include "q1_device_common.cuh"
@@ -58,7 +71,7 @@ constexpr int kObs = 6;
 constexpr int kEnvWarps = 4, kEpiWarps = 8, kMmaWarp = kEnvWarps + kEpiWarps;
 constexpr int kThreads = 32 * (kMmaWarp + 1);
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kMaxTiles = 8; /* tiles of env state a CTA keeps in shared memory (LOOP) */
+constexpr int kMaxTiles = 3; /* tiles of env state a CTA keeps in shared memory (LOOP) */
 
 /* shared-memory image; every UMMA operand block is 1024-byte aligned (128-byte swizzle atoms) */
 constexpr uint32_t SM_B2 = 0;                                  /* W2^T: 4 K-atoms x 256 rows x 128 B */
@@ -69,16 +82,22 @@ constexpr uint32_t SM_BIAS3 = SM_BIAS2 + kHidden * 4;          /* fp32 [16] */
 constexpr uint32_t SM_WEIGHTS_END = SM_BIAS3 + kOutPad * 4;
 constexpr uint32_t kImageBytes = SM_WEIGHTS_END - SM_B2;        /* what the host image holds */
 static_assert(kImageBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
-enum : uint32_t { /* mbarriers, 8 bytes each */
-    /* A waiter tests a phase PARITY, so no barrier may complete two phases between two waits of the same
-     * waiter.  Every barrier below is either gated that way by the protocol or used once per tile: the
-     * "activations of chunk c ready" barriers are one per chunk for that reason -- with one per chunk
-     * parity the epilogue, which needs nothing more from the MMA warp once the last layer-1 chunk is
-     * issued, could publish chunks c and c + 2 before the MMA warp had looked at chunk c. */
-    B_W = 0, B_X = 1 /* [2] */, B_S = 3 /* [2] */, B_H1 = 5 /* [8] */, B_H2 = 13 /* [4] */, B_D2 = 17,
-    B_D3 = 18 /* [2] */, B_E = 20 /* [2] */, B_SE = 22 /* [2] */, B_COUNT = 24
+enum : uint32_t { /* mbarriers, 8 bytes each.  A waiter tests a phase PARITY, so no barrier may complete two
+                     phases between two waits of the same waiter: every barrier here completes once per tile
+                     (B_X: once per two) and the protocol keeps every waiter within one tile of every signaller. */
+    B_W = 0,        /* weights have landed in shared memory */
+    B_X = 1,        /* [2] layer-1 operand of the tile written (env rows -> MMA) */
+    B_L1 = 3,       /* layer-1 accumulator complete (MMA -> epilogue) */
+    B_H1 = 4,       /* [8] chunk c of the layer-1 activations stored (epilogue -> MMA) */
+    B_L2A = 12,     /* layer-2 accumulator, half a, complete */
+    B_L2B = 13,     /* ... half b */
+    B_H2 = 14,      /* [4] chunk j of the layer-2 activations stored */
+    B_D3 = 18,      /* logits complete (MMA -> env rows) */
+    B_E = 19,       /* logits read (env rows -> epilogue: R0 may take the next tile's activations) */
+    B_COUNT = 20
 };
-constexpr uint32_t SM_BAR = SM_WEIGHTS_END;
+constexpr uint32_t SM_X = (SM_WEIGHTS_END + 1023) & ~1023u;     /* two layer-1 operands: 128 rows x 128 B (K = 32 used) */
+constexpr uint32_t SM_BAR = SM_X + 2 * kRows * 128;
 constexpr uint32_t SM_TMEM = SM_BAR + 8 * B_COUNT;
 constexpr uint32_t SM_STATE = (SM_TMEM + 16 + 127) & ~127u;    /* LOOP: kMaxTiles x kSlotBytes */
 constexpr uint32_t SLOT_EPOCH = kTileBytes;                     /* u32 [128] */
@@ -88,8 +107,8 @@ constexpr uint32_t SM_TOTAL_ACT = SM_STATE;
 constexpr uint32_t SM_TOTAL_LOOP = SM_STATE + kMaxTiles * kSlotBytes;
 static_assert(SM_TOTAL_LOOP <= 232448, "one CTA per SM: at most 227 KB of shared memory");
 
-/* tensor-memory columns (32-bit) */
-constexpr uint32_t TM_H = 0, TM_D2 = 128, TM_S = 384, TM_X = 448, TM_D3 = 480;
+/* tensor-memory columns (32-bit), see the map above */
+constexpr uint32_t TM_H1 = 0, TM_D3 = 0, TM_L1 = 128, TM_D2B = 128, TM_H2 = 256, TM_D2A = 384;
 
 /* instruction descriptor of tcgen05.mma kind::f16: D = f32, A = B = bf16, both K-major, M = 128 */
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t n)
@@ -122,6 +141,18 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
                  "}\n" ::"r"(tmem_d),
                  "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+                 : "memory");
+}
+/* both operands from shared memory */
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            bool accumulate)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                 "}\n" ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
                  : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar)
@@ -201,7 +232,7 @@ __device__ __forceinline__ __attribute__((unused)) uint32_t pack_bf16(float lo, 
  *   Q1_POLICY_TANH 0            tanh.approx.f32 per element (relative error 2^-11), two MUFU per pair
  *   Q1_POLICY_TANH 2            tanh.approx.bf16x2: inputs rounded to bf16 first, ~3x the logit error */
 #ifndef Q1_POLICY_TANH
-#define Q1_POLICY_TANH 1
+#define Q1_POLICY_TANH 0
 #endif
 __device__ __forceinline__ uint32_t tanh2_bf16(float lo, float hi)
 {
@@ -398,18 +429,17 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
 
     if (tid == 0) {
         bar_init(bar(B_W), 1);
-        for (int b = 0; b < 2; b++) {
-            bar_init(bar(B_X + b), kRows);
-            bar_init(bar(B_S + b), 1);
-            bar_init(bar(B_SE + b), kEpiThreads);
-            bar_init(bar(B_D3 + b), 1);
-            bar_init(bar(B_E + b), kRows);
-        }
-        for (int b = 0; b < 4; b++)
-            bar_init(bar(B_H2 + b), kEpiThreads);
+        bar_init(bar(B_X + 0), kRows);
+        bar_init(bar(B_X + 1), kRows);
+        bar_init(bar(B_L1), 1);
+        bar_init(bar(B_L2A), 1);
+        bar_init(bar(B_L2B), 1);
+        bar_init(bar(B_D3), 1);
+        bar_init(bar(B_E), kRows);
         for (int b = 0; b < 8; b++)
             bar_init(bar(B_H1 + b), kEpiThreads);
-        bar_init(bar(B_D2), 1);
+        for (int b = 0; b < 4; b++)
+            bar_init(bar(B_H2 + b), kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         /* the weight image -> shared memory, in 32 KB bulk copies */
@@ -453,133 +483,128 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
     if (warp == kMmaWarp) {
         /* ================================================================ MMA issuer ============ */
         if (lane == 0) {
-            bar_wait(bar(B_W), 0, 4096u + B_W * 128u + 0u, 0);
-            uint32_t nX[2] = {0, 0}, nSE[2] = {0, 0}, nE[2] = {0, 0}, nH = 0; /* nH: tiles done */
+            bar_wait(bar(B_W), 0, 4096u + B_W * 128u, 0);
+            uint32_t nX[2] = {0, 0};
             for (int64_t s = 0; s < S; s++) {
-                const uint32_t par = (uint32_t)s & 1u;
-                bar_wait(bar(B_X + par), nX[par]++ & 1u, 4096u + B_X * 128u + 0u, s);
+                const uint32_t par = (uint32_t)s & 1u, ph = (uint32_t)s & 1u;
+                bar_wait(bar(B_X + par), nX[par]++ & 1u, 4096u + B_X * 128u, s);
                 tc_fence_after();
-                /* layer-1 chunk c: S[c & 1] (128 x 32) = X (128 x 32) . W1op rows 32c .. 32c+31 */
-                auto layer1_chunk = [&](uint32_t c) {
+                /* layer 1: L1 (128 x 256) = X (128 x 32, shared memory) . W1op.  R1 / R2 are free: the MMAs
+                 * of the previous tile that read them were issued before these and execute before them, and
+                 * this thread has seen the previous tile's layer-2 epilogue (half b) publish its last chunk */
 #pragma unroll
-                    for (uint32_t ks = 0; ks < 2; ks++)
-                        mma_bf16_ts(tmem + TM_S + 32u * (c & 1u), tmem + TM_X + 16u * par + 8u * ks,
-                                    smem_desc(s0 + SM_B1 + c * 4096u + ks * 32u), instr_desc(32), ks > 0);
-                    mma_commit(bar(B_S + (c & 1u)));
-                };
-                layer1_chunk(0);
-                layer1_chunk(1);
+                for (uint32_t ks = 0; ks < 2; ks++)
+                    mma_bf16_ss(tmem + TM_L1, smem_desc(s0 + SM_X + par * (kRows * 128u) + ks * 32u),
+                                smem_desc(s0 + SM_B1 + ks * 32u), instr_desc(kHidden), ks > 0);
+                mma_commit(bar(B_L1));
+                /* layer 2, half a (output units 0..127) -> R3, K-steps issued as the activations appear */
 #pragma unroll 1
                 for (uint32_t c = 0; c < 8; c++) {
-                    /* the epilogue has chunk c in registers: S[c & 1] can take chunk c + 2 */
-                    bar_wait(bar(B_SE + (c & 1u)), nSE[c & 1u]++ & 1u, 4096u + B_SE * 128u + (c << 4), s);
+                    bar_wait(bar(B_H1 + c), ph, 4096u + B_H1 * 128u + (c << 4), s);
                     tc_fence_after();
-                    if (c + 2 < 8)
-                        layer1_chunk(c + 2);
-                    /* ... and has turned it into activations */
-                    bar_wait(bar(B_H1 + c), nH & 1u, 4096u + B_H1 * 128u + (c << 4), s);
-                    tc_fence_after();
-                    /* layer 2, K-steps 2c and 2c+1: D2 (128 x 256) += H1[:, 32c .. 32c+31] . W2 */
 #pragma unroll
                     for (uint32_t kk = 0; kk < 2; kk++) {
                         const uint32_t ks = 2u * c + kk;
-                        mma_bf16_ts(tmem + TM_D2, tmem + TM_H + ks * 8u,
+                        mma_bf16_ts(tmem + TM_D2A, tmem + TM_H1 + ks * 8u,
                                     smem_desc(s0 + SM_B2 + (ks >> 2) * (kHidden * 128u) + (ks & 3u) * 32u),
-                                    instr_desc(kHidden), ks > 0);
+                                    instr_desc(128), ks > 0);
                     }
                 }
-                mma_commit(bar(B_D2));
-                if (s >= 2) { /* the env warps have read the logits this accumulator held two tiles ago */
-                    bar_wait(bar(B_E + par), nE[par]++ & 1u, 4096u + B_E * 128u + 0u, s);
-                    tc_fence_after();
-                }
+                mma_commit(bar(B_L2A));
+                /* half b (output units 128..255) -> R1, whose layer-1 columns every lane has consumed */
+#pragma unroll
+                for (uint32_t ks = 0; ks < 16; ks++)
+                    mma_bf16_ts(tmem + TM_D2B, tmem + TM_H1 + ks * 8u,
+                                smem_desc(s0 + SM_B2 + (ks >> 2) * (kHidden * 128u) + 128u * 128u + (ks & 3u) * 32u),
+                                instr_desc(128), ks > 0);
+                mma_commit(bar(B_L2B));
+                /* layer 3: D3 (128 x 16, over the first columns of H1, which half b above is the last to
+                 * read) += H2[:, 64j .. 64j+63] . W3 (padded), trailing the layer-2 epilogue */
 #pragma unroll 1
                 for (uint32_t j = 0; j < 4; j++) {
-                    bar_wait(bar(B_H2 + j), nH & 1u, 4096u + B_H2 * 128u + (j << 4), s);
+                    bar_wait(bar(B_H2 + j), ph, 4096u + B_H2 * 128u + (j << 4), s);
                     tc_fence_after();
-                    /* layer 3, K-steps 4j .. 4j+3: D3 (128 x 16) += H2[:, 64j .. 64j+63] . W3 (padded) */
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; kk++) {
                         const uint32_t ks = 4u * j + kk;
-                        mma_bf16_ts(tmem + TM_D3 + 16u * par, tmem + TM_H + ks * 8u,
+                        mma_bf16_ts(tmem + TM_D3, tmem + TM_H2 + ks * 8u,
                                     smem_desc(s0 + SM_B3 + (ks >> 2) * (kOutPad * 128u) + (ks & 3u) * 32u),
                                     instr_desc(kOutPad), ks > 0);
                     }
                 }
-                nH++;
-                mma_commit(bar(B_D3 + par));
+                mma_commit(bar(B_D3));
             }
         }
     } else if (warp >= kEnvWarps) {
         /* ================================================================ tanh epilogues ======== */
         const uint32_t quad = warp & 3u, half = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column half */
         const uint32_t lane_base = tmem + ((quad * 32u) << 16);
-        bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u + 0u, 0);
+        bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u, 0);
         const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2);
-        uint32_t nS[2] = {0, 0}, nD2 = 0;
         for (int64_t s = 0; s < S; s++) {
+            const uint32_t ph = (uint32_t)s & 1u;
             /* Both epilogues are software-pipelined: the tcgen05.ld of the next chunk is in flight while
              * this one's tanh run, and a chunk is published (wait::st, fence, arrive) one chunk late, when
              * its tcgen05.st has long completed -- no TMEM latency sits on the MUFU-bound path. */
-            /* ---- layer-1 epilogue: S chunk (bias already in the MMA) -> tanh -> H1 ---- */
+            /* ---- layer-1 epilogue: accumulator chunk (bias already in the MMA) -> tanh -> H1 ---- */
             uint32_t va[16], vb[16];
-            bar_wait_warp(bar(B_S + 0), nS[0]++ & 1u, 8192u + B_S * 128u + 0u, s);
+            if (s >= 1) /* the first columns of R0 hold the previous tile's logits until the env rows have
+                           read them (they do so the moment the logits are complete) */
+                bar_wait_warp(bar(B_E), ph ^ 1u, 8192u + B_E * 128u, s);
+            bar_wait_warp(bar(B_L1), ph, 8192u + B_L1 * 128u, s);
             tc_fence_after();
-            tmem_ld16_issue(lane_base + TM_S + 16u * half, va);
+            tmem_ld16_issue(lane_base + TM_L1 + 16u * half, va);
 #pragma unroll
             for (uint32_t c = 0; c < 8; c++) {
                 uint32_t *cur = (c & 1u) ? vb : va, *nxt = (c & 1u) ? va : vb;
                 tmem_ld_wait16(cur);
-                tc_fence_before();
-                bar_arrive(bar(B_SE + (c & 1u)));
-                if (c + 1 < 8) {
-                    bar_wait_warp(bar(B_S + ((c + 1u) & 1u)), nS[(c + 1u) & 1u]++ & 1u, 8192u + B_S * 128u + ((c + 1u) << 4), s);
-                    tc_fence_after();
-                    tmem_ld16_issue(lane_base + TM_S + 32u * ((c + 1u) & 1u) + 16u * half, nxt);
-                }
+                if (c + 1 < 8)
+                    tmem_ld16_issue(lane_base + TM_L1 + 32u * (c + 1u) + 16u * half, nxt);
                 uint32_t p[8];
 #pragma unroll
                 for (uint32_t e = 0; e < 8; e++)
                     p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1]));
-                if (c == 0) {
-                    if (s >= 1) { /* H still holds the previous tile's layer-2 activations until its
-                                     layer-3 MMAs have completed */
-                        bar_wait_warp(bar(B_D3 + ((uint32_t)(s - 1) & 1u)), (uint32_t)((s - 1) >> 1) & 1u, 8192u + B_D3 * 128u, s);
-                        tc_fence_after();
-                    }
-                } else { /* publish chunk c - 1 */
+                if (c > 0) { /* publish chunk c - 1 */
                     tmem_st_wait();
                     tc_fence_before();
                     bar_arrive(bar(B_H1 + c - 1u));
                 }
-                tmem_st8(lane_base + TM_H + 16u * c + 8u * half, p);
+                tmem_st8(lane_base + TM_H1 + 16u * c + 8u * half, p);
             }
             tmem_st_wait();
             tc_fence_before();
             bar_arrive(bar(B_H1 + 7u));
-            /* ---- layer-2 epilogue: D2 + bias -> tanh -> H2 (over H1, which layer 2 has consumed) ---- */
-            bar_wait_warp(bar(B_D2), nD2++ & 1u, 8192u + B_D2 * 128u + 0u, s);
-            tc_fence_after();
+            /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (R2: this lane is done with the
+             * layer-1 columns that were there), half a then half b ---- */
             uint32_t wa[32], wb[32];
-            tmem_ld32_issue(lane_base + TM_D2 + 32u * half, wa);
+            bar_wait_warp(bar(B_L2A), ph, 8192u + B_L2A * 128u, s);
+            tc_fence_after();
+            tmem_ld32_issue(lane_base + TM_D2A + 32u * half, wa);
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
                 uint32_t *cur = (j & 1u) ? wb : wa, *nxt = (j & 1u) ? wa : wb;
-                const uint32_t col0 = 64u * j + 32u * half;
+                const uint32_t unit0 = 64u * j + 32u * half;          /* first hidden unit of this chunk */
                 tmem_ld_wait32(cur);
-                if (j + 1 < 4)
-                    tmem_ld32_issue(lane_base + TM_D2 + col0 + 64u, nxt);
+                if (j == 0)
+                    tmem_ld32_issue(lane_base + TM_D2A + 64u + 32u * half, nxt);
+                if (j == 1) { /* the next chunk comes from half b */
+                    bar_wait_warp(bar(B_L2B), ph, 8192u + B_L2B * 128u, s);
+                    tc_fence_after();
+                    tmem_ld32_issue(lane_base + TM_D2B + 32u * half, nxt);
+                }
+                if (j == 2)
+                    tmem_ld32_issue(lane_base + TM_D2B + 64u + 32u * half, nxt);
                 uint32_t p[16];
 #pragma unroll
                 for (uint32_t e = 0; e < 16; e++)
-                    p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]) + bias2[col0 + 2u * e],
-                                      __uint_as_float(cur[2 * e + 1]) + bias2[col0 + 2u * e + 1u]);
-                if (j >= 1) { /* publish sub-step j - 1 */
+                    p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]) + bias2[unit0 + 2u * e],
+                                      __uint_as_float(cur[2 * e + 1]) + bias2[unit0 + 2u * e + 1u]);
+                if (j >= 1) { /* publish chunk j - 1 */
                     tmem_st_wait();
                     tc_fence_before();
                     bar_arrive(bar(B_H2 + j - 1u));
                 }
-                tmem_st16(lane_base + TM_H + 32u * j + 16u * half, p);
+                tmem_st16(lane_base + TM_H2 + 32u * j + 16u * half, p);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -614,11 +639,14 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             }
             uint32_t cols[16];
             layer1_operand(o, cols);
-            __syncwarp(); /* .sync.aligned below: the lanes took different paths through the tick / the
-                             bounds checks, and inline asm gives the compiler no reason to re-converge them */
-            tmem_st16(lane_base + TM_X + 16u * ((uint32_t)s2 & 1u), cols);
-            tmem_st_wait();
-            tc_fence_before();
+            /* row `row` of the K-major, 128-byte-swizzled operand: 16-byte chunk j (K = 8j .. 8j+7) sits at
+             * chunk position j ^ (row & 7) of the row's 128 bytes; chunks 4..7 (K >= 32) are never read */
+            unsigned char *xrow = smem + SM_X + ((uint32_t)s2 & 1u) * (kRows * 128u) + row * 128u;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++)
+                *reinterpret_cast<uint4 *>(xrow + ((j ^ (row & 7u)) << 4)) =
+                    make_uint4(cols[4 * j], cols[4 * j + 1], cols[4 * j + 2], cols[4 * j + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> the MMA's reads */
             bar_arrive(bar(B_X + ((uint32_t)s2 & 1u)));
         };
         bar_wait_warp(bar(B_W), 0, 12288u + B_W * 128u + 0u, 0);
@@ -630,13 +658,12 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         for (int j = 0; j < kMaxTiles; j++)
             rsum[j] = 0.0f;
         for (int64_t s = 0; s < S; s++) {
-            const uint32_t par = (uint32_t)s & 1u;
-            bar_wait_warp(bar(B_D3 + par), (uint32_t)(s >> 1) & 1u, 12288u + B_D3 * 128u + 0u, s);
+            bar_wait_warp(bar(B_D3), (uint32_t)s & 1u, 12288u + B_D3 * 128u, s);
             tc_fence_after();
             uint32_t v[16];
-            tmem_ld16(lane_base + TM_D3 + 16u * par, v);
+            tmem_ld16(lane_base + TM_D3, v);
             tc_fence_before();
-            bar_arrive(bar(B_E + par));
+            bar_arrive(bar(B_E));
             float lg[10];
 #pragma unroll
             for (int q = 0; q < 10; q++)
