@@ -12,25 +12,27 @@
  * q1physrl/action_dist.py:84-101, 186-243, q1physrl_env/env.py:482-510.
  *
  * All three layers run on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators
- * in tensor memory); activations never leave tensor memory.  13 warps, three roles, synchronised by
+ * in tensor memory); activations never leave tensor memory.  21 warps, three roles, synchronised by
  * mbarriers only:
  *
  *   warps 0-3    ENV   one thread per env row: builds the layer-1 operand from the observation, reads
  *                      the logits, samples the action and (LOOP) runs the env tick for its env
- *   warps 4-11   EPI   tanh epilogues: tcgen05.ld accumulator columns -> (+ bias) -> tanh -> bf16 ->
- *                      tcgen05.st as the next layer's A operand; thread = (row, column half)
- *   warp 12      MMA   one lane issues every tcgen05.mma and tcgen05.commit
+ *   warps 4-19   EPI   tanh epilogues: tcgen05.ld accumulator columns -> (+ bias) -> tanh -> bf16 ->
+ *                      tcgen05.st as the next layer's A operand; thread = (row, column part)
+ *   warp 20      MMA   one lane issues every tcgen05.mma and tcgen05.commit
  *
  * The tanh epilogues, not the MMAs, bound the policy (65 536 MUFU.TANH per tile = 4096 cycles; the MMAs
- * of a tile are ~2600), so the protocol is built to keep them running without ever waiting for the MMA
- * warp mid-layer:
- *   layer 1   both K-steps are issued at once into a 256-column accumulator; its epilogue walks the 8
- *             chunks of 32 columns without a single wait, publishing each chunk of activations as it goes
- *   layer 2   runs as two N = 128 halves.  Half a trails the layer-1 epilogue chunk by chunk (its K-steps
- *             are issued as the activations appear) into its own accumulator; half b is issued in one go
- *             when the layer-1 epilogue is done, over the layer-1 accumulator's first half, and executes
- *             while the epilogue of half a runs
- *   layer 3   K-steps trail the layer-2 epilogue chunk by chunk; the logits land in the (dead) first
+ * of a tile are ~2600), and every publish of epilogue output to the MMA warp (tcgen05.wait::st, fence,
+ * mbarrier arrive, the MMA warp's wake-up) costs a few hundred cycles whatever it publishes.  So the
+ * protocol gives every epilogue warp a CONTIGUOUS quarter of the columns and few, large steps:
+ *   layer 1   both K-steps are issued at once into a 256-column accumulator.  Epilogue part p (4 warps)
+ *             turns columns 64p .. 64p+63 into activations in two steps of 32, all four parts at once
+ *   layer 2   runs as four N = 64 quarters.  Quarter 0 trails the layer-1 epilogue (two K-steps per
+ *             published step, in whatever order the parts publish) into its own accumulator; quarters
+ *             1-3 are issued back to back when the layer-1 epilogue is done.  Epilogue part q takes quarter
+ *             q: the parts start one after the other as their quarter completes, so the epilogue of
+ *             quarter q runs while quarter q + 1 is still in the tensor pipe
+ *   layer 3   K-steps trail the layer-2 epilogue part by part; the logits land in the (dead) first
  *             columns of the layer-1 activations
  * With two or more tiles per CTA the env tick of one tile runs under the policy phase of the next.
  *
@@ -43,9 +45,9 @@
  * Tensor memory (512 columns = four regions of 128):
  *   R0 [0,128)    H1: layer-1 activations, A operand of layer 2; afterwards its first 16 columns take
  *                 the logits (layer 3's accumulator)
- *   R1 [128,256)  layer-1 accumulator, columns 0..127; then layer-2 accumulator, half b
+ *   R1 [128,256)  layer-1 accumulator, columns 0..127; then layer-2 accumulators, quarters 2 and 3
  *   R2 [256,384)  layer-1 accumulator, columns 128..255; then H2: layer-2 activations, A operand of layer 3
- *   R3 [384,512)  layer-2 accumulator, half a
+ *   R3 [384,512)  layer-2 accumulators, quarters 0 and 1
  * A thread only ever touches its own lane (= env row), so within a lane program order is enough; the
  * barriers order lanes against the MMAs, and the MMAs of one issuing thread execute in issue order.
  */
@@ -68,9 +70,10 @@ constexpr int kRows = 128;   /* envs per tile = UMMA M */
 constexpr int kHidden = 256; /* hidden width = K of layers 2 and 3, N of layers 1 and 2 */
 constexpr int kOutPad = 16;  /* layer-3 N, zero-padded from 2 * num_keys + 2 = 8 or 10 */
 constexpr int kObs = 6;
-constexpr int kEnvWarps = 4, kEpiWarps = 8, kMmaWarp = kEnvWarps + kEpiWarps;
+constexpr int kEpiParts = 4;  /* epilogue warps = 4 lane quadrants x 4 column parts (one warp of each part per scheduler) */
+constexpr int kEnvWarps = 4, kEpiWarps = 4 * kEpiParts, kMmaWarp = kEnvWarps + kEpiWarps;
+constexpr int kPartThreads = 128; /* threads of one epilogue part */
 constexpr int kThreads = 32 * (kMmaWarp + 1);
-constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kMaxTiles = 3; /* tiles of env state a CTA keeps in shared memory (LOOP) */
 
 /* shared-memory image; every UMMA operand block is 1024-byte aligned (128-byte swizzle atoms) */
@@ -88,13 +91,12 @@ enum : uint32_t { /* mbarriers, 8 bytes each.  A waiter tests a phase PARITY, so
     B_W = 0,        /* weights have landed in shared memory */
     B_X = 1,        /* [2] layer-1 operand of the tile written (env rows -> MMA) */
     B_L1 = 3,       /* layer-1 accumulator complete (MMA -> epilogue) */
-    B_H1 = 4,       /* [8] chunk c of the layer-1 activations stored (epilogue -> MMA) */
-    B_L2A = 12,     /* layer-2 accumulator, half a, complete */
-    B_L2B = 13,     /* ... half b */
-    B_H2 = 14,      /* [4] chunk j of the layer-2 activations stored */
-    B_D3 = 18,      /* logits complete (MMA -> env rows) */
-    B_E = 19,       /* logits read (env rows -> epilogue: R0 may take the next tile's activations) */
-    B_COUNT = 20
+    B_H1 = 4,       /* [8] step h of part p (index 2p + h) of the layer-1 activations stored (epilogue -> MMA) */
+    B_L2 = 12,      /* [4] layer-2 accumulator, quarter q, complete */
+    B_H2 = 16,      /* [4] part q of the layer-2 activations stored */
+    B_D3 = 20,      /* logits complete (MMA -> env rows) */
+    B_E = 21,       /* logits read (env rows -> epilogue: R0 may take the next tile's activations) */
+    B_COUNT = 22
 };
 constexpr uint32_t SM_X = (SM_WEIGHTS_END + 1023) & ~1023u;     /* two layer-1 operands: 128 rows x 128 B (K = 32 used) */
 constexpr uint32_t SM_BAR = SM_X + 2 * kRows * 128;
@@ -108,7 +110,8 @@ constexpr uint32_t SM_TOTAL_LOOP = SM_STATE + kMaxTiles * kSlotBytes;
 static_assert(SM_TOTAL_LOOP <= 232448, "one CTA per SM: at most 227 KB of shared memory");
 
 /* tensor-memory columns (32-bit), see the map above */
-constexpr uint32_t TM_H1 = 0, TM_D3 = 0, TM_L1 = 128, TM_D2B = 128, TM_H2 = 256, TM_D2A = 384;
+constexpr uint32_t TM_H1 = 0, TM_D3 = 0, TM_L1 = 128, TM_H2 = 256;
+__host__ __device__ constexpr uint32_t tm_l2(uint32_t q) { return q < 2 ? 384u + 64u * q : 128u + 64u * (q - 2u); }
 
 /* instruction descriptor of tcgen05.mma kind::f16: D = f32, A = B = bf16, both K-major, M = 128 */
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t n)
@@ -129,36 +132,61 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
     return d;
 }
 
+/* the descriptor of `bytes` further on (bytes a multiple of 16, no carry out of the 14-bit address field:
+ * shared memory is 228 KB, the field covers 256 KB) */
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t bytes) { return base + (uint64_t)(bytes >> 4); }
+
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 /* A operand from tensor memory (lane = row, 16-bit elements packed two per column along K) */
-__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                            bool accumulate)
+/* The MMA warp runs its whole program on all 32 lanes, so that addresses and descriptors are warp-uniform
+ * values the compiler can keep in the uniform datapath; only the tcgen05 instructions themselves are
+ * predicated on the elected lane (`leader`).  Issued from a divergent `if (lane == 0)` region instead, every
+ * MMA cost ~80 cycles of descriptor arithmetic and R2UR moves -- more than an N <= 128 MMA takes to execute. */
+__device__ __forceinline__ void mma_bf16_ts(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                            uint32_t idesc, bool accumulate)
 {
     asm volatile("{\n\t"
-                 ".reg .pred p;\n\t"
+                 ".reg .pred p, q;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+                 "setp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
                  "}\n" ::"r"(tmem_d),
-                 "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+                 "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate), "r"(leader)
                  : "memory");
 }
 /* both operands from shared memory */
-__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            bool accumulate)
+__device__ __forceinline__ void mma_bf16_ss(uint32_t leader, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, bool accumulate)
 {
     asm volatile("{\n\t"
-                 ".reg .pred p;\n\t"
+                 ".reg .pred p, q;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                 "setp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
                  "}\n" ::"r"(tmem_d),
-                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate), "r"(leader)
                  : "memory");
 }
-__device__ __forceinline__ void mma_commit(uint32_t bar)
+__device__ __forceinline__ void mma_commit(uint32_t leader, uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+    asm volatile("{\n\t"
+                 ".reg .pred q;\n\t"
+                 "setp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+                 "}\n" ::"r"(bar), "r"(leader)
                  : "memory");
+}
+/* 1 on exactly one lane of the (converged) warp, the same lane every time */
+__device__ __forceinline__ uint32_t elect_leader()
+{
+    uint32_t is;
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "elect.sync _|p, 0xffffffff;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t"
+                 "}\n" : "=r"(is));
+    return is;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -306,16 +334,47 @@ __device__ __forceinline__ void pin16(uint32_t *v)
                       "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
                       "+r"(v[14]), "+r"(v[15]));
 }
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t v[16])
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t v[8])
 {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    pin16(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait32(uint32_t v[32])
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t v[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+/* N consecutive columns, N in {8, 16, 32} (loads) / {4, 8, 16} (stores) */
+template <int N> __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t *v)
+{
+    if (N == 8)
+        tmem_ld8_issue(taddr, v);
+    else if (N == 16)
+        tmem_ld16_issue(taddr, v);
+    else
+        tmem_ld32_issue(taddr, v);
+}
+template <int N> __device__ __forceinline__ void tmem_ld_wait(uint32_t *v)
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    pin16(v);
-    pin16(v + 16);
+    if (N == 8) {
+        asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+    } else {
+        pin16(v);
+        if (N == 32)
+            pin16(v + 16);
+    }
+}
+template <int N> __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t *v)
+{
+    if (N == 4)
+        tmem_st4(taddr, v);
+    else if (N == 8)
+        tmem_st8(taddr, v);
+    else
+        tmem_st16(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16])
 {
@@ -362,6 +421,22 @@ __device__ __forceinline__ void layer1_operand(const float o[kObs], uint32_t col
     for (int j = 0; j < 16; j++)
         cols[j] = a[2 * j] | (a[2 * j + 1] << 16);
 }
+
+/* -DQ1_ACTOR_TRACE=1: CTA 0 stamps the SM clock at its protocol events into g_trace[sequence][event]
+ * (tools/trace_actor.py prints the timeline).  Never set in the shipped build. */
+#ifndef Q1_ACTOR_TRACE
+#define Q1_ACTOR_TRACE 0
+#endif
+#if Q1_ACTOR_TRACE
+__device__ long long g_trace[16][64];
+#define TRACE(seq, ev)                                                              \
+    do {                                                                            \
+        if (blockIdx.x == 0 && (seq) < 16 && (threadIdx.x & 31u) == 0)              \
+            g_trace[(seq)][(ev)] = clock64();                                       \
+    } while (0)
+#else
+#define TRACE(seq, ev) do { } while (0)
+#endif
 
 struct ActorArgs {
     const unsigned char *image;
@@ -432,14 +507,14 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         bar_init(bar(B_X + 0), kRows);
         bar_init(bar(B_X + 1), kRows);
         bar_init(bar(B_L1), 1);
-        bar_init(bar(B_L2A), 1);
-        bar_init(bar(B_L2B), 1);
         bar_init(bar(B_D3), 1);
         bar_init(bar(B_E), kRows);
         for (int b = 0; b < 8; b++)
-            bar_init(bar(B_H1 + b), kEpiThreads);
-        for (int b = 0; b < 4; b++)
-            bar_init(bar(B_H2 + b), kEpiThreads);
+            bar_init(bar(B_H1 + b), kPartThreads);
+        for (int b = 0; b < 4; b++) {
+            bar_init(bar(B_H2 + b), kPartThreads);
+            bar_init(bar(B_L2 + b), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         /* the weight image -> shared memory, in 32 KB bulk copies */
@@ -482,133 +557,129 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
 
     if (warp == kMmaWarp) {
         /* ================================================================ MMA issuer ============ */
-        if (lane == 0) {
-            bar_wait(bar(B_W), 0, 4096u + B_W * 128u, 0);
-            uint32_t nX[2] = {0, 0};
-            for (int64_t s = 0; s < S; s++) {
-                const uint32_t par = (uint32_t)s & 1u, ph = (uint32_t)s & 1u;
-                bar_wait(bar(B_X + par), nX[par]++ & 1u, 4096u + B_X * 128u, s);
+        const uint32_t leader = elect_leader();
+        bar_wait_warp(bar(B_W), 0, 4096u + B_W * 128u, 0);
+        const uint64_t dX = smem_desc(s0 + SM_X), dB1 = smem_desc(s0 + SM_B1), dB2 = smem_desc(s0 + SM_B2),
+                       dB3 = smem_desc(s0 + SM_B3);
+        for (int64_t s = 0; s < S; s++) {
+            const uint32_t par = (uint32_t)s & 1u, ph = (uint32_t)s & 1u;
+            TRACE(s, 0);
+            bar_wait_warp(bar(B_X + par), (uint32_t)(s >> 1) & 1u, 4096u + B_X * 128u, s);
+            tc_fence_after();
+            TRACE(s, 1);
+            /* layer 1: L1 (128 x 256) = X (128 x 32, shared memory) . W1op.  R1 / R2 are free: the MMAs
+             * of the previous tile that read them were issued before these and execute before them, and
+             * this warp has seen the previous tile's layer-2 epilogue publish its last part */
+#pragma unroll
+            for (uint32_t ks = 0; ks < 2; ks++)
+                mma_bf16_ss(leader, tmem + TM_L1, desc_at(dX, par * (kRows * 128u) + ks * 32u),
+                            desc_at(dB1, ks * 32u), instr_desc(kHidden), ks > 0);
+            mma_commit(leader, bar(B_L1));
+            TRACE(s, 2);
+            /* layer 2, quarter q: D (128 x 64) = H1 . W2[:, 64q .. 64q+63] */
+            auto layer2_kstep = [&](uint32_t q, uint32_t ks, bool accumulate) {
+                mma_bf16_ts(leader, tmem + tm_l2(q), tmem + TM_H1 + ks * 8u,
+                            desc_at(dB2, (ks >> 2) * (kHidden * 128u) + q * (64u * 128u) + (ks & 3u) * 32u),
+                            instr_desc(64), accumulate);
+            };
+            /* quarter 0 trails the layer-1 epilogue: the parts publish their first steps together, then
+             * their second steps -- take them in that order (K-steps may accumulate in any order) */
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint32_t p = i & 3u, h = i >> 2;
+                bar_wait_warp(bar(B_H1 + 2u * p + h), ph, 4096u + B_H1 * 128u + (i << 4), s);
                 tc_fence_after();
-                /* layer 1: L1 (128 x 256) = X (128 x 32, shared memory) . W1op.  R1 / R2 are free: the MMAs
-                 * of the previous tile that read them were issued before these and execute before them, and
-                 * this thread has seen the previous tile's layer-2 epilogue (half b) publish its last chunk */
+                layer2_kstep(0, 4u * p + 2u * h, i > 0);
+                layer2_kstep(0, 4u * p + 2u * h + 1u, true);
+                TRACE(s, 3 + i);
+            }
+            mma_commit(leader, bar(B_L2 + 0));
+            /* quarters 1-3, back to back (R1 takes 2 and 3: every lane has consumed its layer-1 columns) */
 #pragma unroll
-                for (uint32_t ks = 0; ks < 2; ks++)
-                    mma_bf16_ss(tmem + TM_L1, smem_desc(s0 + SM_X + par * (kRows * 128u) + ks * 32u),
-                                smem_desc(s0 + SM_B1 + ks * 32u), instr_desc(kHidden), ks > 0);
-                mma_commit(bar(B_L1));
-                /* layer 2, half a (output units 0..127) -> R3, K-steps issued as the activations appear */
-#pragma unroll 1
-                for (uint32_t c = 0; c < 8; c++) {
-                    bar_wait(bar(B_H1 + c), ph, 4096u + B_H1 * 128u + (c << 4), s);
-                    tc_fence_after();
-#pragma unroll
-                    for (uint32_t kk = 0; kk < 2; kk++) {
-                        const uint32_t ks = 2u * c + kk;
-                        mma_bf16_ts(tmem + TM_D2A, tmem + TM_H1 + ks * 8u,
-                                    smem_desc(s0 + SM_B2 + (ks >> 2) * (kHidden * 128u) + (ks & 3u) * 32u),
-                                    instr_desc(128), ks > 0);
-                    }
-                }
-                mma_commit(bar(B_L2A));
-                /* half b (output units 128..255) -> R1, whose layer-1 columns every lane has consumed */
+            for (uint32_t q = 1; q < 4; q++) {
 #pragma unroll
                 for (uint32_t ks = 0; ks < 16; ks++)
-                    mma_bf16_ts(tmem + TM_D2B, tmem + TM_H1 + ks * 8u,
-                                smem_desc(s0 + SM_B2 + (ks >> 2) * (kHidden * 128u) + 128u * 128u + (ks & 3u) * 32u),
-                                instr_desc(128), ks > 0);
-                mma_commit(bar(B_L2B));
-                /* layer 3: D3 (128 x 16, over the first columns of H1, which half b above is the last to
-                 * read) += H2[:, 64j .. 64j+63] . W3 (padded), trailing the layer-2 epilogue */
-#pragma unroll 1
-                for (uint32_t j = 0; j < 4; j++) {
-                    bar_wait(bar(B_H2 + j), ph, 4096u + B_H2 * 128u + (j << 4), s);
-                    tc_fence_after();
-#pragma unroll
-                    for (uint32_t kk = 0; kk < 4; kk++) {
-                        const uint32_t ks = 4u * j + kk;
-                        mma_bf16_ts(tmem + TM_D3, tmem + TM_H2 + ks * 8u,
-                                    smem_desc(s0 + SM_B3 + (ks >> 2) * (kOutPad * 128u) + (ks & 3u) * 32u),
-                                    instr_desc(kOutPad), ks > 0);
-                    }
-                }
-                mma_commit(bar(B_D3));
+                    layer2_kstep(q, ks, ks > 0);
+                mma_commit(leader, bar(B_L2 + q));
+                TRACE(s, 11 + q);
             }
+            /* layer 3: D3 (128 x 16, over the first columns of H1, which the MMAs above are the last to
+             * read) += H2[:, 64q .. 64q+63] . W3 (padded), trailing the layer-2 epilogue part by part */
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                bar_wait_warp(bar(B_H2 + q), ph, 4096u + B_H2 * 128u + (q << 4), s);
+                tc_fence_after();
+#pragma unroll
+                for (uint32_t kk = 0; kk < 4; kk++) {
+                    const uint32_t ks = 4u * q + kk;
+                    mma_bf16_ts(leader, tmem + TM_D3, tmem + TM_H2 + ks * 8u,
+                                desc_at(dB3, (ks >> 2) * (kOutPad * 128u) + (ks & 3u) * 32u),
+                                instr_desc(kOutPad), ks > 0);
+                }
+                TRACE(s, 15 + q);
+            }
+            mma_commit(leader, bar(B_D3));
         }
     } else if (warp >= kEnvWarps) {
         /* ================================================================ tanh epilogues ======== */
-        const uint32_t quad = warp & 3u, half = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column half */
+        const uint32_t quad = warp & 3u, part = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column part */
         const uint32_t lane_base = tmem + ((quad * 32u) << 16);
         bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u, 0);
-        const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2);
+        const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2) + 64u * part;
         for (int64_t s = 0; s < S; s++) {
             const uint32_t ph = (uint32_t)s & 1u;
-            /* Both epilogues are software-pipelined: the tcgen05.ld of the next chunk is in flight while
-             * this one's tanh run, and a chunk is published (wait::st, fence, arrive) one chunk late, when
-             * its tcgen05.st has long completed -- no TMEM latency sits on the MUFU-bound path. */
-            /* ---- layer-1 epilogue: accumulator chunk (bias already in the MMA) -> tanh -> H1 ---- */
-            uint32_t va[16], vb[16];
+            uint32_t va[32], vb[32], p[16];
+            /* ---- layer-1 epilogue, columns 64 part .. +63 (bias already in the MMA) -> tanh -> H1 ---- */
             if (s >= 1) /* the first columns of R0 hold the previous tile's logits until the env rows have
                            read them (they do so the moment the logits are complete) */
                 bar_wait_warp(bar(B_E), ph ^ 1u, 8192u + B_E * 128u, s);
+            if (quad == 0) TRACE(s, 20 + 8 * part + 0);
             bar_wait_warp(bar(B_L1), ph, 8192u + B_L1 * 128u, s);
             tc_fence_after();
-            tmem_ld16_issue(lane_base + TM_L1 + 16u * half, va);
+            if (quad == 0) TRACE(s, 20 + 8 * part + 1);
+            tmem_ld_issue<32>(lane_base + TM_L1 + 64u * part, va);
+            tmem_ld_wait<32>(va);
+            tmem_ld_issue<32>(lane_base + TM_L1 + 64u * part + 32u, vb);       /* in flight under the tanh below */
 #pragma unroll
-            for (uint32_t c = 0; c < 8; c++) {
-                uint32_t *cur = (c & 1u) ? vb : va, *nxt = (c & 1u) ? va : vb;
-                tmem_ld_wait16(cur);
-                if (c + 1 < 8)
-                    tmem_ld16_issue(lane_base + TM_L1 + 32u * (c + 1u) + 16u * half, nxt);
-                uint32_t p[8];
-#pragma unroll
-                for (uint32_t e = 0; e < 8; e++)
-                    p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1]));
-                if (c > 0) { /* publish chunk c - 1 */
-                    tmem_st_wait();
-                    tc_fence_before();
-                    bar_arrive(bar(B_H1 + c - 1u));
-                }
-                tmem_st8(lane_base + TM_H1 + 16u * c + 8u * half, p);
-            }
+            for (uint32_t e = 0; e < 16; e++)
+                p[e] = tanh2_bf16(__uint_as_float(va[2 * e]), __uint_as_float(va[2 * e + 1]));
+            tmem_st<16>(lane_base + TM_H1 + 32u * part, p);
+            tmem_ld_wait<32>(vb);
             tmem_st_wait();
             tc_fence_before();
-            bar_arrive(bar(B_H1 + 7u));
-            /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (R2: this lane is done with the
-             * layer-1 columns that were there), half a then half b ---- */
-            uint32_t wa[32], wb[32];
-            bar_wait_warp(bar(B_L2A), ph, 8192u + B_L2A * 128u, s);
+            bar_arrive(bar(B_H1 + 2u * part));
+            if (quad == 0) TRACE(s, 20 + 8 * part + 2);
+#pragma unroll
+            for (uint32_t e = 0; e < 16; e++)
+                p[e] = tanh2_bf16(__uint_as_float(vb[2 * e]), __uint_as_float(vb[2 * e + 1]));
+            tmem_st<16>(lane_base + TM_H1 + 32u * part + 16u, p);
+            tmem_st_wait();
+            tc_fence_before();
+            bar_arrive(bar(B_H1 + 2u * part + 1u));
+            if (quad == 0) TRACE(s, 20 + 8 * part + 3);
+            /* ---- layer-2 epilogue, quarter `part`: accumulator + bias -> tanh -> H2 (R2: this lane is done
+             * with the layer-1 columns that were there) ---- */
+            bar_wait_warp(bar(B_L2 + part), ph, 8192u + B_L2 * 128u + (part << 4), s);
             tc_fence_after();
-            tmem_ld32_issue(lane_base + TM_D2A + 32u * half, wa);
+            if (quad == 0) TRACE(s, 20 + 8 * part + 4);
+            tmem_ld_issue<32>(lane_base + tm_l2(part), va);
+            tmem_ld_wait<32>(va);
+            tmem_ld_issue<32>(lane_base + tm_l2(part) + 32u, vb);
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) {
-                uint32_t *cur = (j & 1u) ? wb : wa, *nxt = (j & 1u) ? wa : wb;
-                const uint32_t unit0 = 64u * j + 32u * half;          /* first hidden unit of this chunk */
-                tmem_ld_wait32(cur);
-                if (j == 0)
-                    tmem_ld32_issue(lane_base + TM_D2A + 64u + 32u * half, nxt);
-                if (j == 1) { /* the next chunk comes from half b */
-                    bar_wait_warp(bar(B_L2B), ph, 8192u + B_L2B * 128u, s);
-                    tc_fence_after();
-                    tmem_ld32_issue(lane_base + TM_D2B + 32u * half, nxt);
-                }
-                if (j == 2)
-                    tmem_ld32_issue(lane_base + TM_D2B + 64u + 32u * half, nxt);
-                uint32_t p[16];
+            for (uint32_t e = 0; e < 16; e++)
+                p[e] = tanh2_bf16(__uint_as_float(va[2 * e]) + bias2[2u * e],
+                                  __uint_as_float(va[2 * e + 1]) + bias2[2u * e + 1u]);
+            tmem_st<16>(lane_base + TM_H2 + 32u * part, p);
+            tmem_ld_wait<32>(vb);
 #pragma unroll
-                for (uint32_t e = 0; e < 16; e++)
-                    p[e] = tanh2_bf16(__uint_as_float(cur[2 * e]) + bias2[unit0 + 2u * e],
-                                      __uint_as_float(cur[2 * e + 1]) + bias2[unit0 + 2u * e + 1u]);
-                if (j >= 1) { /* publish chunk j - 1 */
-                    tmem_st_wait();
-                    tc_fence_before();
-                    bar_arrive(bar(B_H2 + j - 1u));
-                }
-                tmem_st16(lane_base + TM_H2 + 32u * j + 16u * half, p);
-            }
+            for (uint32_t e = 0; e < 16; e++)
+                p[e] = tanh2_bf16(__uint_as_float(vb[2 * e]) + bias2[32u + 2u * e],
+                                  __uint_as_float(vb[2 * e + 1]) + bias2[32u + 2u * e + 1u]);
+            tmem_st<16>(lane_base + TM_H2 + 32u * part + 16u, p);
             tmem_st_wait();
             tc_fence_before();
-            bar_arrive(bar(B_H2 + 3u));
+            bar_arrive(bar(B_H2 + part));
+            if (quad == 0) TRACE(s, 20 + 8 * part + 5);
         }
     } else {
         /* ================================================================ env rows =============== */
@@ -658,12 +729,15 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         for (int j = 0; j < kMaxTiles; j++)
             rsum[j] = 0.0f;
         for (int64_t s = 0; s < S; s++) {
+            if (warp == 0) TRACE(s, 52);
             bar_wait_warp(bar(B_D3), (uint32_t)s & 1u, 12288u + B_D3 * 128u, s);
             tc_fence_after();
+            if (warp == 0) TRACE(s, 53);
             uint32_t v[16];
             tmem_ld16(lane_base + TM_D3, v);
             tc_fence_before();
             bar_arrive(bar(B_E));
+            if (warp == 0) TRACE(s, 54);
             float lg[10];
 #pragma unroll
             for (int q = 0; q < 10; q++)
@@ -733,8 +807,10 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 }
                 slot_store(slot, row, e);
             }
+            if (warp == 0) TRACE(s, 55);
             if (s + stride < S)
                 prepare(s + stride); /* reads only this thread's own row of the slot */
+            if (warp == 0) TRACE(s, 56);
         }
         if (LOOP) { /* results of the launch: final observation and per-env reward sum */
             for (int j = 0; j < k; j++) {
@@ -924,6 +1000,13 @@ int q1_policy_create(int device, int num_keys, const float *w1, const float *b1,
     *out = p;
     return Q1_OK;
 }
+
+#if Q1_ACTOR_TRACE
+int q1_actor_trace(long long *out) /* 16 x 64 stamps of CTA 0 */
+{
+    return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 /* Synchronises the device and reports a watchdog record of the policy kernels, if any. */
 int q1_policy_check(q1_policy *p)
