@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t s0 = saddr_of(smem);
     auto bar = [&](uint32_t b) { return s0 + SM_BAR + 8u * b; };
 

@@ -12,17 +12,28 @@ namespace q1 {
  * of 0, logit of 1), then (mean, log_std) of the mouse action: one Categorical(2) per key, then
  * GaussianSquashedGaussian (mean, log_std clipped as in action_dist.py:67-76; squash =
  * clip(NormalCDF(raw / 0.90685), 1e-6, 1 - 1e-6) * (high - low) + low, action_dist.py:151, 186-192).
- * deterministic: argmax / squash(mean) (action_dist.py:84-88).  Noise: Philox4x32-10 keyed by
- * `seed`, counter (global env index, step).  Returns the key bit mask; *mouse receives the action. */
+ * deterministic: argmax / squash(mean) (action_dist.py:84-88).  Returns the key bit mask; *mouse
+ * receives the action.
+ *
+ * Noise: two Philox4x32-10 blocks keyed by `seed`, counter (global env index, step, block tag).  Block 0
+ * gives each key its own 32-bit word, of which the top 24 bits make a uniform in (0, 1) (the resolution of
+ * a float significand: a key with probability >= 2^-24 can fire); block 1 gives the two uniforms of the
+ * Box-Muller normal.  The arithmetic is float32 with the accurate library functions (expf, logf, cospif,
+ * erfcf: <= 2 ulp each), i.e. the sampled action is a function of the float32 logits to within a few ulp of
+ * float32 -- orders of magnitude inside what bf16 tensor-core logits differ from fp32 ones by.
+ * tests/test_sampling_gpu.py checks the key frequencies down to p = 1e-5 and the mouse action's
+ * distribution against scipy.stats.norm. */
 __device__ __forceinline__ uint32_t sample_action_row(const float *row, int num_keys, float low,
                                                       float high, bool deterministic, uint64_t seed,
                                                       uint64_t step, uint64_t gidx, float *mouse)
 {
-    /* one Philox block per (env, step): 16 bits per key draw, 2 x 32 bits for the Gaussian */
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (!deterministic)
+    uint32_t w[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
+    if (!deterministic) {
         philox4x32((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step,
                    (uint32_t)(step >> 32) ^ 0x504F4C00u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+        philox4x32((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step,
+                   (uint32_t)(step >> 32) ^ 0x504F4C01u, (uint32_t)seed, (uint32_t)(seed >> 32), g);
+    }
     uint32_t keybits = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -32,9 +43,8 @@ __device__ __forceinline__ uint32_t sample_action_row(const float *row, int num_
             if (deterministic) {
                 key = l1 > l0;
             } else {
-                const float p1 = __fdividef(1.0f, 1.0f + __expf(l0 - l1));  /* softmax over two logits */
-                const uint32_t bits = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                const float u = ((float)bits + 0.5f) * (1.0f / 65536.0f);
+                const float p1 = 1.0f / (1.0f + expf(l0 - l1));              /* softmax over two logits */
+                const float u = ((float)(w[k] >> 8) + 0.5f) * (1.0f / 16777216.0f);
                 key = u < p1;
             }
             keybits |= (key ? 1u : 0u) << k;
@@ -43,10 +53,10 @@ __device__ __forceinline__ uint32_t sample_action_row(const float *row, int num_
     float raw = fminf(fmaxf(row[2 * num_keys], -3.0f), 3.0f);             /* clipped mean */
     if (!deterministic) {
         const float log_std = fminf(fmaxf(row[2 * num_keys + 1], -20.0f), 2.0f);
-        const float u1 = ((float)(w[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float u2 = ((float)(w[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float eps = sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2); /* Box-Muller */
-        raw = raw + __expf(log_std) * eps;
+        const float u1 = ((float)(g[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((float)(g[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float eps = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);      /* Box-Muller */
+        raw = raw + expf(log_std) * eps;
     }
     const float scale = 0.5f * 1.8137f;
     float cdf = 0.5f * erfcf(-(raw / scale) * 0.70710678118654752440f);   /* NormalCDF */

@@ -2,7 +2,7 @@
 # usage: tools/ncu_range.sh [envs] [launches] -> gpurun_out/r2_range_<envs>.csv + profiles/r2_step_tma_range.json
 n=${1:-1048576}; l=${2:-16}
 mkdir -p gpurun_out
-ncu --replay-mode app-range --profile-from-start off --clock-control none \
+ncu --replay-mode app-range --clock-control none \
     --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum \
     --csv --log-file gpurun_out/r2_range_$n.csv python tools/ncu_range.py $n $l > gpurun_out/r2_range_$n.log 2>&1
 python - "$n" "$l" <<'PY'
