@@ -283,6 +283,18 @@ int q1_phys_apply_host(int device, int64_t n,
                        double *z_pos_out, float *vel_out, uint8_t *on_ground_out,
                        uint8_t *jump_released_out);
 
+/* phys.apply for a PlayerState whose velocity array is FLOAT64 -- what PlayerState.from_df (phys:163-170)
+ * builds.  NumPy then never rounds the velocity to f32 (friction speed phys:85, store phys:190, z velocity
+ * phys:119-122 all in f64); vel / vel_out are (n,3) f64 HOST arrays, the rest as q1_phys_apply_host. */
+int q1_phys_apply_vel64_host(int device, int64_t n,
+                             const double *yaw, const double *pitch, const double *roll,
+                             const double *fmove, const double *smove, const uint8_t *button2,
+                             const double *time_delta, int time_delta_f32,
+                             const double *z_pos, const double *vel, const uint8_t *on_ground,
+                             const uint8_t *jump_released,
+                             double *z_pos_out, double *vel_out, uint8_t *on_ground_out,
+                             uint8_t *jump_released_out);
+
 /* EvalSimResult.hypothetical_delta_speeds (q1physrl/analyse.py:92-118) in one launch instead of
  * num_angles phys.apply calls: delta_speed[a * n + t] = |v'_xy| - |v_xy| (f32) of one phys.apply
  * tick on row t with yaw = base_yaw[t] + rel_angles[a] and constant fmove / smove / time_delta.

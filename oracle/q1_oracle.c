@@ -162,6 +162,83 @@ void q1o_phys_apply(int64_t n,
     }
 }
 
+/* phys.apply when PlayerState.vel is FLOAT64 (PlayerState.from_df, phys:163-170, yields that: the
+ * notebook / demo comparison path).  NumPy then keeps every intermediate in f64: the friction speed
+ * (phys:85 norm of an f64 array), the stored velocity (phys:190 assigns into an f64 array: no rounding)
+ * and the z velocity (phys:119-122).  dt_f32 as above: 10 * dt and 800 * dt are then f32 products. */
+void q1o_phys_apply_vel64(int64_t n,
+                          const double *yaw, const double *pitch, const double *roll,
+                          const double *fmove, const double *smove, const uint8_t *button2,
+                          const double *time_delta, int dt_f32,
+                          const double *z_in, const double *vel_in,
+                          const uint8_t *og_in, const uint8_t *jr_in,
+                          double *z_out, double *vel_out, uint8_t *og_out, uint8_t *jr_out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        double ay = yaw[i] * M_PI / 180.;
+        double ap = pitch ? pitch[i] * M_PI / 180. : 0.0;
+        double ar = roll ? roll[i] * M_PI / 180. : 0.0;
+        double sy = sin(ay), cy = cos(ay);
+        double sp = sin(ap), cp = cos(ap);
+        double sr = sin(ar), cr = cos(ar);
+        double fwd_x = cp * cy;
+        double right_x = (-1 * sr * sp * cy + -1 * cr * -sy);
+        double fwd_y = cp * sy;
+        double right_y = (-1 * sr * sp * sy + -1 * cr * cy);
+        const double dt = time_delta[i];
+        const float dtf = (float)dt;
+        const int was_on_ground = og_in[i] != 0, jump = button2[i] != 0;
+        double vx = vel_in[3 * i], vy = vel_in[3 * i + 1], vz = vel_in[3 * i + 2];
+
+        double wx = fwd_x * fmove[i] + right_x * smove[i];             /* phys:95-101 */
+        double wy = fwd_y * fmove[i] + right_y * smove[i];
+        double ws = sqrt(wx * wx + wy * wy);
+        double wdx = wx, wdy = wy;
+        if (ws > 0) {
+            wdx = wx / ws;
+            wdy = wy / ws;
+        }
+        double wish_speed = ws < (double)Q_MAX_SPEED ? ws : (double)Q_MAX_SPEED;
+        if (ws != ws)
+            wish_speed = ws;
+        if (was_on_ground) {                                           /* phys:83-90, all f64 */
+            double speed = sqrt(vx * vx + vy * vy);
+            double control = speed > (double)Q_STOP_SPEED ? speed : (double)Q_STOP_SPEED;
+            double new_speed = speed - dt * control * (double)Q_FRICTION;
+            if (!(new_speed > 0))
+                new_speed = 0;
+            if (speed > 0) {
+                double ratio = new_speed / speed;
+                vx = vx * ratio;
+                vy = vy * ratio;
+            }
+        }
+        double current = vx * wdx + vy * wdy;                          /* phys:69-80 */
+        double clipped = (wish_speed > 30 && !was_on_ground) ? 30.0 : wish_speed;
+        double add = clipped - current;
+        if (!(add > 0))
+            add = 0;
+        double accel = (dt_f32 ? (double)(Q_ACCELERATE * dtf) : (double)Q_ACCELERATE * dt) * wish_speed;
+        if (add < accel)
+            accel = add;
+        vx = vx + accel * wdx;
+        vy = vy + accel * wdy;
+
+        int jr = (jr_in[i] != 0) | !jump;                              /* phys:112-132 */
+        int do_jump = was_on_ground && jump && jr;
+        vz = vz + (do_jump ? (double)Q_JUMP_SPEED : 0.0);
+        vz = vz - (dt_f32 ? (double)(Q_GRAVITY * dtf) : (double)Q_GRAVITY * dt);
+        double z = z_in[i] + dt * vz;
+        int og = z < (double)Q_FLOOR_HEIGHT;
+        z_out[i] = og ? (double)Q_FLOOR_HEIGHT : z;
+        vel_out[3 * i] = vx;
+        vel_out[3 * i + 1] = vy;
+        vel_out[3 * i + 2] = og ? 0.0 : vz;
+        og_out[i] = (uint8_t)og;
+        jr_out[i] = (uint8_t)jr;
+    }
+}
+
 /* ------------------------------------------------------------------ action decode (env.py) -- */
 
 typedef struct {

@@ -83,6 +83,15 @@ void q1o_phys_apply(int64_t n,
                     const uint8_t *og_in, const uint8_t *jr_in,
                     double *z_out, float *vel_out, uint8_t *og_out, uint8_t *jr_out);
 
+/* The same for a FLOAT64 velocity array (what PlayerState.from_df builds): every intermediate f64. */
+void q1o_phys_apply_vel64(int64_t n,
+                          const double *yaw, const double *pitch, const double *roll,
+                          const double *fmove, const double *smove, const uint8_t *button2,
+                          const double *time_delta, int dt_f32,
+                          const double *z_in, const double *vel_in,
+                          const uint8_t *og_in, const uint8_t *jr_in,
+                          double *z_out, double *vel_out, uint8_t *og_out, uint8_t *jr_out);
+
 /* Observation of the current state (env:392-408). */
 void q1o_observe(const q1o_config *cfg, int64_t n, const q1o_state *st, double *obs);
 

@@ -68,7 +68,7 @@ def lib():
         _lib.q1o_num_keys.restype = ctypes.c_int
         for name in ("q1o_step", "q1o_decode", "q1o_phys_apply", "q1o_observe", "q1o_reset_env",
                      "q1o_philox4x32", "q1o_reset_draws", "q1o_policy_action",
-                     "q1o_policy_actions", "q1o_reset_philox", "q1o_sincos"):
+                     "q1o_policy_actions", "q1o_reset_philox", "q1o_sincos", "q1o_phys_apply_vel64"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -222,13 +222,15 @@ def phys_apply(yaw, pitch, roll, fmove, smove, button2, time_delta, z_pos, vel, 
     u8 = lambda a: np.ascontiguousarray(np.asarray(a).astype(bool), np.uint8)
     yaw, pitch, roll, fmove, smove, dt, z = map(f64, (yaw, pitch, roll, fmove, smove,
                                                        time_delta, z_pos))
-    vel = np.ascontiguousarray(vel, np.float32)
+    vel64 = np.asarray(vel).dtype == np.float64      # PlayerState.from_df: NumPy then stays in f64 throughout
+    vel = np.ascontiguousarray(vel, np.float64 if vel64 else np.float32)
     b2, og, jr = u8(button2), u8(on_ground), u8(jump_released)
     z_out = np.empty(n, np.float64)
-    vel_out = np.empty((n, 3), np.float32)
+    vel_out = np.empty((n, 3), vel.dtype)
     og_out = np.empty(n, np.uint8)
     jr_out = np.empty(n, np.uint8)
-    lib().q1o_phys_apply(ctypes.c_int64(n), _ptr(yaw), _ptr(pitch), _ptr(roll), _ptr(fmove),
+    fn = lib().q1o_phys_apply_vel64 if vel64 else lib().q1o_phys_apply
+    fn(ctypes.c_int64(n), _ptr(yaw), _ptr(pitch), _ptr(roll), _ptr(fmove),
                          _ptr(smove), _ptr(b2), _ptr(dt), ctypes.c_int(dt_f32), _ptr(z), _ptr(vel),
                          _ptr(og), _ptr(jr),
                          _ptr(z_out), _ptr(vel_out), _ptr(og_out), _ptr(jr_out))

@@ -131,6 +131,7 @@ SIGNATURES = {
     "q1_get_metrics_host": (c_int, [c_void_p, c_int, ctypes.POINTER(Q1Metrics)]),
     "q1_phys_apply": (c_int, [c_int, c_i64] + [c_void_p] * 7 + [c_int] + [c_void_p] * 8 + [c_void_p]),
     "q1_phys_apply_host": (c_int, [c_int, c_i64] + [c_void_p] * 7 + [c_int] + [c_void_p] * 8),
+    "q1_phys_apply_vel64_host": (c_int, [c_int, c_i64] + [c_void_p] * 7 + [c_int] + [c_void_p] * 8),
     "q1_delta_speed_sweep_host": (c_int, [c_int, c_i64, c_i64, c_void_p, c_void_p, c_double, c_double,
                                           c_void_p, c_double, c_int] + [c_void_p] * 5),
     "q1_sample_actions": (c_int, [c_int, c_i64, c_int, c_void_p, c_double, c_double, c_int, c_u64, c_u64,

@@ -629,6 +629,85 @@ k_phys_apply(int64_t n, const double *__restrict__ yaw, const double *__restrict
     jr_out[i] = jr;
 }
 
+/* phys.apply when PlayerState.vel is FLOAT64 (PlayerState.from_df, phys:163-170: the notebook's comparison
+ * with recorded game frames).  NumPy then keeps the friction speed (phys:85), the stored velocity (phys:190
+ * assigns into an f64 array: no rounding) and the z velocity (phys:119-122) in f64.  dt_f32: 10 * dt and
+ * 800 * dt are float32 products (phys:78, 122 with a float32 time_delta array). */
+__global__ void __launch_bounds__(kBlock)
+k_phys_apply_vel64(int64_t n, const double *__restrict__ yaw, const double *__restrict__ pitch,
+                   const double *__restrict__ roll, const double *__restrict__ fmove,
+                   const double *__restrict__ smove, const uint8_t *__restrict__ button2,
+                   const double *__restrict__ time_delta, int dt_f32, const double *__restrict__ z_pos,
+                   const double *__restrict__ vel, const uint8_t *__restrict__ on_ground,
+                   const uint8_t *__restrict__ jump_released, double *__restrict__ z_out,
+                   double *__restrict__ vel_out, uint8_t *__restrict__ og_out, uint8_t *__restrict__ jr_out)
+{
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n)
+        return;
+    double sy, cy, sp = 0.0, cp = 1.0, sr = 0.0, cr = 1.0;                                  /* phys:58-66 */
+    sincos_ref(div64(mul64(yaw[i], kPi), 180.0), sy, cy);
+    if (pitch)
+        sincos_ref(div64(mul64(pitch[i], kPi), 180.0), sp, cp);
+    if (roll)
+        sincos_ref(div64(mul64(roll[i], kPi), 180.0), sr, cr);
+    const double fx = mul64(cp, cy);
+    const double rx = add64(mul64(mul64(mul64(-1.0, sr), sp), cy), mul64(mul64(-1.0, cr), -sy));
+    const double fy = mul64(cp, sy);
+    const double ry = add64(mul64(mul64(mul64(-1.0, sr), sp), sy), mul64(mul64(-1.0, cr), cy));
+    const double dt = time_delta[i];
+    const float dtf = (float)dt;
+    const bool was_on_ground = on_ground[i] != 0, jump = button2[i] != 0;
+    double vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+
+    double wx = add64(mul64(fx, fmove[i]), mul64(rx, smove[i]));                            /* phys:95-103 */
+    double wy = add64(mul64(fy, fmove[i]), mul64(ry, smove[i]));
+    double ws = __dsqrt_rn(add64(mul64(wx, wx), mul64(wy, wy)));
+    double wdx = wx, wdy = wy;
+    if (ws > 0.0) {
+        wdx = div64(wx, ws);
+        wdy = div64(wy, ws);
+    }
+    double wish_speed = ws < (double)kMaxSpeed ? ws : (double)kMaxSpeed;
+    if (ws != ws)
+        wish_speed = ws;
+    if (was_on_ground) {                                                                    /* phys:83-90 */
+        const double speed = __dsqrt_rn(add64(mul64(vx, vx), mul64(vy, vy)));
+        const double control = speed > (double)kStopSpeed ? speed : (double)kStopSpeed;
+        double new_speed = sub64(speed, mul64(mul64(dt, control), (double)kFriction));
+        if (!(new_speed > 0.0))
+            new_speed = 0.0;
+        if (speed > 0.0) {
+            const double ratio = div64(new_speed, speed);
+            vx = mul64(vx, ratio);
+            vy = mul64(vy, ratio);
+        }
+    }
+    const double current = add64(mul64(vx, wdx), mul64(vy, wdy));                           /* phys:69-80 */
+    const double clipped = (wish_speed > 30.0 && !was_on_ground) ? 30.0 : wish_speed;
+    double add = sub64(clipped, current);
+    if (!(add > 0.0))
+        add = 0.0;
+    double accel = mul64(dt_f32 ? (double)mul32(10.0f, dtf) : mul64(10.0, dt), wish_speed);
+    if (add < accel)
+        accel = add;
+    vx = add64(vx, mul64(accel, wdx));
+    vy = add64(vy, mul64(accel, wdy));
+
+    const bool jr = (jump_released[i] != 0) | !jump;                                        /* phys:112-132 */
+    const bool do_jump = was_on_ground && jump && jr;
+    vz = add64(vz, do_jump ? (double)kJumpSpeed : 0.0);
+    vz = sub64(vz, dt_f32 ? (double)mul32(800.0f, dtf) : mul64(800.0, dt));
+    const double z = add64(z_pos[i], mul64(dt, vz));
+    const bool og = z < (double)kFloorHeight;
+    z_out[i] = og ? (double)kFloorHeight : z;
+    vel_out[3 * i] = vx;
+    vel_out[3 * i + 1] = vy;
+    vel_out[3 * i + 2] = og ? 0.0 : vz;
+    og_out[i] = og;
+    jr_out[i] = jr;
+}
+
 /* q1physrl/analyse.py:92-118 `hypothetical_delta_speeds` in one launch: for every frame t and every
  * relative wish angle a, the ground-speed change of one phys.apply tick with yaw = base_yaw[t] +
  * rel_angle[a] and constant fmove / smove / time_delta.  out[a * n + t] = |v'| - |v| in f32. */
@@ -2230,6 +2309,64 @@ int q1_phys_apply_host(int device, int64_t n, const double *yaw, const double *p
         return rc;
     Q1_CUDA(cudaMemcpy(z_pos_out, d_zo, 8 * N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(vel_out, d_velo, 12 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(on_ground_out, d_ogo, N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(jump_released_out, d_jro, N, cudaMemcpyDeviceToHost));
+    return Q1_OK;
+}
+
+int q1_phys_apply_vel64_host(int device, int64_t n, const double *yaw, const double *pitch,
+                             const double *roll, const double *fmove, const double *smove,
+                             const uint8_t *button2, const double *time_delta, int time_delta_f32,
+                             const double *z_pos, const double *vel, const uint8_t *on_ground,
+                             const uint8_t *jump_released, double *z_pos_out, double *vel_out,
+                             uint8_t *on_ground_out, uint8_t *jump_released_out)
+{
+    if (n < 0)
+        return fail(Q1_EINVAL, "n must be >= 0");
+    if (n == 0)
+        return Q1_OK;
+    if (!yaw || !fmove || !smove || !button2 || !time_delta || !z_pos || !vel || !on_ground ||
+        !jump_released || !z_pos_out || !vel_out || !on_ground_out || !jump_released_out)
+        return fail(Q1_EINVAL, "a required array is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(Q1_ENODEV, "cudaSetDevice failed: libq1phys has no CPU implementation");
+    const size_t N = (size_t)n;
+    Staging st;
+    int rc = st.reserve(align_up(8 * N) * 8 + align_up(24 * N) * 2 + align_up(N) * 5 + 4096);
+    if (rc != Q1_OK)
+        return rc;
+    auto up = [&](auto *dst, const auto *src, size_t count) -> cudaError_t {
+        return cudaMemcpy(dst, src, count * sizeof(*src), cudaMemcpyHostToDevice);
+    };
+    double *d_yaw = st.take<double>(N), *d_pitch = pitch ? st.take<double>(N) : nullptr;
+    double *d_roll = roll ? st.take<double>(N) : nullptr;
+    double *d_fm = st.take<double>(N), *d_sm = st.take<double>(N), *d_dt = st.take<double>(N);
+    double *d_z = st.take<double>(N), *d_zo = st.take<double>(N);
+    double *d_vel = st.take<double>(3 * N), *d_velo = st.take<double>(3 * N);
+    uint8_t *d_b2 = st.take<uint8_t>(N), *d_og = st.take<uint8_t>(N), *d_jr = st.take<uint8_t>(N);
+    uint8_t *d_ogo = st.take<uint8_t>(N), *d_jro = st.take<uint8_t>(N);
+    Q1_CUDA(up(d_yaw, yaw, N));
+    if (pitch)
+        Q1_CUDA(up(d_pitch, pitch, N));
+    if (roll)
+        Q1_CUDA(up(d_roll, roll, N));
+    Q1_CUDA(up(d_fm, fmove, N));
+    Q1_CUDA(up(d_sm, smove, N));
+    Q1_CUDA(up(d_dt, time_delta, N));
+    Q1_CUDA(up(d_z, z_pos, N));
+    Q1_CUDA(up(d_vel, vel, 3 * N));
+    Q1_CUDA(up(d_b2, button2, N));
+    Q1_CUDA(up(d_og, on_ground, N));
+    Q1_CUDA(up(d_jr, jump_released, N));
+    k_phys_apply_vel64<<<grid_for(n), kBlock>>>(n, d_yaw, d_pitch, d_roll, d_fm, d_sm, d_b2, d_dt,
+                                                time_delta_f32, d_z, d_vel, d_og, d_jr, d_zo, d_velo, d_ogo,
+                                                d_jro);
+    rc = check_launch("k_phys_apply_vel64");
+    if (rc != Q1_OK)
+        return rc;
+    Q1_CUDA(cudaMemcpy(z_pos_out, d_zo, 8 * N, cudaMemcpyDeviceToHost));
+    Q1_CUDA(cudaMemcpy(vel_out, d_velo, 24 * N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(on_ground_out, d_ogo, N, cudaMemcpyDeviceToHost));
     Q1_CUDA(cudaMemcpy(jump_released_out, d_jro, N, cudaMemcpyDeviceToHost));
     return Q1_OK;

@@ -82,13 +82,16 @@ def apply(inputs: Inputs, player_state: PlayerState, device: int = 0) -> PlayerS
     """One movement tick for every row (phys.py:184-197), computed on the GPU.
 
     Accepts what the reference accepts: integer or float `fmove` / `smove`, per-row `time_delta`,
-    non-zero `pitch` / `roll`.  Velocity is carried in f32 exactly as `PlayerState.vel` is.
+    non-zero `pitch` / `roll`.  The velocity keeps its dtype, as in the reference: float32 (what the env
+    holds, phys.py:159) runs the f32 / f64 mix of env.vector_step; float64 (what `PlayerState.from_df`
+    builds) makes NumPy keep everything in f64, and so does the `k_phys_apply_vel64` kernel.
     """
     n = int(np.shape(player_state.z_pos)[0])
     vel_in = np.asarray(player_state.vel)
     if vel_in.shape != (n, 3):
         raise ValueError(f"player_state.vel must have shape ({n}, 3), got {vel_in.shape}")
-    vel = np.ascontiguousarray(vel_in, dtype=np.float32)
+    vel64 = vel_in.dtype == np.float64
+    vel = np.ascontiguousarray(vel_in, dtype=np.float64 if vel64 else np.float32)
     yaw, fmove, smove, dt, z = (_f64(a, n) for a in (inputs.yaw, inputs.fmove, inputs.smove,
                                                      inputs.time_delta, player_state.z_pos))
     pitch = _f64(inputs.pitch, n) if np.any(np.asarray(inputs.pitch) != 0) else None
@@ -98,10 +101,11 @@ def apply(inputs: Inputs, player_state: PlayerState, device: int = 0) -> PlayerS
     # NumPy computes friction / gravity in f32 when the time_delta array is float32 (analyse.py:110)
     dt_f32 = int(np.asarray(inputs.time_delta).dtype == np.float32)
     z_out = np.empty(n, np.float64)
-    vel_out = np.empty((n, 3), np.float32)
+    vel_out = np.empty((n, 3), vel.dtype)
     og_out = np.empty(n, np.uint8)
     jr_out = np.empty(n, np.uint8)
-    _lib.check(_lib.load().q1_phys_apply_host(
+    entry = _lib.load().q1_phys_apply_vel64_host if vel64 else _lib.load().q1_phys_apply_host
+    _lib.check(entry(
         device, n, _ptr(yaw), _ptr(pitch) if pitch is not None else None,
         _ptr(roll) if roll is not None else None, _ptr(fmove), _ptr(smove), _ptr(button2),
         _ptr(dt), dt_f32, _ptr(z), _ptr(vel), _ptr(og), _ptr(jr),

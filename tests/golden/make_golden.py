@@ -195,6 +195,39 @@ def record_phys_apply_dt32(name, n, seed):
     print(f"{name}: n={n} {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def record_phys_apply_vel64(name, n, seed):
+    """phys.apply on a PlayerState whose velocity is FLOAT64 -- what PlayerState.from_df (phys.py:163-170)
+    builds for the notebook's comparison with recorded game frames.  NumPy then runs the friction speed,
+    the stored velocity and the z velocity in f64.  Half the rows get a float32-valued time_delta column."""
+    rng = np.random.default_rng(seed)
+    yaw = rng.uniform(-4000, 4000, n)
+    pitch = np.where(rng.random(n) < 0.5, 0.0, rng.uniform(-30, 30, n))
+    roll = np.where(rng.random(n) < 0.5, 0.0, rng.uniform(-10, 10, n))
+    fmove = rng.choice([0., 400., 800., -800., 123.5], n)
+    smove = rng.choice([0., 530., -530., 1060., -1060., 350.], n)
+    button2 = rng.random(n) < 0.5
+    dt = rng.choice([1. / 72, 0.014, 0.013888888888888, 0.05], n)
+    z = np.where(rng.random(n) < 0.4, np.float64(np.float32(24.03125)), rng.uniform(24.03125, 80, n))
+    vel = rng.normal(0, 250, (n, 3)) * (rng.random((n, 1)) > 0.05)            # float64, not f32-valued
+    og = z <= 24.03125
+    vel[og, 2] = 0
+    jr = rng.random(n) < 0.8
+    out = {}
+    for tag, dtv in (("f64", dt), ("f32", dt.astype(np.float32))):
+        inputs = ref_phys.Inputs(yaw=yaw, pitch=pitch, roll=roll, fmove=fmove, smove=smove,
+                                 button2=button2, time_delta=dtv)
+        ps = ref_phys.PlayerState(z_pos=z, vel=vel, on_ground=og, jump_released=jr)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            res = ref_phys.apply(inputs, ps)
+        assert res.vel.dtype == np.float64 and res.z_pos.dtype == np.float64
+        out.update({f"{tag}_out_z_pos": res.z_pos, f"{tag}_out_vel": res.vel,
+                    f"{tag}_out_on_ground": res.on_ground, f"{tag}_out_jump_released": res.jump_released})
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, yaw=yaw, pitch=pitch, roll=roll, fmove=fmove, smove=smove, button2=button2,
+                        time_delta=dt, z_pos=z, vel=vel, on_ground=og, jump_released=jr, **out)
+    print(f"{name}: n={n} {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def record_delta_speeds(name, seed):
     """EvalSimResult.hypothetical_delta_speeds (q1physrl/analyse.py:92-118) of a scripted zero-start
     run: the loop of 360 phys.apply calls, restated here because analyse.py itself imports cv2 / ray."""
@@ -287,6 +320,7 @@ def main():
         record("odd_divisors_n16", dict(PARAMS_100M, action_range=7.3, time_limit=7.3), 16, 560, seed=15)
         record_phys_apply("phys_apply_n4096", 4096, seed=10)
         record_phys_apply_dt32("phys_apply_dt32_n4096", 4096, seed=13)
+        record_phys_apply_vel64("phys_apply_vel64_n2048", 2048, seed=16)
         record_delta_speeds("delta_speeds", seed=14)
         record_decoder("decoder_n64", PARAMS_100M, 64, 120, seed=11)
         record_decoder("decoder_discrete_n64", dict(DEFAULT, discrete_yaw_steps=7, smooth_keys=False,

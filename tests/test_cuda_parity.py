@@ -448,6 +448,34 @@ def test_phys_apply_float32_time_delta_golden():
     assert np.array_equal(out.vel, g["out_vel"])
 
 
+def test_phys_apply_float64_velocity_golden():
+    """PlayerState.from_df (phys.py:163-170) hands phys.apply a float64 velocity, and NumPy then
+    keeps friction, the stored velocity and the z velocity in f64.  k_phys_apply_vel64 against what the
+    unmodified reference returned, for a float64 and a float32 time_delta column."""
+    import pandas as pd
+    from q1physrl_b200 import phys
+    g = harness.load_golden("phys_apply_vel64_n2048")
+    for tag, dt in (("f64", g["time_delta"]), ("f32", g["time_delta"].astype(np.float32))):
+        out = phys.apply(phys.Inputs(yaw=g["yaw"], pitch=g["pitch"], roll=g["roll"], fmove=g["fmove"],
+                                     smove=g["smove"], button2=g["button2"], time_delta=dt),
+                         phys.PlayerState(g["z_pos"], g["vel"], g["on_ground"], g["jump_released"]))
+        assert out.vel.dtype == np.float64
+        assert np.array_equal(out.z_pos, g[f"{tag}_out_z_pos"]) and np.array_equal(out.vel, g[f"{tag}_out_vel"])
+        assert np.array_equal(out.on_ground, g[f"{tag}_out_on_ground"])
+        assert np.array_equal(out.jump_released, g[f"{tag}_out_jump_released"])
+    # the route the notebook takes: a DataFrame round trip yields float64 columns
+    ps = phys.PlayerState(g["z_pos"], g["vel"].astype(np.float32), g["on_ground"], g["jump_released"])
+    back = phys.PlayerState.from_df(ps.to_df())
+    assert isinstance(ps.to_df(), pd.DataFrame) and back.vel.dtype == np.float64
+    n = g["yaw"].shape[0]
+    inputs = phys.Inputs(yaw=g["yaw"], pitch=np.zeros(n), roll=np.zeros(n), fmove=g["fmove"], smove=g["smove"],
+                         button2=g["button2"], time_delta=g["time_delta"])
+    z, vel, og, jr = qo.phys_apply(g["yaw"], np.zeros(n), np.zeros(n), g["fmove"], g["smove"], g["button2"],
+                                   g["time_delta"], back.z_pos, back.vel, back.on_ground, back.jump_released)
+    out = phys.apply(inputs, back)
+    assert out.vel.dtype == np.float64 and np.array_equal(out.vel, vel) and np.array_equal(out.z_pos, z)
+
+
 def test_hypothetical_delta_speeds_golden():
     """analyse.EvalSimResult.hypothetical_delta_speeds: one sweep launch vs the reference's 360
     phys.apply calls."""

@@ -127,6 +127,18 @@ def test_oracle_phys_apply_float32_time_delta():
     assert np.array_equal(og, g["out_on_ground"]) and np.array_equal(jr, g["out_jump_released"])
 
 
+def test_oracle_phys_apply_float64_velocity():
+    """PlayerState.from_df gives a float64 velocity; NumPy then never rounds to f32 (phys.py:83-90, 190)."""
+    g = harness.load_golden("phys_apply_vel64_n2048")
+    assert g["vel"].dtype == np.float64
+    for tag, dt in (("f64", g["time_delta"]), ("f32", g["time_delta"].astype(np.float32))):
+        z, vel, og, jr = qo.phys_apply(g["yaw"], g["pitch"], g["roll"], g["fmove"], g["smove"], g["button2"],
+                                       dt, g["z_pos"], g["vel"], g["on_ground"], g["jump_released"])
+        assert vel.dtype == np.float64
+        assert np.array_equal(z, g[f"{tag}_out_z_pos"]) and np.array_equal(vel, g[f"{tag}_out_vel"])
+        assert np.array_equal(og, g[f"{tag}_out_on_ground"]) and np.array_equal(jr, g[f"{tag}_out_jump_released"])
+
+
 def test_oracle_hypothetical_delta_speeds():
     """analyse.py:92-118 through the oracle: 360 phys.apply calls on the recorded episode."""
     g = harness.load_golden("delta_speeds")
