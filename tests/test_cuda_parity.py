@@ -464,9 +464,9 @@ def test_phys_apply_float64_velocity_golden():
         assert np.array_equal(out.on_ground, g[f"{tag}_out_on_ground"])
         assert np.array_equal(out.jump_released, g[f"{tag}_out_jump_released"])
     # the route the notebook takes: a DataFrame round trip yields float64 columns
-    ps = phys.PlayerState(g["z_pos"], g["vel"].astype(np.float32), g["on_ground"], g["jump_released"])
-    back = phys.PlayerState.from_df(ps.to_df())
-    assert isinstance(ps.to_df(), pd.DataFrame) and back.vel.dtype == np.float64
+    ps = phys.PlayerState(g["z_pos"], g["vel"], g["on_ground"], g["jump_released"])
+    back = phys.PlayerState.from_df(pd.DataFrame(ps.to_df().to_dict("list")))
+    assert back.vel.dtype == np.float64 and np.array_equal(back.vel, g["vel"])
     n = g["yaw"].shape[0]
     inputs = phys.Inputs(yaw=g["yaw"], pitch=np.zeros(n), roll=np.zeros(n), fmove=g["fmove"], smove=g["smove"],
                          button2=g["button2"], time_delta=g["time_delta"])
