@@ -11,7 +11,10 @@ want = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum',
  'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
  'lts__t_bytes.sum','l1tex__t_bytes.sum','launch__grid_size','launch__block_size','sm__cycles_elapsed.avg','launch__occupancy_limit_registers',
  'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum','l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum','lts__t_sectors_op_write.sum','lts__t_sectors_op_read.sum',
- 'smsp__average_warp_latency_issue_stalled_long_scoreboard.pct','smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio']
+ 'smsp__average_warp_latency_issue_stalled_long_scoreboard.pct','smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+ 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active',
+ 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio','smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+ 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio','smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio']
 for r in rows[2:3]:
     print('kernel:', r[hdr.index('Kernel Name')][:90])
     for w in want:

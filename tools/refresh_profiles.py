@@ -1,6 +1,7 @@
-"""Turn the artefacts of tools/evidence.sh (gpurun_out/) into the committed profiles/r1_* files:
-bench lines, the ncu launch list and its per-kernel summary, the raw metrics of the `ncu --set full`
-capture of k_step_tma and the SASS / stall summary of tools/ncu_summary.py."""
+"""Turn the artefacts of tools/evidence.sh (gpurun_out/) into the committed profiles/<tag>_* files
+(python tools/refresh_profiles.py r2): bench lines, the ncu launch list and its per-kernel summary, the raw
+metrics of the `ncu --set full` capture of k_step_tma and the SASS / stall summaries of tools/ncu_summary.py
+for the step kernel, the policy kernel (k_actor, both modes) and the rollout kernel; sanitizer log."""
 import collections
 import csv
 import json
@@ -14,8 +15,10 @@ OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 
 for src, dst in (("bench_b200.json", f"{tag}_bench_b200.json"), ("bench_reference.json", f"{tag}_bench_reference.json"),
-                 ("launches.csv", f"{tag}_bench_launches.csv")):
-    shutil.copyfile(os.path.join(OUT, src), os.path.join(PROF, dst))
+                 ("bench_b200_20steps.json", f"{tag}_bench_b200_20steps.json"),
+                 ("launches.csv", f"{tag}_bench_launches.csv"), ("sanitizer.txt", f"{tag}_sanitizer.txt")):
+    if os.path.exists(os.path.join(OUT, src)):
+        shutil.copyfile(os.path.join(OUT, src), os.path.join(PROF, dst))
 
 # per-kernel summary of the launch list
 rows = [r for r in csv.reader(open(os.path.join(OUT, "launches.csv"))) if len(r) > 14 and r[0].isdigit()]
@@ -23,15 +26,16 @@ per = collections.OrderedDict()
 for r in rows:
     us = float(r[14]) / 1e3
     name = r[4]
-    if "k_step_tma<0, 1, 1>" in name and us > 200:   # the e2e leg: same kernel on mapped host buffers (PCIe-bound)
-        name = "k_step_tma<0, 1, 1> on page-locked HOST buffers (e2e leg, PCIe-bound)"
+    if "k_step_tma<" in name and us > 200:   # the e2e leg: same kernel on mapped host buffers (PCIe-bound)
+        name = "k_step_tma on page-locked HOST buffers (e2e leg, PCIe-bound)"
     per.setdefault(name, []).append(us)
 total = sum(sum(v) for v in per.values())
 with open(os.path.join(PROF, f"{tag}_bench_launches_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 python bench.py --steps 300 "
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 400 python bench.py --steps 300 "
             "--warmup 20 --no-cpu-baseline\n(per-launch times are cold-cache and serialised: compare shares; the "
-            "launches after the k_step_tma<0,1,1> ones belong to the e2e leg and to the closed-loop policy rollout / "
-            "config-4 rollout that run outside the timed region)\n\n")
+            "window starts inside the 200 warm-up + 300 timed k_step_tma launches; what follows them is the same-size "
+            "copy, the strong-scaling / e2e / host-ceiling legs and the closed-loop and config-4 rollouts, all outside "
+            "the timed region)\n\n")
     for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"{name[:72]:72s} n={len(v):4d} mean={sum(v) / len(v):8.2f} us share={sum(v) / total:.3f}\n")
 
@@ -56,8 +60,8 @@ def num(launch, key):
 
 first = launches[0]
 doc = {
-    "kernel": "k_step_tma<TRACK=false,LEAN=true,COMMON=true>",
-    "source": "ncu --set full --clock-control none --import-source on -k regex:k_step_tma -s 30 -c 2, python bench.py "
+    "kernel": "k_step_tma<TRACK=false,LEAN=true,COMMON=true,CTAS=6>",
+    "source": "ncu --set full --clock-control none --import-source on -k regex:k_step_tma -s 230 -c 2, python bench.py "
               "--steps 40 --warmup 10 --no-cpu-baseline (2^20 envs, nk=3)",
     "dram_bytes_read": num(first, "dram__bytes_read.sum"),
     "dram_bytes_write": num(first, "dram__bytes_write.sum"),
@@ -65,13 +69,20 @@ doc = {
     "algorithmic_bytes": 117 << 20,
     "note": "single launch under the profiler: reads (49.3 MB) equal the algorithmic 47 B/env exactly -- no re-reads; "
             "of the 73 MB written part is still dirty in the 126 MB L2 when the kernel ends and is written back during "
-            "later launches, so the in-kernel DRAM write count is below the algorithmic figure. In the back-to-back "
-            "bench loop (ring of 4 shards) every step moves the full 123 MB. The global loads are the 2 x 256-bit "
-            "lookups per env in the 3.5 KB libm sin/cos table (L1-resident).",
+            "later launches, so the in-kernel DRAM write count is below the algorithmic figure: the RANGE capture over "
+            "16 consecutive ring launches (profiles/r2_step_tma_range.json, tools/ncu_range.sh) counts 115.9 MB per "
+            "launch against 122.7 MB algorithmic. The global loads are the 2 x 256-bit lookups per env in the 3.5 KB "
+            "libm sin/cos table (L1-resident).",
     "raw": launches,
 }
 json.dump(doc, open(os.path.join(PROF, f"{tag}_step_tma_ncu.json"), "w"), indent=1)
-summary = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep],
-                         capture_output=True, text=True).stdout
-open(os.path.join(PROF, f"{tag}_step_tma_ncu_summary.txt"), "w").write(summary)
-print(summary)
+for name, out in (("prof_step_tma", "step_tma"), ("prof_actor_act", "actor_act"), ("prof_actor_loop", "actor_loop"),
+                  ("prof_rollout", "rollout")):
+    rep = os.path.join(OUT, name + ".ncu-rep")
+    if not os.path.exists(rep):
+        print("missing", rep)
+        continue
+    summary = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep],
+                             capture_output=True, text=True).stdout
+    open(os.path.join(PROF, f"{tag}_{out}_ncu_summary.txt"), "w").write(summary)
+    print(summary)
