@@ -202,7 +202,7 @@ __device__ __forceinline__ void bar_arrive(uint32_t bar)
  * takes microseconds) records who waited for what and raises g_fault[0]; every wait in every CTA then
  * falls through, so a protocol bug ends the launch with an error report (q1_policy_* return Q1_ECUDA
  * at their next call) instead of hanging the GPU. */
-constexpr uint32_t kWatchdogPolls = 1u << 22;
+constexpr uint32_t kWatchdogPolls = 1u << 26;
 __device__ unsigned int g_fault[8]; /* [0] raised, [1] tag of the first waiter that gave up, [2] sequence */
 
 __device__ __forceinline__ bool bar_test(uint32_t bar, uint32_t parity)

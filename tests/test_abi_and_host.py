@@ -71,6 +71,30 @@ def test_num_keys_and_null_arguments():
     assert lib.q1_destroy(None) == 0
 
 
+def test_new_entry_points_reject_bad_arguments_before_touching_a_device():
+    """Argument checks of the round-2 entry points (recorder, closed loop, tick counter, f64-velocity
+    phys.apply) run before any CUDA call: Q1_EINVAL with a message, never a crash."""
+    from q1physrl_b200 import _lib
+    lib = _lib.load()
+    src, view = _lib.Q1ActionSource(), _lib.Q1RecordView()
+    assert lib.q1_rollout_record(None, ctypes.byref(src), 1, 0, 0, ctypes.byref(view), None, None) == _lib.Q1_EINVAL
+    assert lib.q1_rollout_record_host(None, ctypes.byref(src), 1, 0, 0, ctypes.byref(view), None) == _lib.Q1_EINVAL
+    assert b"NULL" in lib.q1_last_error()
+    assert lib.q1_policy_rollout(None, None, 1, 1, 0, 0, -10.0, 10.0, 0, None, None, None, None) == _lib.Q1_EINVAL
+    assert lib.q1_policy_rollout_host(None, None, 1, 1, 0, 0, -10.0, 10.0, 0, ctypes.byref(view), None) == _lib.Q1_EINVAL
+    assert lib.q1_policy_check(None) == _lib.Q1_EINVAL and lib.q1_policy_destroy(None) == 0
+    assert lib.q1_advance_ticks(None, 1) == _lib.Q1_EINVAL
+    handle = ctypes.c_void_p()
+    w = np.zeros(4, np.float32)
+    p = ctypes.c_void_p(w.ctypes.data)
+    assert lib.q1_policy_create(0, 5, p, p, p, p, p, p, ctypes.byref(handle)) == _lib.Q1_EINVAL   # num_keys 3 or 4
+    assert lib.q1_policy_create(0, 4, None, p, p, p, p, p, ctypes.byref(handle)) == _lib.Q1_EINVAL
+    z = ctypes.c_void_p(np.zeros(3).ctypes.data)
+    assert lib.q1_phys_apply_vel64_host(0, -1, *([z] * 7), 0, *([z] * 8)) == _lib.Q1_EINVAL
+    assert lib.q1_phys_apply_vel64_host(0, 0, *([None] * 7), 0, *([None] * 8)) == 0                  # n = 0: nothing to do
+    assert lib.q1_phys_apply_vel64_host(0, 1, None, *([z] * 6), 0, *([z] * 8)) == _lib.Q1_EINVAL
+
+
 def test_config_matches_reference_dataclass():
     from q1physrl_b200 import env as benv
     c = benv.Config.get_default()
