@@ -91,12 +91,12 @@ enum : uint32_t { /* mbarriers, 8 bytes each.  A waiter tests a phase PARITY, so
     B_W = 0,        /* weights have landed in shared memory */
     B_X = 1,        /* [2] layer-1 operand of the tile written (env rows -> MMA) */
     B_L1 = 3,       /* layer-1 accumulator complete (MMA -> epilogue) */
-    B_H1 = 4,       /* [8] step h of part p (index 2p + h) of the layer-1 activations stored (epilogue -> MMA) */
-    B_L2 = 12,      /* [4] layer-2 accumulator, quarter q, complete */
-    B_H2 = 16,      /* [4] part q of the layer-2 activations stored */
-    B_D3 = 20,      /* logits complete (MMA -> env rows) */
-    B_E = 21,       /* logits read (env rows -> epilogue: R0 may take the next tile's activations) */
-    B_COUNT = 22
+    B_H1 = 4,       /* [2] step h of the layer-1 activations stored by all four parts (epilogue -> MMA) */
+    B_L2 = 6,       /* [4] layer-2 accumulator, quarter q, complete */
+    B_H2 = 10,      /* [4] quarter q of the layer-2 activations stored */
+    B_D3 = 14,      /* logits complete (MMA -> env rows) */
+    B_E = 15,       /* logits read (env rows -> epilogue: R0 may take the next tile's activations) */
+    B_COUNT = 16
 };
 constexpr uint32_t SM_X = (SM_WEIGHTS_END + 1023) & ~1023u;     /* two layer-1 operands: 128 rows x 128 B (K = 32 used) */
 constexpr uint32_t SM_BAR = SM_X + 2 * kRows * 128;
@@ -509,10 +509,10 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         bar_init(bar(B_L1), 1);
         bar_init(bar(B_D3), 1);
         bar_init(bar(B_E), kRows);
-        for (int b = 0; b < 8; b++)
-            bar_init(bar(B_H1 + b), kPartThreads);
+        for (int b = 0; b < 2; b++)
+            bar_init(bar(B_H1 + b), 4 * kPartThreads);
         for (int b = 0; b < 4; b++) {
-            bar_init(bar(B_H2 + b), kPartThreads);
+            bar_init(bar(B_H2 + b), b == 3 ? 2 * kPartThreads : kPartThreads); /* quarter 3 is shared by two parts */
             bar_init(bar(B_L2 + b), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -582,16 +582,18 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                             desc_at(dB2, (ks >> 2) * (kHidden * 128u) + q * (64u * 128u) + (ks & 3u) * 32u),
                             instr_desc(64), accumulate);
             };
-            /* quarter 0 trails the layer-1 epilogue: the parts publish their first steps together, then
-             * their second steps -- take them in that order (K-steps may accumulate in any order) */
+            /* quarter 0 trails the layer-1 epilogue: the four parts publish their first steps together, then
+             * their second steps -- eight K-steps each time (K-steps may accumulate in any order) */
 #pragma unroll
-            for (uint32_t i = 0; i < 8; i++) {
-                const uint32_t p = i & 3u, h = i >> 2;
-                bar_wait_warp(bar(B_H1 + 2u * p + h), ph, 4096u + B_H1 * 128u + (i << 4), s);
+            for (uint32_t h = 0; h < 2; h++) {
+                bar_wait_warp(bar(B_H1 + h), ph, 4096u + B_H1 * 128u + (h << 4), s);
                 tc_fence_after();
-                layer2_kstep(0, 4u * p + 2u * h, i > 0);
-                layer2_kstep(0, 4u * p + 2u * h + 1u, true);
-                TRACE(s, 3 + i);
+#pragma unroll
+                for (uint32_t p = 0; p < 4; p++) {
+                    layer2_kstep(0, 4u * p + 2u * h, h + p > 0);
+                    layer2_kstep(0, 4u * p + 2u * h + 1u, true);
+                }
+                TRACE(s, 3 + h);
             }
             mma_commit(leader, bar(B_L2 + 0));
             /* quarters 1-3, back to back (R1 takes 2 and 3: every lane has consumed its layer-1 columns) */
@@ -625,7 +627,6 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         const uint32_t quad = warp & 3u, part = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column part */
         const uint32_t lane_base = tmem + ((quad * 32u) << 16);
         bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u, 0);
-        const float *bias2 = reinterpret_cast<const float *>(smem + SM_BIAS2) + 64u * part;
         for (int64_t s = 0; s < S; s++) {
             const uint32_t ph = (uint32_t)s & 1u;
             uint32_t va[32], vb[32], p[16];
@@ -647,7 +648,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             tmem_ld_wait<32>(vb);
             tmem_st_wait();
             tc_fence_before();
-            bar_arrive(bar(B_H1 + 2u * part));
+            bar_arrive(bar(B_H1 + 0));
             if (quad == 0) TRACE(s, 20 + 8 * part + 2);
 #pragma unroll
             for (uint32_t e = 0; e < 16; e++)
@@ -655,31 +656,47 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             tmem_st<16>(lane_base + TM_H1 + 32u * part + 16u, p);
             tmem_st_wait();
             tc_fence_before();
-            bar_arrive(bar(B_H1 + 2u * part + 1u));
+            bar_arrive(bar(B_H1 + 1));
             if (quad == 0) TRACE(s, 20 + 8 * part + 3);
-            /* ---- layer-2 epilogue, quarter `part`: accumulator + bias -> tanh -> H2 (R2: this lane is done
-             * with the layer-1 columns that were there) ---- */
-            bar_wait_warp(bar(B_L2 + part), ph, 8192u + B_L2 * 128u + (part << 4), s);
-            tc_fence_after();
-            if (quad == 0) TRACE(s, 20 + 8 * part + 4);
-            tmem_ld_issue<32>(lane_base + tm_l2(part), va);
-            tmem_ld_wait<32>(va);
-            tmem_ld_issue<32>(lane_base + tm_l2(part) + 32u, vb);
+            /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (R2: this lane is done with the layer-1
+             * columns that were there).  Parts 0-2 take quarters 0-2 as they complete; quarter 3, which
+             * completes last, is shared: part 3 takes its first 32 columns, part 0 -- long done with quarter 0
+             * by then -- its second 32, so the tile does not end on one warp per scheduler working alone ---- */
+            auto half_quarter = [&](uint32_t q, uint32_t hh, const uint32_t *v) {  /* 32 columns -> 16 of H2 */
+                const float *b = reinterpret_cast<const float *>(smem + SM_BIAS2) + 64u * q + 32u * hh;
 #pragma unroll
-            for (uint32_t e = 0; e < 16; e++)
-                p[e] = tanh2_bf16(__uint_as_float(va[2 * e]) + bias2[2u * e],
-                                  __uint_as_float(va[2 * e + 1]) + bias2[2u * e + 1u]);
-            tmem_st<16>(lane_base + TM_H2 + 32u * part, p);
-            tmem_ld_wait<32>(vb);
-#pragma unroll
-            for (uint32_t e = 0; e < 16; e++)
-                p[e] = tanh2_bf16(__uint_as_float(vb[2 * e]) + bias2[32u + 2u * e],
-                                  __uint_as_float(vb[2 * e + 1]) + bias2[32u + 2u * e + 1u]);
-            tmem_st<16>(lane_base + TM_H2 + 32u * part + 16u, p);
-            tmem_st_wait();
-            tc_fence_before();
-            bar_arrive(bar(B_H2 + part));
-            if (quad == 0) TRACE(s, 20 + 8 * part + 5);
+                for (uint32_t e = 0; e < 16; e++)
+                    p[e] = tanh2_bf16(__uint_as_float(v[2 * e]) + b[2u * e], __uint_as_float(v[2 * e + 1]) + b[2u * e + 1u]);
+                tmem_st<16>(lane_base + TM_H2 + 32u * q + 16u * hh, p);
+            };
+            if (part < 3) {
+                bar_wait_warp(bar(B_L2 + part), ph, 8192u + B_L2 * 128u + (part << 4), s);
+                tc_fence_after();
+                if (quad == 0) TRACE(s, 20 + 8 * part + 4);
+                tmem_ld_issue<32>(lane_base + tm_l2(part), va);
+                tmem_ld_wait<32>(va);
+                tmem_ld_issue<32>(lane_base + tm_l2(part) + 32u, vb);
+                half_quarter(part, 0, va);
+                tmem_ld_wait<32>(vb);
+                half_quarter(part, 1, vb);
+                tmem_st_wait();
+                tc_fence_before();
+                bar_arrive(bar(B_H2 + part));
+                if (quad == 0) TRACE(s, 20 + 8 * part + 5);
+            }
+            if (part == 3 || part == 0) {
+                const uint32_t hh = part == 3 ? 0u : 1u;
+                bar_wait_warp(bar(B_L2 + 3), ph, 8192u + B_L2 * 128u + (3u << 4), s);
+                tc_fence_after();
+                if (quad == 0 && part == 3) TRACE(s, 20 + 8 * part + 4);
+                tmem_ld_issue<32>(lane_base + tm_l2(3) + 32u * hh, va);
+                tmem_ld_wait<32>(va);
+                half_quarter(3, hh, va);
+                tmem_st_wait();
+                tc_fence_before();
+                bar_arrive(bar(B_H2 + 3));
+                if (quad == 0 && part == 3) TRACE(s, 20 + 8 * part + 5);
+            }
         }
     } else {
         /* ================================================================ env rows =============== */

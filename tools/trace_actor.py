@@ -24,7 +24,7 @@ assert lib.q1_actor_trace(ctypes.c_void_p(t.ctypes.data)) == 0
 names = {0: "mma:top", 1: "mma:X", 2: "mma:L1 issued", 11: "", 12: "mma:L2q1 issued", 13: "mma:L2q2", 14: "mma:L2q3",
          15: "mma:M3q0", 16: "mma:M3q1", 17: "mma:M3q2", 18: "mma:M3q3", 52: "env:top", 53: "env:D3", 54: "env:E arrived",
          55: "env:acted", 56: "env:prepared"}
-for i in range(8):
+for i in range(2):
     names[3 + i] = f"mma:L2q0 step{i}"
 for p in range(4):
     for k, nm in enumerate(("top", "L1 seen", "H1 step0", "H1 step1", "L2 seen", "H2 done")):
