@@ -106,9 +106,9 @@ class EvalSimResult:
 
     @property
     def hypothetical_delta_speeds(self):
-        """Hypothetical speed increases for this run, were a given action taken: shape (360,
-        num_frames), first axis = wish angle - move angle from -180 to 179 degrees
-        (analyse.py:92-118)."""
+        """(360, frames) float32: the ground-speed change each frame would have seen had the wish
+        direction been `move_angle + d` for d = -180 .. 179 degrees (forward key only, the recorded jump
+        button) -- the array behind analyse.py:92-118, from one `k_delta_speed_sweep` launch."""
         return self.delta_speeds(np.arange(-180, 180))
 
 

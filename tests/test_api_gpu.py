@@ -195,7 +195,10 @@ def test_fused_tcgen05_policy_kernel():
         assert b.shape == a.shape
         print(f"logit error vs fp32: max {np.abs(a - b).max():.4f}, mean {np.abs(a - b).mean():.5f} "
               f"(|logit| up to {np.abs(a).max():.1f})")
-        assert np.abs(a - b).max() < 0.15 and np.abs(a - b).mean() < 0.02, (np.abs(a - b).max(),)
+        # budget: weights and both hidden activations are bf16 (2^-9 relative each); through two 256-wide
+        # layers that is ~0.01 rms on logits of magnitude up to 49 and, measured, 0.044 / 0.067 at the worst
+        # element of the two batches.  Bound: 0.1 absolute, 0.02 mean.
+        assert np.abs(a - b).max() < 0.1 and np.abs(a - b).mean() < 0.02, (np.abs(a - b).max(),)
         ka, ma = ref.act(o, deterministic=True)
         kb, mb = fused.act(o, deterministic=True)
         ka, kb = ka.cpu().numpy(), kb.cpu().numpy()
