@@ -251,17 +251,77 @@ __device__ __forceinline__ __attribute__((unused)) uint32_t pack_bf16(float lo, 
     return *reinterpret_cast<uint32_t *>(&v);
 }
 /* tanh of two pre-activations -> packed bf16x2 (what the next layer's A operand holds).  The special-
- * function unit is what bounds the epilogues (tanh.approx.f32 issues at half the MUFU rate: 8 per clock
- * per SM, 65 536 of them per tile), so the default spends ONE MUFU instruction on the pair:
- *   Q1_POLICY_TANH 1 (default)  tanh.approx.f16x2: inputs rounded to f16 (11 significant bits; |x| here
- *                               is < 100), result error 2^-10.99 -- both below the bf16 rounding of the
- *                               stored activation (2^-9), so the logits move by less than that rounding
- *                               already moves them (tests/test_api_gpu.py states and checks the bound)
- *   Q1_POLICY_TANH 0            tanh.approx.f32 per element (relative error 2^-11), two MUFU per pair
- *   Q1_POLICY_TANH 2            tanh.approx.bf16x2: inputs rounded to bf16 first, ~3x the logit error */
+ * function unit is what bounds the epilogues: MUFU.TANH retires 4 lanes per clock per scheduler (a warp
+ * instruction every 8 cycles, measured), and a tile needs 65 536 of them = 4096 cycles per SM against
+ * ~2300 for its MMAs.
+ *   Q1_POLICY_TANH 0 (default)  tanh.approx.f32 per element (relative error 2^-11), two MUFU per pair
+ *   Q1_POLICY_TANH 1            tanh.approx.f16x2: ptxas splits it into two MUFU.TANH.F16 plus conversions
+ *                               (no faster, measured)
+ *   Q1_POLICY_TANH 2            tanh.approx.bf16x2: inputs rounded to bf16 first, ~3x the logit error
+ * So the XU is relieved the other way round: Q1_POLICY_POLY_PAIRS of every 16 column pairs do not go to it
+ * at all but through tanh2_poly_bf16 below on the FMA pipe, which the epilogue otherwise leaves idle. */
 #ifndef Q1_POLICY_TANH
 #define Q1_POLICY_TANH 0
 #endif
+/* Measured on one box, per 2^20 envs of k_actor<ACT> / per tick of the closed loop at 32 768 envs:
+ *   pairs    0      2      3      4      5      6      8
+ *   ACT    209.0  193.1  191.9  190.4  196.2  197.1  217 us
+ *   LOOP    9.19   9.16   9.32   9.51   9.77   9.96        us     (the env rows' tick keeps the FMA / FP64
+ * pipes busy there).  ONE value for both, because the closed loop is tested bit-identical to per-tick
+ * q1_policy_act + q1_step: 2. */
+#ifndef Q1_POLICY_POLY_PAIRS
+#define Q1_POLICY_POLY_PAIRS 2
+#endif
+/* tanh(x) ~ x P(x^2) on |x| <= 3.5, x clamped to that range first (beyond it tanh rounds to +-1 in bf16, and
+ * so does this).  tools/make_tanh_poly.py: degree 17, minimax relative error 5.4e-4 (5.8e-4 evaluated in
+ * float32) -- the size of MUFU.TANH's own 2^-11 and a quarter of the bf16 rounding of the stored activation;
+ * 96 % of the results equal bf16(tanh x), the rest are the neighbouring bf16.  Evaluated on both elements
+ * of the pair at once with the packed float32 instructions of sm_100 (FMUL2 / FFMA2, coefficients as
+ * immediates): 4 FMNMX + 10 packed instructions per pair.  A NaN input clamps to +-3.5 (MUFU would return
+ * NaN); q1_policy_check rejects non-finite weights and the observations of a finite state are finite. */
+constexpr float kTanhClamp = 3.5f;
+#define Q1_TANH_POLY(X) /* constant term first */                                                            \
+    X(0.9994622468948364f) X(-0.32549557089805603f) X(0.1126757487654686f) X(-0.0303287822753191f)            \
+    X(0.005662580020725727f) X(-0.0006888179923407733f) X(5.15220635861624e-05f) X(-2.1402802303782664e-06f)  \
+    X(3.7685438769585744e-08f)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t tanh2_poly_bf16(float lo, float hi)
+{
+    lo = fminf(fmaxf(lo, -kTanhClamp), kTanhClamp);
+    hi = fminf(fmaxf(hi, -kTanhClamp), kTanhClamp);
+    const uint64_t x = pack_f32x2(lo, hi), t = mul_f32x2(x, x);
+#define X(c) c,
+    const float coef[9] = {Q1_TANH_POLY(X)};
+#undef X
+    uint64_t p = pack_f32x2(coef[8], coef[8]);
+#pragma unroll
+    for (int j = 7; j >= 0; j--)
+        p = fma_f32x2(p, t, pack_f32x2(coef[j], coef[j]));
+    p = mul_f32x2(p, x);
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p));
+    return pack_bf16(a, b);
+}
+/* column pair e of a 32-column step: on the FMA pipe or the XU?  (spread evenly over the 16 pairs) */
+template <uint32_t PAIRS>
+__host__ __device__ constexpr bool pair_uses_poly(uint32_t e) { return (e * PAIRS) % 16u < PAIRS; }
 __device__ __forceinline__ uint32_t tanh2_bf16(float lo, float hi)
 {
 #if Q1_POLICY_TANH == 1
@@ -287,6 +347,11 @@ __device__ __forceinline__ uint32_t tanh2_bf16(float lo, float hi)
     asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(hi));
     return pack_bf16(a, b);
 #endif
+}
+template <uint32_t PAIRS>
+__device__ __forceinline__ uint32_t tanh2_pair(uint32_t e, float lo, float hi)
+{
+    return pair_uses_poly<PAIRS>(e) ? tanh2_poly_bf16(lo, hi) : tanh2_bf16(lo, hi);
 }
 /* consecutive 32-bit columns of this thread's TMEM lane */
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t v[8])
@@ -428,12 +493,24 @@ __device__ __forceinline__ void layer1_operand(const float o[kObs], uint32_t col
 #define Q1_ACTOR_TRACE 0
 #endif
 #if Q1_ACTOR_TRACE
+#ifndef Q1_ACTOR_TRACE_BASE
+#define Q1_ACTOR_TRACE_BASE 0 /* first of the 16 sequences recorded */
+#endif
+#ifndef Q1_ACTOR_TRACE_BLOCK
+#define Q1_ACTOR_TRACE_BLOCK 0
+#endif
 __device__ long long g_trace[16][64];
-#define TRACE(seq, ev)                                                              \
-    do {                                                                            \
-        if (blockIdx.x == 0 && (seq) < 16 && (threadIdx.x & 31u) == 0)              \
-            g_trace[(seq)][(ev)] = clock64();                                       \
+__device__ long long g_block_cycles[256];   /* (entry -> exit cycles) << 8 | SM id, per CTA */
+#if Q1_ACTOR_TRACE == 2 /* only the entry / exit stamps: the code between them is the shipped build's */
+#define TRACE(seq, ev) do { } while (0)
+#else
+#define TRACE(seq, ev)                                                                                     \
+    do {                                                                                                   \
+        if (blockIdx.x == Q1_ACTOR_TRACE_BLOCK && (seq) >= Q1_ACTOR_TRACE_BASE &&                         \
+            (seq) < Q1_ACTOR_TRACE_BASE + 16 && (threadIdx.x & 31u) == 0)                                 \
+            g_trace[(seq) - Q1_ACTOR_TRACE_BASE][(ev)] = clock64();                                       \
     } while (0)
+#endif
 #else
 #define TRACE(seq, ev) do { } while (0)
 #endif
@@ -492,6 +569,15 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t s0 = saddr_of(smem);
     auto bar = [&](uint32_t b) { return s0 + SM_BAR + 8u * b; };
+#if Q1_ACTOR_TRACE
+    const long long trace_entry = clock64();
+    if (blockIdx.x == Q1_ACTOR_TRACE_BLOCK && tid == 0) {
+        g_trace[0][62] = trace_entry;    /* kernel entry (event 63: exit) */
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        g_trace[0][60] = (long long)ns;  /* the same two moments in nanoseconds: 60, 61 */
+    }
+#endif
 
     /* this CTA's work: LOOP: tiles tile_begin + blockIdx.x + j * gridDim.x (j < k), each for `ticks`
      * ticks, visited round-robin; ACT: the same tile walk, each tile once */
@@ -582,28 +668,26 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                             desc_at(dB2, (ks >> 2) * (kHidden * 128u) + q * (64u * 128u) + (ks & 3u) * 32u),
                             instr_desc(64), accumulate);
             };
-            /* quarter 0 trails the layer-1 epilogue: the four parts publish their first steps together, then
-             * their second steps -- eight K-steps each time (K-steps may accumulate in any order) */
+            /* Layer 2 trails the layer-1 epilogue, which publishes the activations in two halves of 128
+             * columns (= 8 K-steps each; K-steps may accumulate in any order).  The first half is everything R1
+             * held, so R1 may take quarters 2 and 3 at once: the first K-half of ALL four quarters runs on the
+             * tensor pipe while the second half of the tanh runs on the XU, and after the second publication
+             * quarter q is complete after q + 1 half-quarters instead of q + 1 whole ones. */
 #pragma unroll
             for (uint32_t h = 0; h < 2; h++) {
                 bar_wait_warp(bar(B_H1 + h), ph, 4096u + B_H1 * 128u + (h << 4), s);
                 tc_fence_after();
-#pragma unroll
-                for (uint32_t p = 0; p < 4; p++) {
-                    layer2_kstep(0, 4u * p + 2u * h, h + p > 0);
-                    layer2_kstep(0, 4u * p + 2u * h + 1u, true);
-                }
                 TRACE(s, 3 + h);
-            }
-            mma_commit(leader, bar(B_L2 + 0));
-            /* quarters 1-3, back to back (R1 takes 2 and 3: every lane has consumed its layer-1 columns) */
 #pragma unroll
-            for (uint32_t q = 1; q < 4; q++) {
+                for (uint32_t q = 0; q < 4; q++) {
 #pragma unroll
-                for (uint32_t ks = 0; ks < 16; ks++)
-                    layer2_kstep(q, ks, ks > 0);
-                mma_commit(leader, bar(B_L2 + q));
-                TRACE(s, 11 + q);
+                    for (uint32_t j = 0; j < 8; j++)
+                        layer2_kstep(q, 8u * h + j, h + j > 0);
+                    if (h == 1) {
+                        mma_commit(leader, bar(B_L2 + q));
+                        TRACE(s, 11 + q);
+                    }
+                }
             }
             /* layer 3: D3 (128 x 16, over the first columns of H1, which the MMAs above are the last to
              * read) += H2[:, 64q .. 64q+63] . W3 (padded), trailing the layer-2 epilogue part by part */
@@ -629,8 +713,9 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u, 0);
         for (int64_t s = 0; s < S; s++) {
             const uint32_t ph = (uint32_t)s & 1u;
+            constexpr uint32_t kPoly = Q1_POLICY_POLY_PAIRS;
             uint32_t va[32], vb[32], p[16];
-            /* ---- layer-1 epilogue, columns 64 part .. +63 (bias already in the MMA) -> tanh -> H1 ---- */
+            /* ---- layer-1 epilogue (bias already in the MMA) -> tanh -> H1 ---- */
             if (s >= 1) /* the first columns of R0 hold the previous tile's logits until the env rows have
                            read them (they do so the moment the logits are complete) */
                 bar_wait_warp(bar(B_E), ph ^ 1u, 8192u + B_E * 128u, s);
@@ -638,26 +723,23 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             bar_wait_warp(bar(B_L1), ph, 8192u + B_L1 * 128u, s);
             tc_fence_after();
             if (quad == 0) TRACE(s, 20 + 8 * part + 1);
-            tmem_ld_issue<32>(lane_base + TM_L1 + 64u * part, va);
-            tmem_ld_wait<32>(va);
-            tmem_ld_issue<32>(lane_base + TM_L1 + 64u * part + 32u, vb);       /* in flight under the tanh below */
+            /* Half h: this part's 32 of the accumulator columns 128 h .. 128 h + 127 (R1, then R2).  A loop that
+             * is NOT unrolled: unrolled, ptxas interleaves the arithmetic of the two halves for latency and the
+             * first publication -- which the layer-2 MMAs are waiting for -- sinks to the end (seen in the SASS
+             * as soon as the halves contain dependent FFMA2 chains). */
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; h++) {
+                tmem_ld_issue<32>(lane_base + TM_L1 + 128u * h + 32u * part, va);
+                tmem_ld_wait<32>(va);
 #pragma unroll
-            for (uint32_t e = 0; e < 16; e++)
-                p[e] = tanh2_bf16(__uint_as_float(va[2 * e]), __uint_as_float(va[2 * e + 1]));
-            tmem_st<16>(lane_base + TM_H1 + 32u * part, p);
-            tmem_ld_wait<32>(vb);
-            tmem_st_wait();
-            tc_fence_before();
-            bar_arrive(bar(B_H1 + 0));
-            if (quad == 0) TRACE(s, 20 + 8 * part + 2);
-#pragma unroll
-            for (uint32_t e = 0; e < 16; e++)
-                p[e] = tanh2_bf16(__uint_as_float(vb[2 * e]), __uint_as_float(vb[2 * e + 1]));
-            tmem_st<16>(lane_base + TM_H1 + 32u * part + 16u, p);
-            tmem_st_wait();
-            tc_fence_before();
-            bar_arrive(bar(B_H1 + 1));
-            if (quad == 0) TRACE(s, 20 + 8 * part + 3);
+                for (uint32_t e = 0; e < 16; e++)
+                    p[e] = tanh2_pair<kPoly>(e, __uint_as_float(va[2 * e]), __uint_as_float(va[2 * e + 1]));
+                tmem_st<16>(lane_base + TM_H1 + 64u * h + 16u * part, p);
+                tmem_st_wait();
+                tc_fence_before();
+                bar_arrive(bar(B_H1 + h));
+                if (quad == 0) TRACE(s, 20 + 8 * part + 2 + h);
+            }
             /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (R2: this lane is done with the layer-1
              * columns that were there).  Parts 0-2 take quarters 0-2 as they complete; quarter 3, which
              * completes last, is shared: part 3 takes its first 32 columns, part 0 -- long done with quarter 0
@@ -666,7 +748,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 const float *b = reinterpret_cast<const float *>(smem + SM_BIAS2) + 64u * q + 32u * hh;
 #pragma unroll
                 for (uint32_t e = 0; e < 16; e++)
-                    p[e] = tanh2_bf16(__uint_as_float(v[2 * e]) + b[2u * e], __uint_as_float(v[2 * e + 1]) + b[2u * e + 1u]);
+                    p[e] = tanh2_pair<kPoly>(e, __uint_as_float(v[2 * e]) + b[2u * e], __uint_as_float(v[2 * e + 1]) + b[2u * e + 1u]);
                 tmem_st<16>(lane_base + TM_H2 + 32u * q + 16u * hh, p);
             };
             if (part < 3) {
@@ -874,6 +956,19 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
     }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+#if Q1_ACTOR_TRACE
+    if (blockIdx.x == Q1_ACTOR_TRACE_BLOCK && tid == 0) {
+        g_trace[0][63] = clock64();
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        g_trace[0][61] = (long long)ns;
+    }
+    if (tid == 0 && blockIdx.x < 256) {
+        unsigned smid;
+        asm("mov.u32 %0, %smid;" : "=r"(smid));
+        g_block_cycles[blockIdx.x] = ((clock64() - trace_entry) << 8) | (long long)(smid & 255u);
+    }
+#endif
 }
 
 uint16_t to_bf16(float f)
@@ -1022,6 +1117,10 @@ int q1_policy_create(int device, int num_keys, const float *w1, const float *b1,
 int q1_actor_trace(long long *out) /* 16 x 64 stamps of CTA 0 */
 {
     return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -1;
+}
+int q1_actor_block_cycles(long long *out) /* 256 entries, see g_block_cycles */
+{
+    return cudaMemcpyFromSymbol(out, g_block_cycles, sizeof(long long) * 256) == cudaSuccess ? 0 : -1;
 }
 #endif
 
