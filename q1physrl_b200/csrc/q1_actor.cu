@@ -12,28 +12,32 @@
  * q1physrl/action_dist.py:84-101, 186-243, q1physrl_env/env.py:482-510.
  *
  * All three layers run on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators
- * in tensor memory); activations never leave tensor memory.  21 warps, three roles, synchronised by
- * mbarriers only:
+ * in tensor memory); activations never leave tensor memory.  28 warps in seven warpgroups, three roles,
+ * synchronised by mbarriers only:
  *
- *   warps 0-3    ENV   one thread per env row: builds the layer-1 operand from the observation, reads
- *                      the logits, samples the action and (LOOP) runs the env tick for its env
- *   warps 4-19   EPI   tanh epilogues: tcgen05.ld accumulator columns -> (+ bias) -> tanh -> bf16 ->
+ *   warps 0-7    ENV   two groups of four; a thread per env row: builds the layer-1 operand from the
+ *                      observation, reads the logits, samples the action and (LOOP) runs the env tick for
+ *                      its env.  The groups take alternate sequences (see the role's comment)
+ *   warps 8-23   EPI   tanh epilogues: tcgen05.ld accumulator columns -> (+ bias) -> tanh -> bf16 ->
  *                      tcgen05.st as the next layer's A operand; thread = (row, column part)
- *   warp 20      MMA   one lane issues every tcgen05.mma and tcgen05.commit
+ *   warp 24      MMA   issues every tcgen05.mma and tcgen05.commit (warps 25-27 only complete its
+ *                      warpgroup: registers move between whole warpgroups, setmaxnreg)
  *
- * The tanh epilogues, not the MMAs, bound the policy (65 536 MUFU.TANH per tile = 4096 cycles; the MMAs
- * of a tile are ~2600), and every publish of epilogue output to the MMA warp (tcgen05.wait::st, fence,
- * mbarrier arrive, the MMA warp's wake-up) costs a few hundred cycles whatever it publishes.  So the
- * protocol gives every epilogue warp a CONTIGUOUS quarter of the columns and few, large steps:
- *   layer 1   both K-steps are issued at once into a 256-column accumulator.  Epilogue part p (4 warps)
- *             turns columns 64p .. 64p+63 into activations in two steps of 32, all four parts at once
- *   layer 2   runs as four N = 64 quarters.  Quarter 0 trails the layer-1 epilogue (two K-steps per
- *             published step, in whatever order the parts publish) into its own accumulator; quarters
- *             1-3 are issued back to back when the layer-1 epilogue is done.  Epilogue part q takes quarter
- *             q: the parts start one after the other as their quarter completes, so the epilogue of
- *             quarter q runs while quarter q + 1 is still in the tensor pipe
- *   layer 3   K-steps trail the layer-2 epilogue part by part; the logits land in the (dead) first
- *             columns of the layer-1 activations
+ * The tanh epilogues, not the MMAs, bound the policy (65 536 tanh per tile: 4096 cycles of the XU if all
+ * went through MUFU.TANH; the MMAs of a tile are ~2600 cycles), and every publish of epilogue output to the
+ * MMA warp (tcgen05.wait::st, fence, mbarrier arrive, the MMA warp's wake-up) costs a few hundred cycles
+ * whatever it publishes.  So: few, large steps, and the XU never waits for the tensor pipe:
+ *   layer 1   two N = 128 halves, both K-steps each.  Its epilogue runs in two halves of 128 columns, all
+ *             four parts at once (part p: 32 columns of each half)
+ *   layer 2   four N = 64 quarters.  The first K-half of all four is issued when the first half of the
+ *             layer-1 activations is published and runs under the second half of that epilogue; the second
+ *             K-halves follow quarter by quarter, and epilogue part q starts on quarter q as it completes
+ *             (quarter 3 is shared between parts 3 and 0)
+ *   layer 3   K-steps trail the layer-2 epilogue part by part; the logits land over quarter 3's first
+ *             accumulator columns
+ *   next tile (open policy step) its layer 1 is issued as soon as parts 0 and 1 have their accumulators in
+ *             registers, into the regions this tile no longer needs, so the epilogue warps go from this
+ *             tile's layer 2 straight into the next tile's layer 1
  * With two or more tiles per CTA the env tick of one tile runs under the policy phase of the next.
  *
  * Layer 1 on the tensor cores without bf16-quantising the observation (yaw / 90 would lose 3 degrees):
@@ -42,12 +46,14 @@
  * two carry 1 x (b_hi, b_lo): the bias comes out of the MMA too.  Relative error ~2^-17 of |x w|.  That
  * operand is written by the env warps into shared memory (K-major, 128-byte swizzle, like the weights).
  *
- * Tensor memory (512 columns = four regions of 128):
- *   R0 [0,128)    H1: layer-1 activations, A operand of layer 2; afterwards its first 16 columns take
- *                 the logits (layer 3's accumulator)
- *   R1 [128,256)  layer-1 accumulator, columns 0..127; then layer-2 accumulators, quarters 2 and 3
- *   R2 [256,384)  layer-1 accumulator, columns 128..255; then H2: layer-2 activations, A operand of layer 3
- *   R3 [384,512)  layer-2 accumulators, quarters 0 and 1
+ * Tensor memory (512 columns = four regions of 128), for an even sequence; an odd one uses the regions
+ * rotated (A <-> C, B <-> D: tm_a .. tm_d below), which is what lets two consecutive tiles overlap:
+ *   A [128,256)  layer-1 accumulator, columns 0..127; then layer-2 accumulators, quarters 2 and 3; then the
+ *                logits over quarter 3's first 16 columns.  The NEXT tile's H1
+ *   B [256,384)  layer-1 accumulator, columns 128..255; then H2: layer-2 activations, A operand of layer 3.
+ *                The next tile's quarters 0 and 1
+ *   C [0,128)    H1: layer-1 activations, A operand of layer 2.  The next tile's region A
+ *   D [384,512)  layer-2 accumulators, quarters 0 and 1.  The next tile's region B
  * A thread only ever touches its own lane (= env row), so within a lane program order is enough; the
  * barriers order lanes against the MMAs, and the MMAs of one issuing thread execute in issue order.
  */
@@ -71,9 +77,10 @@ constexpr int kHidden = 256; /* hidden width = K of layers 2 and 3, N of layers 
 constexpr int kOutPad = 16;  /* layer-3 N, zero-padded from 2 * num_keys + 2 = 8 or 10 */
 constexpr int kObs = 6;
 constexpr int kEpiParts = 4;  /* epilogue warps = 4 lane quadrants x 4 column parts (one warp of each part per scheduler) */
-constexpr int kEnvWarps = 4, kEpiWarps = 4 * kEpiParts, kMmaWarp = kEnvWarps + kEpiWarps;
+constexpr int kEnvWarps = 8; /* two groups of four (a group = the 128 rows of a tile), taking alternate sequences */
+constexpr int kEpiWarps = 4 * kEpiParts, kMmaWarp = kEnvWarps + kEpiWarps;
 constexpr int kPartThreads = 128; /* threads of one epilogue part */
-constexpr int kThreads = 32 * (kMmaWarp + 1);
+constexpr int kThreads = 32 * (kMmaWarp + 4); /* the MMA warp brings its warpgroup: registers move between whole warpgroups */
 constexpr int kMaxTiles = 3; /* tiles of env state a CTA keeps in shared memory (LOOP) */
 
 /* shared-memory image; every UMMA operand block is 1024-byte aligned (128-byte swizzle atoms) */
@@ -94,9 +101,13 @@ enum : uint32_t { /* mbarriers, 8 bytes each.  A waiter tests a phase PARITY, so
     B_H1 = 4,       /* [2] step h of the layer-1 activations stored by all four parts (epilogue -> MMA) */
     B_L2 = 6,       /* [4] layer-2 accumulator, quarter q, complete */
     B_H2 = 10,      /* [4] quarter q of the layer-2 activations stored */
-    B_D3 = 14,      /* logits complete (MMA -> env rows) */
-    B_E = 15,       /* logits read (env rows -> epilogue: R0 may take the next tile's activations) */
-    B_COUNT = 16
+    B_D3 = 14,      /* [2] logits of an even / odd sequence complete (MMA -> that sequence's env rows; one barrier
+                       per parity because an env group that takes every other sequence waits on every other phase) */
+    B_E = 16,       /* logits read (env rows -> epilogue: the next tile's activations may overwrite them) */
+    B_R01 = 17,     /* layer-2 accumulators, quarters 0 and 1, are in registers (epilogue parts 0, 1 -> MMA:
+                       region D may take the next tile's layer 1) */
+    B_R3 = 18,      /* quarter 3's first columns are in registers (part 3 -> MMA: the logits may go there) */
+    B_COUNT = 19
 };
 constexpr uint32_t SM_X = (SM_WEIGHTS_END + 1023) & ~1023u;     /* two layer-1 operands: 128 rows x 128 B (K = 32 used) */
 constexpr uint32_t SM_BAR = SM_X + 2 * kRows * 128;
@@ -109,9 +120,15 @@ constexpr uint32_t SM_TOTAL_ACT = SM_STATE;
 constexpr uint32_t SM_TOTAL_LOOP = SM_STATE + kMaxTiles * kSlotBytes;
 static_assert(SM_TOTAL_LOOP <= 232448, "one CTA per SM: at most 227 KB of shared memory");
 
-/* tensor-memory columns (32-bit), see the map above */
-constexpr uint32_t TM_H1 = 0, TM_D3 = 0, TM_L1 = 128, TM_H2 = 256;
-__host__ __device__ constexpr uint32_t tm_l2(uint32_t q) { return q < 2 ? 384u + 64u * q : 128u + 64u * (q - 2u); }
+/* tensor-memory columns (32-bit) of the tile of parity a = sequence & 1, see the map above */
+__host__ __device__ constexpr uint32_t tm_a(uint32_t a) { return a ? 0u : 128u; }   /* L1 cols 0..127; then L2 quarters 2, 3 */
+__host__ __device__ constexpr uint32_t tm_b(uint32_t a) { return a ? 384u : 256u; } /* L1 cols 128..255; then H2 */
+__host__ __device__ constexpr uint32_t tm_c(uint32_t a) { return a ? 128u : 0u; }   /* H1 */
+__host__ __device__ constexpr uint32_t tm_d(uint32_t a) { return a ? 256u : 384u; } /* L2 quarters 0, 1 */
+__host__ __device__ constexpr uint32_t tm_l2(uint32_t a, uint32_t q) { return q < 2 ? tm_d(a) + 64u * q : tm_a(a) + 64u * (q - 2u); }
+__host__ __device__ constexpr uint32_t tm_d3(uint32_t a) { return tm_a(a) + 64u; }  /* logits: over quarter 3's first columns */
+static_assert(tm_a(1) == tm_c(0) && tm_b(1) == tm_d(0) && tm_c(1) == tm_a(0) && tm_d(1) == tm_b(0),
+              "the next tile's regions are this tile's, rotated");
 
 /* instruction descriptor of tcgen05.mma kind::f16: D = f32, A = B = bf16, both K-major, M = 128 */
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t n)
@@ -561,6 +578,19 @@ __device__ __forceinline__ void slot_store(unsigned char *blk, int l, const Env 
     reinterpret_cast<double *>(blk + kTileTrem)[l] = e.trem;
 }
 
+/* 28 warps (the SM hands registers out per four warps) start with 72 registers each = 64 512 of the 65 536.
+ * The MMA warpgroup -- one working warp -- gives all but 24 back, which is exactly what lets the six env and
+ * epilogue warpgroups grow to the 80 they need (32 + 32 accumulator columns in flight + 16 packed results). */
+template <uint32_t N>
+__device__ __forceinline__ void warpgroup_reg_inc()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void warpgroup_reg_dec()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 template <bool LOOP, bool TRACK, bool LEAN, bool RECORD>
 __global__ void __launch_bounds__(kThreads, 1)
 k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
@@ -593,8 +623,11 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         bar_init(bar(B_X + 0), kRows);
         bar_init(bar(B_X + 1), kRows);
         bar_init(bar(B_L1), 1);
-        bar_init(bar(B_D3), 1);
+        bar_init(bar(B_D3 + 0), 1);
+        bar_init(bar(B_D3 + 1), 1);
         bar_init(bar(B_E), kRows);
+        bar_init(bar(B_R01), 2 * kPartThreads);
+        bar_init(bar(B_R3), kPartThreads);
         for (int b = 0; b < 2; b++)
             bar_init(bar(B_H1 + b), 4 * kPartThreads);
         for (int b = 0; b < 4; b++) {
@@ -641,38 +674,52 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
     if (A.step_device)
         step = *A.step_device;
 
-    if (warp == kMmaWarp) {
+    if (warp > kMmaWarp) {
+        warpgroup_reg_dec<24>(); /* the three warps that only came to make a warpgroup */
+    } else if (warp == kMmaWarp) {
         /* ================================================================ MMA issuer ============ */
+        warpgroup_reg_dec<24>();
         const uint32_t leader = elect_leader();
         bar_wait_warp(bar(B_W), 0, 4096u + B_W * 128u, 0);
         const uint64_t dX = smem_desc(s0 + SM_X), dB1 = smem_desc(s0 + SM_B1), dB2 = smem_desc(s0 + SM_B2),
                        dB3 = smem_desc(s0 + SM_B3);
+        /* layer 1 of sequence s2: L1 (128 x 256) = X (128 x 32, shared memory) . W1op, as two N = 128 halves
+         * (the two accumulator regions of a tile are not adjacent for odd tiles) */
+        auto layer1 = [&](int64_t s2) {
+            const uint32_t par = (uint32_t)s2 & 1u;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; half++)
+#pragma unroll
+                for (uint32_t ks = 0; ks < 2; ks++)
+                    mma_bf16_ss(leader, tmem + (half ? tm_b(par) : tm_a(par)),
+                                desc_at(dX, par * (kRows * 128u) + ks * 32u),
+                                desc_at(dB1, half * (128u * 128u) + ks * 32u), instr_desc(128), ks > 0);
+            mma_commit(leader, bar(B_L1));
+        };
+        bool l1_issued = false; /* layer 1 of the sequence about to start went out under the previous one */
         for (int64_t s = 0; s < S; s++) {
             const uint32_t par = (uint32_t)s & 1u, ph = (uint32_t)s & 1u;
             TRACE(s, 0);
-            bar_wait_warp(bar(B_X + par), (uint32_t)(s >> 1) & 1u, 4096u + B_X * 128u, s);
-            tc_fence_after();
-            TRACE(s, 1);
-            /* layer 1: L1 (128 x 256) = X (128 x 32, shared memory) . W1op.  R1 / R2 are free: the MMAs
-             * of the previous tile that read them were issued before these and execute before them, and
-             * this warp has seen the previous tile's layer-2 epilogue publish its last part */
-#pragma unroll
-            for (uint32_t ks = 0; ks < 2; ks++)
-                mma_bf16_ss(leader, tmem + TM_L1, desc_at(dX, par * (kRows * 128u) + ks * 32u),
-                            desc_at(dB1, ks * 32u), instr_desc(kHidden), ks > 0);
-            mma_commit(leader, bar(B_L1));
-            TRACE(s, 2);
+            if (!l1_issued) {
+                bar_wait_warp(bar(B_X + par), (uint32_t)(s >> 1) & 1u, 4096u + B_X * 128u, s);
+                tc_fence_after();
+                TRACE(s, 1);
+                /* its regions are free: the previous tile's MMAs that read them were issued before these and
+                 * execute before them, and this warp has seen that tile's layer-2 epilogue publish every part */
+                layer1(s);
+                TRACE(s, 2);
+            }
             /* layer 2, quarter q: D (128 x 64) = H1 . W2[:, 64q .. 64q+63] */
             auto layer2_kstep = [&](uint32_t q, uint32_t ks, bool accumulate) {
-                mma_bf16_ts(leader, tmem + tm_l2(q), tmem + TM_H1 + ks * 8u,
+                mma_bf16_ts(leader, tmem + tm_l2(par, q), tmem + tm_c(par) + ks * 8u,
                             desc_at(dB2, (ks >> 2) * (kHidden * 128u) + q * (64u * 128u) + (ks & 3u) * 32u),
                             instr_desc(64), accumulate);
             };
             /* Layer 2 trails the layer-1 epilogue, which publishes the activations in two halves of 128
-             * columns (= 8 K-steps each; K-steps may accumulate in any order).  The first half is everything R1
-             * held, so R1 may take quarters 2 and 3 at once: the first K-half of ALL four quarters runs on the
-             * tensor pipe while the second half of the tanh runs on the XU, and after the second publication
-             * quarter q is complete after q + 1 half-quarters instead of q + 1 whole ones. */
+             * columns (= 8 K-steps each; K-steps may accumulate in any order).  The first half is everything
+             * region A held, so A may take quarters 2 and 3 at once: the first K-half of ALL four quarters runs
+             * on the tensor pipe while the second half of the tanh runs on the XU, and after the second
+             * publication quarter q is complete after q + 1 half-quarters instead of q + 1 whole ones. */
 #pragma unroll
             for (uint32_t h = 0; h < 2; h++) {
                 bar_wait_warp(bar(B_H1 + h), ph, 4096u + B_H1 * 128u + (h << 4), s);
@@ -689,25 +736,52 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                     }
                 }
             }
-            /* layer 3: D3 (128 x 16, over the first columns of H1, which the MMAs above are the last to
-             * read) += H2[:, 64q .. 64q+63] . W3 (padded), trailing the layer-2 epilogue part by part */
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
+            /* Regions C (H1: every layer-2 MMA has been issued) and D (quarters 0 and 1, once the epilogue has
+             * them in registers) of this tile are regions A and B of the next.  In the open policy step the next
+             * operand has been waiting since the env rows read the previous logits, so its layer 1 goes out right
+             * here, under this tile's layer-2 epilogue, and the epilogue warps run from one tile into the next
+             * without waiting for the logits.  In the closed loop the next operand is the END of another tile's
+             * env tick -- the loop is bound by that chain, not by the pipes -- and waiting for it here would
+             * hold back this tile's logits: there layer 1 goes out at the top of the loop.  (Looking without
+             * waiting, mbarrier.test_wait, is no way out: ~300 cycles of this warp per look that fails.) */
+            l1_issued = false;
+            if (!LOOP && s + 1 < S) {
+                bar_wait_warp(bar(B_R01), ph, 4096u + B_R01 * 128u, s);
+                bar_wait_warp(bar(B_X + (par ^ 1u)), (uint32_t)((s + 1) >> 1) & 1u, 4096u + B_X * 128u + 16u, s + 1);
+                tc_fence_after();
+                TRACE(s + 1, 1);
+                layer1(s + 1);
+                TRACE(s + 1, 2);
+                l1_issued = true;
+            }
+            /* layer 3: D3 (128 x 16) += H2[:, 64q .. 64q+63] . W3 (padded), trailing the layer-2 epilogue part
+             * by part in the order the parts finish.  The logits go over the first columns of quarter 3's
+             * accumulator: the last place the next tile's activations reach. */
+            auto layer3 = [&](uint32_t q, bool accumulate) {
                 bar_wait_warp(bar(B_H2 + q), ph, 4096u + B_H2 * 128u + (q << 4), s);
                 tc_fence_after();
+                TRACE(s, 5 + q);
 #pragma unroll
                 for (uint32_t kk = 0; kk < 4; kk++) {
                     const uint32_t ks = 4u * q + kk;
-                    mma_bf16_ts(leader, tmem + TM_D3, tmem + TM_H2 + ks * 8u,
+                    mma_bf16_ts(leader, tmem + tm_d3(par), tmem + tm_b(par) + ks * 8u,
                                 desc_at(dB3, (ks >> 2) * (kOutPad * 128u) + (ks & 3u) * 32u),
-                                instr_desc(kOutPad), ks > 0);
+                                instr_desc(kOutPad), accumulate || kk > 0);
                 }
                 TRACE(s, 15 + q);
-            }
-            mma_commit(leader, bar(B_D3));
+            };
+            TRACE(s, 9);
+            bar_wait_warp(bar(B_R3), ph, 4096u + B_R3 * 128u, s);
+            TRACE(s, 10);
+            layer3(0, false);
+            layer3(2, true);
+            layer3(1, true);
+            layer3(3, true);
+            mma_commit(leader, bar(B_D3 + par));
         }
     } else if (warp >= kEnvWarps) {
         /* ================================================================ tanh epilogues ======== */
+        warpgroup_reg_inc<80>();
         const uint32_t quad = warp & 3u, part = (warp - kEnvWarps) >> 2; /* TMEM lanes 32 quad .., column part */
         const uint32_t lane_base = tmem + ((quad * 32u) << 16);
         bar_wait_warp(bar(B_W), 0, 8192u + B_W * 128u, 0);
@@ -716,32 +790,38 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             constexpr uint32_t kPoly = Q1_POLICY_POLY_PAIRS;
             uint32_t va[32], vb[32], p[16];
             /* ---- layer-1 epilogue (bias already in the MMA) -> tanh -> H1 ---- */
-            if (s >= 1) /* the first columns of R0 hold the previous tile's logits until the env rows have
-                           read them (they do so the moment the logits are complete) */
-                bar_wait_warp(bar(B_E), ph ^ 1u, 8192u + B_E * 128u, s);
             if (quad == 0) TRACE(s, 20 + 8 * part + 0);
             bar_wait_warp(bar(B_L1), ph, 8192u + B_L1 * 128u, s);
             tc_fence_after();
             if (quad == 0) TRACE(s, 20 + 8 * part + 1);
-            /* Half h: this part's 32 of the accumulator columns 128 h .. 128 h + 127 (R1, then R2).  A loop that
-             * is NOT unrolled: unrolled, ptxas interleaves the arithmetic of the two halves for latency and the
-             * first publication -- which the layer-2 MMAs are waiting for -- sinks to the end (seen in the SASS
-             * as soon as the halves contain dependent FFMA2 chains). */
+            /* Half h: this part's 32 of the accumulator columns 128 h .. 128 h + 127 (region A, then B).  A loop
+             * that is NOT unrolled: unrolled, ptxas interleaves the arithmetic of the two halves for latency and
+             * the first publication -- which the layer-2 MMAs are waiting for -- sinks to the end (seen in the
+             * SASS as soon as the halves contain dependent FFMA2 chains).
+             * H1 goes where the PREVIOUS tile kept its layer-2 quarters 2 (first half) and 3 (second half, with
+             * its logits over the first columns): the store waits until those have been read -- by the
+             * epilogue part that took quarter 2, by the env rows -- which is long ago unless a role fell behind. */
 #pragma unroll 1
             for (uint32_t h = 0; h < 2; h++) {
-                tmem_ld_issue<32>(lane_base + TM_L1 + 128u * h + 32u * part, va);
+                tmem_ld_issue<32>(lane_base + (h ? tm_b(ph) : tm_a(ph)) + 32u * part, va);
                 tmem_ld_wait<32>(va);
 #pragma unroll
                 for (uint32_t e = 0; e < 16; e++)
                     p[e] = tanh2_pair<kPoly>(e, __uint_as_float(va[2 * e]), __uint_as_float(va[2 * e + 1]));
-                tmem_st<16>(lane_base + TM_H1 + 64u * h + 16u * part, p);
+                if (s >= 1) {
+                    if (h == 0)
+                        bar_wait_warp(bar(B_H2 + 2), ph ^ 1u, 8192u + B_H2 * 128u + (2u << 4) + 1u, s);
+                    else
+                        bar_wait_warp(bar(B_E), ph ^ 1u, 8192u + B_E * 128u, s);
+                }
+                tmem_st<16>(lane_base + tm_c(ph) + 64u * h + 16u * part, p);
                 tmem_st_wait();
                 tc_fence_before();
                 bar_arrive(bar(B_H1 + h));
                 if (quad == 0) TRACE(s, 20 + 8 * part + 2 + h);
             }
-            /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (R2: this lane is done with the layer-1
-             * columns that were there).  Parts 0-2 take quarters 0-2 as they complete; quarter 3, which
+            /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (region B: this lane is done with the
+             * layer-1 columns that were there).  Parts 0-2 take quarters 0-2 as they complete; quarter 3, which
              * completes last, is shared: part 3 takes its first 32 columns, part 0 -- long done with quarter 0
              * by then -- its second 32, so the tile does not end on one warp per scheduler working alone ---- */
             auto half_quarter = [&](uint32_t q, uint32_t hh, const uint32_t *v) {  /* 32 columns -> 16 of H2 */
@@ -749,17 +829,21 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
 #pragma unroll
                 for (uint32_t e = 0; e < 16; e++)
                     p[e] = tanh2_pair<kPoly>(e, __uint_as_float(v[2 * e]) + b[2u * e], __uint_as_float(v[2 * e + 1]) + b[2u * e + 1u]);
-                tmem_st<16>(lane_base + TM_H2 + 32u * q + 16u * hh, p);
+                tmem_st<16>(lane_base + tm_b(ph) + 32u * q + 16u * hh, p);
             };
             if (part < 3) {
                 bar_wait_warp(bar(B_L2 + part), ph, 8192u + B_L2 * 128u + (part << 4), s);
                 tc_fence_after();
                 if (quad == 0) TRACE(s, 20 + 8 * part + 4);
-                tmem_ld_issue<32>(lane_base + tm_l2(part), va);
+                tmem_ld_issue<32>(lane_base + tm_l2(ph, part), va);
                 tmem_ld_wait<32>(va);
-                tmem_ld_issue<32>(lane_base + tm_l2(part) + 32u, vb);
+                tmem_ld_issue<32>(lane_base + tm_l2(ph, part) + 32u, vb);
                 half_quarter(part, 0, va);
                 tmem_ld_wait<32>(vb);
+                if (part < 2) { /* the whole quarter is in registers */
+                    tc_fence_before();
+                    bar_arrive(bar(B_R01));
+                }
                 half_quarter(part, 1, vb);
                 tmem_st_wait();
                 tc_fence_before();
@@ -771,8 +855,12 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 bar_wait_warp(bar(B_L2 + 3), ph, 8192u + B_L2 * 128u + (3u << 4), s);
                 tc_fence_after();
                 if (quad == 0 && part == 3) TRACE(s, 20 + 8 * part + 4);
-                tmem_ld_issue<32>(lane_base + tm_l2(3) + 32u * hh, va);
+                tmem_ld_issue<32>(lane_base + tm_l2(ph, 3) + 32u * hh, va);
                 tmem_ld_wait<32>(va);
+                if (part == 3) {
+                    tc_fence_before();
+                    bar_arrive(bar(B_R3));
+                }
                 half_quarter(3, hh, va);
                 tmem_st_wait();
                 tc_fence_before();
@@ -782,11 +870,20 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         }
     } else {
         /* ================================================================ env rows =============== */
-        const uint32_t row = tid; /* warp w owns TMEM lanes 32w .. 32w+31 = rows 32w .. 32w+31 */
-        const uint32_t lane_base = tmem + ((warp * 32u) << 16);
+        warpgroup_reg_inc<80>();
+        /* Two groups of four warps; warp w of a group owns TMEM lanes 32 (w & 3) .. + 31 = those rows of the tile.
+         * The sample + tick of a tile is one long dependent instruction stream per warp (~7000 cycles in the
+         * closed loop, more than the policy phase of a tile), so with ONE group the env rows, not the tensor
+         * pipe or the XU, set the pace.  With an even number of tiles per CTA (and in the open policy step) the
+         * groups take alternate sequences -- disjoint tiles, so no state is shared between them; otherwise
+         * group 0 takes every sequence as before and group 1 leaves. */
+        const uint32_t group = warp >> 2, row = tid & 127u;
+        const bool two_groups = !LOOP || (k & 1) == 0;
+        const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);
         const float *bias3 = reinterpret_cast<const float *>(smem + SM_BIAS3);
         const int width = 2 * A.num_keys + 2;
         const int64_t stride = (LOOP && k < 2) ? 1 : 2; /* how far ahead the layer-1 operand is prepared */
+        const int64_t s_first = two_groups ? group : (group == 0 ? 0 : S), s_step = two_groups ? 2 : 1;
 
         /* the layer-1 operand of sequence s2 -> X[s2 & 1] */
         auto prepare = [&](int64_t s2) {
@@ -820,27 +917,34 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             bar_arrive(bar(B_X + ((uint32_t)s2 & 1u)));
         };
         bar_wait_warp(bar(B_W), 0, 12288u + B_W * 128u + 0u, 0);
-        for (int64_t s2 = 0; s2 < stride && s2 < S; s2++)
-            prepare(s2);
+        if (two_groups) {
+            if ((int64_t)group < S)
+                prepare(group);
+        } else {
+            for (int64_t s2 = s_first; s2 < stride && s2 < S; s2++)
+                prepare(s2);
+        }
 
         float rsum[kMaxTiles];
 #pragma unroll
         for (int j = 0; j < kMaxTiles; j++)
             rsum[j] = 0.0f;
-        for (int64_t s = 0; s < S; s++) {
-            if (warp == 0) TRACE(s, 52);
-            bar_wait_warp(bar(B_D3), (uint32_t)s & 1u, 12288u + B_D3 * 128u, s);
+        for (int64_t s = s_first; s < S; s += s_step) {
+            if ((warp & 3u) == 0) TRACE(s, 52);
+            bar_wait_warp(bar(B_D3 + ((uint32_t)s & 1u)), (uint32_t)(s >> 1) & 1u, 12288u + B_D3 * 128u, s);
             tc_fence_after();
-            if (warp == 0) TRACE(s, 53);
+            if ((warp & 3u) == 0) TRACE(s, 53);
             uint32_t v[16];
-            tmem_ld16(lane_base + TM_D3, v);
+            tmem_ld16(lane_base + tm_d3((uint32_t)s & 1u), v);
             tc_fence_before();
             bar_arrive(bar(B_E));
-            if (warp == 0) TRACE(s, 54);
+            if ((warp & 3u) == 0) TRACE(s, 54);
             float lg[10];
 #pragma unroll
             for (int q = 0; q < 10; q++)
                 lg[q] = __uint_as_float(v[q]) + bias3[q];
+            if (!LOOP && s + stride < S) /* nothing of it depends on this tile's action: the MMA warp wants it early */
+                prepare(s + stride);
             const int64_t tile = tile_of(s);
             const int64_t i = tile * kRows + row;
             const bool active = i < (LOOP ? P.n : A.n);
@@ -906,15 +1010,15 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 }
                 slot_store(slot, row, e);
             }
-            if (warp == 0) TRACE(s, 55);
-            if (s + stride < S)
+            if ((warp & 3u) == 0) TRACE(s, 55);
+            if (LOOP && s + stride < S)
                 prepare(s + stride); /* reads only this thread's own row of the slot */
-            if (warp == 0) TRACE(s, 56);
+            if ((warp & 3u) == 0) TRACE(s, 56);
         }
         if (LOOP) { /* results of the launch: final observation and per-env reward sum */
             for (int j = 0; j < k; j++) {
                 const int64_t i = tile_of(j) * kRows + row;
-                if (i >= P.n)
+                if (i >= P.n || (two_groups ? ((uint32_t)j & 1u) != group : group != 0))
                     continue;
                 if (A.final_obs) {
                     Env e;

@@ -32,13 +32,18 @@ assert lib.q1_actor_trace(ctypes.c_void_p(t.ctypes.data)) == 0
 names = {0: "mma:top", 1: "mma:X", 2: "mma:L1 issued", 11: "mma:L2q0 issued", 12: "mma:L2q1 issued", 13: "mma:L2q2 issued", 14: "mma:L2q3 issued",
          15: "mma:M3q0", 16: "mma:M3q1", 17: "mma:M3q2", 18: "mma:M3q3", 52: "env:top", 53: "env:D3", 54: "env:E arrived",
          55: "env:acted", 56: "env:prepared"}
+for q in range(4):
+    names[5 + q] = f"mma:H2 quarter {q} seen"
+names[9], names[10] = "mma:quarters 0, 1 read (or last tile)", "mma:quarter 3 read"
 for i in range(2):
     names[3 + i] = f"mma:H1 half {i} seen"
 for p in range(4):
     for k, nm in enumerate(("top", "L1 seen", "H1 step0", "H1 step1", "L2 seen", "H2 done")):
         names[20 + 8 * p + k] = f"epi{p}:{nm}"
 t0 = t[2, 0]
-for s in range(2, 4):
+first = 2 if mode == 'act' else 6
+t0 = t[first, 0]
+for s in range(first, first + 2):
     ev = sorted((int(t[s, e]), e) for e in range(64) if t[s, e] and names.get(e))
     print(f"--- sequence {s} (cycles since sequence 2 top)")
     for c, e in ev:
