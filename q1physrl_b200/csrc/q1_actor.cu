@@ -32,7 +32,6 @@
  *   layer 2   four N = 64 quarters.  The first K-half of all four is issued when the first half of the
  *             layer-1 activations is published and runs under the second half of that epilogue; the second
  *             K-halves follow quarter by quarter, and epilogue part q starts on quarter q as it completes
- *             (quarter 3 is shared between parts 3 and 0)
  *   layer 3   K-steps trail the layer-2 epilogue part by part; the logits land over quarter 3's first
  *             accumulator columns
  *   next tile (open policy step) its layer 1 is issued as soon as parts 0 and 1 have their accumulators in
@@ -289,6 +288,7 @@ __device__ __forceinline__ __attribute__((unused)) uint32_t pack_bf16(float lo, 
 #ifndef Q1_POLICY_POLY_PAIRS
 #define Q1_POLICY_POLY_PAIRS 2
 #endif
+
 /* tanh(x) ~ x P(x^2) on |x| <= 3.5, x clamped to that range first (beyond it tanh rounds to +-1 in bf16, and
  * so does this).  tools/make_tanh_poly.py: degree 17, minimax relative error 5.4e-4 (5.8e-4 evaluated in
  * float32) -- the size of MUFU.TANH's own 2^-11 and a quarter of the bf16 rounding of the stored activation;
@@ -631,7 +631,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
         for (int b = 0; b < 2; b++)
             bar_init(bar(B_H1 + b), 4 * kPartThreads);
         for (int b = 0; b < 4; b++) {
-            bar_init(bar(B_H2 + b), b == 3 ? 2 * kPartThreads : kPartThreads); /* quarter 3 is shared by two parts */
+            bar_init(bar(B_H2 + b), kPartThreads);
             bar_init(bar(B_L2 + b), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -755,7 +755,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 l1_issued = true;
             }
             /* layer 3: D3 (128 x 16) += H2[:, 64q .. 64q+63] . W3 (padded), trailing the layer-2 epilogue part
-             * by part in the order the parts finish.  The logits go over the first columns of quarter 3's
+             * by part.  The logits go over the first columns of quarter 3's
              * accumulator: the last place the next tile's activations reach. */
             auto layer3 = [&](uint32_t q, bool accumulate) {
                 bar_wait_warp(bar(B_H2 + q), ph, 4096u + B_H2 * 128u + (q << 4), s);
@@ -774,8 +774,8 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             bar_wait_warp(bar(B_R3), ph, 4096u + B_R3 * 128u, s);
             TRACE(s, 10);
             layer3(0, false);
-            layer3(2, true);
             layer3(1, true);
+            layer3(2, true);
             layer3(3, true);
             mma_commit(leader, bar(B_D3 + par));
         }
@@ -821,9 +821,9 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 if (quad == 0) TRACE(s, 20 + 8 * part + 2 + h);
             }
             /* ---- layer-2 epilogue: accumulator + bias -> tanh -> H2 (region B: this lane is done with the
-             * layer-1 columns that were there).  Parts 0-2 take quarters 0-2 as they complete; quarter 3, which
-             * completes last, is shared: part 3 takes its first 32 columns, part 0 -- long done with quarter 0
-             * by then -- its second 32, so the tile does not end on one warp per scheduler working alone ---- */
+             * layer-1 columns that were there).  Part q takes quarter q as it completes.  (Sharing the last
+             * quarter between two parts shortened the tail of a tile while tiles did not overlap; now that the
+             * epilogue warps run on into the next tile, equal work per part is worth more: measured.) ---- */
             auto half_quarter = [&](uint32_t q, uint32_t hh, const uint32_t *v) {  /* 32 columns -> 16 of H2 */
                 const float *b = reinterpret_cast<const float *>(smem + SM_BIAS2) + 64u * q + 32u * hh;
 #pragma unroll
@@ -831,12 +831,16 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                     p[e] = tanh2_pair<kPoly>(e, __uint_as_float(v[2 * e]) + b[2u * e], __uint_as_float(v[2 * e + 1]) + b[2u * e + 1u]);
                 tmem_st<16>(lane_base + tm_b(ph) + 32u * q + 16u * hh, p);
             };
-            if (part < 3) {
+            {
                 bar_wait_warp(bar(B_L2 + part), ph, 8192u + B_L2 * 128u + (part << 4), s);
                 tc_fence_after();
                 if (quad == 0) TRACE(s, 20 + 8 * part + 4);
                 tmem_ld_issue<32>(lane_base + tm_l2(ph, part), va);
                 tmem_ld_wait<32>(va);
+                if (part == 3) { /* the columns the logits will overwrite */
+                    tc_fence_before();
+                    bar_arrive(bar(B_R3));
+                }
                 tmem_ld_issue<32>(lane_base + tm_l2(ph, part) + 32u, vb);
                 half_quarter(part, 0, va);
                 tmem_ld_wait<32>(vb);
@@ -849,23 +853,6 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 tc_fence_before();
                 bar_arrive(bar(B_H2 + part));
                 if (quad == 0) TRACE(s, 20 + 8 * part + 5);
-            }
-            if (part == 3 || part == 0) {
-                const uint32_t hh = part == 3 ? 0u : 1u;
-                bar_wait_warp(bar(B_L2 + 3), ph, 8192u + B_L2 * 128u + (3u << 4), s);
-                tc_fence_after();
-                if (quad == 0 && part == 3) TRACE(s, 20 + 8 * part + 4);
-                tmem_ld_issue<32>(lane_base + tm_l2(ph, 3) + 32u * hh, va);
-                tmem_ld_wait<32>(va);
-                if (part == 3) {
-                    tc_fence_before();
-                    bar_arrive(bar(B_R3));
-                }
-                half_quarter(3, hh, va);
-                tmem_st_wait();
-                tc_fence_before();
-                bar_arrive(bar(B_H2 + 3));
-                if (quad == 0 && part == 3) TRACE(s, 20 + 8 * part + 5);
             }
         }
     } else {
