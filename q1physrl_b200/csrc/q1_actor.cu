@@ -918,6 +918,10 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             rsum[j] = 0.0f;
         for (int64_t s = s_first; s < S; s += s_step) {
             if ((warp & 3u) == 0) TRACE(s, 52);
+            /* the noise of this row's action needs no logits: drawn while the policy runs */
+            const ActionNoise noise = draw_action_noise(
+                A.deterministic != 0, A.seed, LOOP ? step + (uint64_t)(s / k) : step,
+                (LOOP ? P.env_index_base : A.env_index_base) + (uint64_t)(tile_of(s) * kRows + row));
             bar_wait_warp(bar(B_D3 + ((uint32_t)s & 1u)), (uint32_t)(s >> 1) & 1u, 12288u + B_D3 * 128u, s);
             tc_fence_after();
             if ((warp & 3u) == 0) TRACE(s, 53);
@@ -938,8 +942,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             if (!LOOP) {
                 if (active) {
                     float m;
-                    const uint32_t kb = sample_action_row(lg, A.num_keys, A.low, A.high, A.deterministic != 0,
-                                                          A.seed, step, A.env_index_base + (uint64_t)i, &m);
+                    const uint32_t kb = apply_action_noise(lg, A.num_keys, A.low, A.high, A.deterministic != 0, noise, &m);
                     for (int q = 0; q < A.num_keys; q++)
                         A.keys[i * A.num_keys + q] = (kb >> q) & 1u;
                     A.mouse[i] = m;
@@ -954,8 +957,7 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 unsigned char *slot = smem + SM_STATE + slot_no * kSlotBytes;
                 const uint64_t gidx = P.env_index_base + (uint64_t)i;
                 float m;
-                const uint32_t keybits = sample_action_row(lg, A.num_keys, A.low, A.high, A.deterministic != 0,
-                                                           A.seed, step + (uint64_t)tick_no, gidx, &m);
+                const uint32_t keybits = apply_action_noise(lg, A.num_keys, A.low, A.high, A.deterministic != 0, noise, &m);
                 Env e;
                 slot_load(slot, row, e);
                 float r;
