@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "q1physrl_b200", "libq1phys.so")
 WANT = {
     "k_step_tma": ("k_step_tmaILb0ELb1ELb1ELi6E", ("UBLKCP", "SYNCS", "ACQBULK", "UTMA", "DADD", "DFMA", "DMUL", "MUFU.RCP64H")),
-    "k_actor": ("k_actorILb1ELb1ELb1ELb0E", ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "SYNCS", "MUFU.TANH", "ELECT")),
+    "k_actor": ("k_actorILb1ELb1ELb1ELb0E", ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "SYNCS", "MUFU.TANH", "ELECT", "FFMA2", "FMUL2", "USETMAXREG")),
 }
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 blocks = re.split(r"\n\s*Function : ", out)
