@@ -349,3 +349,31 @@ def test_shard_ranges_partition_the_population():
         assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
     with pytest.raises(ValueError):
         sharding.shard_range(10, 3, 3)
+
+
+def test_tanh_polynomial_in_the_policy_kernel_is_the_generated_one_and_as_accurate_as_stated():
+    """csrc/q1_actor.cu evaluates tanh for a share of the hidden units as x P(x^2) on the FMA pipe.  The
+    coefficients in the source are the ones tools/make_tanh_poly.py derives (minimax, scipy linprog), and
+    evaluated in float32 they are within 6e-4 relative of tanh on the clamp range, round to +-1 in bfloat16
+    beyond it like tanh itself, and differ from bf16(tanh x) by at most one bf16 step anywhere."""
+    import re
+    import importlib.util
+    src = open(os.path.join(ROOT, "q1physrl_b200", "csrc", "q1_actor.cu")).read()
+    body = src[src.index("#define Q1_TANH_POLY(X)"):]
+    body = body[:body.index("__device__")]
+    coef = np.array([float(c) for c in re.findall(r"X\((-?[0-9.e+-]+)f\)", body)], np.float32)
+    clamp = float(re.search(r"constexpr float kTanhClamp = ([0-9.]+)f;", src).group(1))
+    spec = importlib.util.spec_from_file_location("make_tanh_poly", os.path.join(ROOT, "tools", "make_tanh_poly.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert clamp == gen.C and len(coef) == gen.K + 1
+    fitted, err = gen.fit()
+    assert err < 5.5e-4 and np.array_equal(fitted.astype(np.float32), coef)
+    x = np.concatenate([np.linspace(-8, 8, 400_001), np.linspace(-0.01, 0.01, 20_001)])
+    got, ref = gen.evaluate(coef.astype(np.float64), x), np.tanh(x)
+    inside = np.abs(x) <= clamp
+    assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30))[inside].max() < 6e-4
+    gb, rb = gen.bf16(got), gen.bf16(ref.astype(np.float32))
+    assert np.array_equal(gb[~inside], np.sign(x[~inside]).astype(np.float32))
+    steps = np.abs(gb.view(np.int32).astype(np.int64) - rb.view(np.int32).astype(np.int64)) >> 16
+    assert steps.max() <= 1 and (steps == 0).mean() > 0.95
