@@ -280,11 +280,11 @@ __device__ __forceinline__ __attribute__((unused)) uint32_t pack_bf16(float lo, 
 #define Q1_POLICY_TANH 0
 #endif
 /* Measured on one box, per 2^20 envs of k_actor<ACT> / per tick of the closed loop at 32 768 envs:
- *   pairs    0      2      3      4      5
- *   ACT    189.6  180.7  179.9  182.3  188.6 us
- *   LOOP    9.28   9.40   9.45   9.54   9.78 us     (there the env rows' tick keeps the FMA / FP64 pipes busy
- * and the chain env tick -> policy -> env tick, not a pipe, sets the pace).  ONE value for both, because the
- * closed loop is tested bit-identical to per-tick q1_policy_act + q1_step: 2. */
+ *   pairs    0      2      3      4
+ *   ACT    195.4  182.3  184.2  182.3 us
+ *   LOOP    8.60   8.52   8.57   8.70 us     (there the chain env tick -> policy -> env tick of a tile, not
+ * a pipe, sets the pace, and the env rows want the FMA pipe too).  ONE value for both, because the closed loop
+ * is tested bit-identical to per-tick q1_policy_act + q1_step: 2. */
 #ifndef Q1_POLICY_POLY_PAIRS
 #define Q1_POLICY_POLY_PAIRS 2
 #endif
