@@ -554,6 +554,41 @@ def run_cuda_arm(args, rank, world, local_rank):
     red = sharding.reduce_metrics(tracked.metrics(), device=dev)
     zs_mean, zs_episodes = red["zero_start_total_reward_mean"], red["zero_start_episodes"]
 
+    # ---- the policy kernel alone (k_actor, one launch per call): forward + sampling for 2^20 observations,
+    # against the measured bf16 tensor peak (the MMAs it issues incl. the padding of layers 1 and 3)
+    policy_step = None
+    if os.path.exists(policy_path) and rank == 0:
+        obs_p = torch.rand((NUM_ENVS, 6), device=dev) * 2
+        out_p = (torch.empty((NUM_ENVS, pol.num_keys), dtype=torch.uint8, device=dev),
+                 torch.empty(NUM_ENVS, device=dev))
+        for _ in range(5):
+            pol.act(obs_p, out=out_p)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        p0.record()
+        for _ in range(reps):
+            pol.act(obs_p, out=out_p)
+        p1.record()
+        torch.cuda.synchronize(dev)
+        us = p0.elapsed_time(p1) / reps * 1e3
+        issued = 2 * (32 + 256 + 16) * 256           # flop per env the tensor cores execute (K = 32 / 256 / 256)
+        useful = 2 * (6 * 256 + 256 * 256 + 256 * 10)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sustained = peaks.get("bf16_tflops_sustained")
+        policy_step = {"us_per_call": us, "envs": NUM_ENVS, "kernel": "k_actor<ACT>: tcgen05 MLP 6-256-256-10 + sampling",
+                       "roofline": {"bound": "tensor", "achieved": NUM_ENVS * issued / us / 1e6,
+                                    "peak": sustained, "unit": "TFLOP/s",
+                                    "frac": (NUM_ENVS * issued / us / 1e6 / sustained) if sustained else None,
+                                    "useful_tflops": NUM_ENVS * useful / us / 1e6,
+                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if sustained else "none",
+                                    "note": "the tanh epilogues (XU), not the MMAs, bound this kernel: DESIGN.md 8.1"}}
+        del obs_p, out_p
+    barrier()
+
     # ---- BASELINE config 4: 2^20 envs sharded 131072 per GPU, scripted strafe-jump policy, 10k ticks
     # in the multi-tick in-register rollout kernel (no per-tick HBM traffic)
     n4, ticks4 = 1 << 17, 10000
@@ -610,6 +645,8 @@ def run_cuda_arm(args, rank, world, local_rank):
                                              "policy": policy_desc, "env_steps_per_s": rate5,
                                              "collective": "all_reduce(sum) of (sum, count)" if world > 1 else "none (1 GPU)"},
         }
+        if policy_step is not None:
+            line["policy_step"] = policy_step
         if strong_headline and strong is not None:
             line.update({"value": strong["value"], "ms_per_step": strong["us_per_tick"] * 1e-3,
                          "scaling": "strong", "steps": strong["steps"], "roofline": dict(
