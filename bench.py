@@ -311,14 +311,24 @@ def time_ring(ring, steps, warmup, barrier, world, dist, dev, clocks=None, min_s
     import torch
     for i in range(warmup):
         ring.step(i)
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if os.environ.get("Q1_BENCH_SLEEP_US"):   # diagnostic: an idle device before the timed region
+        time.sleep(float(os.environ["Q1_BENCH_SLEEP_US"]) * 1e-6)
     t_wall = time.perf_counter()
     ev0.record(ring.stream)
+    marks = []
     for i in range(steps):
         ring.step(warmup + i)
+        if os.environ.get("Q1_BENCH_STEP_EVENTS"):      # debugging aid: where inside a short timed region the time goes
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record(ring.stream)
     ev1.record(ring.stream)
+    if marks:
+        torch.cuda.synchronize(dev)
+        ends = [ev0.elapsed_time(m) * 1e3 for m in marks]
+        print(f"rank {os.environ.get('RANK', 0)}: first step ends {ends[0]:.1f} us after the start event; step "
+              f"durations after it: {[round(b - a, 1) for a, b in zip(ends, ends[1:])][:24]}", file=sys.stderr, flush=True)
     if clocks is not None:
         i = warmup + steps
         while time.perf_counter() - t_wall < min_sample_s:
