@@ -4,7 +4,7 @@
  *
  *   k_actor<LOOP = false>   obs -> tanh 256 -> tanh 256 -> logits -> Q1PhysActionDist sample -> the action
  *                           arrays q1_step consumes (q1_policy_act), tile after tile of 128 envs;
- *   k_actor<LOOP = true>    the closed loop: every CTA keeps the state of up to 8 tiles of 128 envs in
+ *   k_actor<LOOP = true>    the closed loop: every CTA keeps the state of up to three tiles of 128 envs in
  *                           shared memory for T ticks and runs policy -> sample -> tick<>() -> observe ->
  *                           policy ... with no launch and no HBM traffic per tick (q1_policy_rollout);
  *                           optionally writes the per-tick record of analyse.eval_sim.
@@ -93,7 +93,7 @@ constexpr uint32_t kImageBytes = SM_WEIGHTS_END - SM_B2;        /* what the host
 static_assert(kImageBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 enum : uint32_t { /* mbarriers, 8 bytes each.  A waiter tests a phase PARITY, so no barrier may complete two
                      phases between two waits of the same waiter: every barrier here completes once per tile
-                     (B_X: once per two) and the protocol keeps every waiter within one tile of every signaller. */
+                     (B_X, B_D3: once per two) and the protocol keeps every waiter within one tile of every signaller. */
     B_W = 0,        /* weights have landed in shared memory */
     B_X = 1,        /* [2] layer-1 operand of the tile written (env rows -> MMA) */
     B_L1 = 3,       /* layer-1 accumulator complete (MMA -> epilogue) */
