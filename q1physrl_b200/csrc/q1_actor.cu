@@ -958,6 +958,10 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 const uint64_t gidx = P.env_index_base + (uint64_t)i;
                 float m;
                 const uint32_t keybits = apply_action_noise(lg, A.num_keys, A.low, A.high, A.deterministic != 0, noise, &m);
+#if Q1_ACTOR_TRACE == 1 /* the stamp is only a stamp if the value exists by then */
+                if (__float_as_uint(m) == 0x7fc12345u && keybits == 77u) TRACE(s, 59);
+#endif
+                if ((warp & 3u) == 0) TRACE(s, 57);
                 Env e;
                 slot_load(slot, row, e);
                 float r;
@@ -975,6 +979,10 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
                 } else {
                     tick<false, LEAN, false>(P, e, keybits, (double)m, r, d);
                 }
+#if Q1_ACTOR_TRACE == 1
+                if (__float_as_uint(r) == 0x7fc12345u && d) TRACE(s, 59);
+#endif
+                if ((warp & 3u) == 0) TRACE(s, 58);
 #pragma unroll
                 for (int j = 0; j < kMaxTiles; j++)
                     if (j == slot_no)

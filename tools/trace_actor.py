@@ -31,7 +31,7 @@ t = np.zeros((16, 64), np.int64)
 assert lib.q1_actor_trace(ctypes.c_void_p(t.ctypes.data)) == 0
 names = {0: "mma:top", 1: "mma:X", 2: "mma:L1 issued", 11: "mma:L2q0 issued", 12: "mma:L2q1 issued", 13: "mma:L2q2 issued", 14: "mma:L2q3 issued",
          15: "mma:M3q0", 16: "mma:M3q1", 17: "mma:M3q2", 18: "mma:M3q3", 52: "env:top", 53: "env:D3", 54: "env:E arrived",
-         55: "env:acted", 56: "env:prepared"}
+         55: "env:acted", 56: "env:prepared", 57: "env:sampled", 58: "env:ticked"}
 for q in range(4):
     names[5 + q] = f"mma:H2 quarter {q} seen"
 names[9], names[10] = "mma:quarters 0, 1 read (or last tile)", "mma:quarter 3 read"
