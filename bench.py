@@ -309,9 +309,11 @@ def time_ring(ring, steps, warmup, barrier, world, dist, dev, clocks=None, min_s
     stream, max over ranks.  -> elapsed ms.  With `clocks`, stepping continues untimed after the timed
     region until the sampler has seen `min_sample_s` of this load (a 20-step region is 0.5 ms long)."""
     import torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()   # the ranks start their warm-up together, so that none of them sits idle at the next barrier
+                # waiting for the others: the first steps behind an idle device run slower (DESIGN.md section 7)
     for i in range(warmup):
         ring.step(i)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if os.environ.get("Q1_BENCH_SLEEP_US"):   # diagnostic: an idle device before the timed region (DESIGN.md section 7)
         time.sleep(float(os.environ["Q1_BENCH_SLEEP_US"]) * 1e-6)
