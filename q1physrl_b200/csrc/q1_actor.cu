@@ -797,7 +797,10 @@ k_actor(const __grid_constant__ Params P, const __grid_constant__ ActorArgs A)
             /* Half h: this part's 32 of the accumulator columns 128 h .. 128 h + 127 (region A, then B).  A loop
              * that is NOT unrolled: unrolled, ptxas interleaves the arithmetic of the two halves for latency and
              * the first publication -- which the layer-2 MMAs are waiting for -- sinks to the end (seen in the
-             * SASS as soon as the halves contain dependent FFMA2 chains).
+             * SASS as soon as the halves contain dependent FFMA2 chains).  (Written out instead, with the second
+             * half's tcgen05.ld in flight under the first half's arithmetic and its wait::ld placed after the
+             * first publication, the order holds too, but ptxas sinks that load next to its wait and the
+             * larger live set costs more than the latency it could hide: 190.5 vs 179.3 us, measured.)
              * H1 goes where the PREVIOUS tile kept its layer-2 quarters 2 (first half) and 3 (second half, with
              * its logits over the first columns): the store waits until those have been read -- by the
              * epilogue part that took quarter 2, by the env rows -- which is long ago unless a role fell behind. */
